@@ -1,0 +1,59 @@
+"""Philox4x32-10 counter-based stream of the product's *generated-RNG* mode, restated
+in numpy -- TEST INFRASTRUCTURE ONLY (checker for `podsdf_df_random_slabs_*`).
+
+The reference draws from the unseeded global MT19937 (DF:1344, 1361-1366, 1460-1467), so
+there is no reference-defined stream to match; the product defines its own, and this is
+its CPU restatement (Salmon et al. 2011, Random123 constants).
+
+Layout (shared with pods-digital-filter_b200/csrc/philox.cuh):
+  key     = (seed & 0xffffffff, seed >> 32)
+  counter = (idx & 0xffffffff, idx >> 32, (s >> 1) & 0xffffffff, comp + 4*((s >> 1) >> 32))
+            idx = p*Kp + q in the padded plane (Jp x Kp), s = global slab index, comp in 0..2
+  output words r0..r3:  slab s even -> (r0, r1),  s odd -> (r2, r3)
+  u = ((a >> 5) * 2^26 + (b >> 6)) / 2^53          (numpy's 53-bit double, random_sample)
+  x = -sqrt(3) + (2 sqrt(3)) * u                   (np.random.uniform(low, high): low + (high-low)*u)
+"""
+import numpy as np
+
+M0 = np.uint64(0xD2511F53)
+M1 = np.uint64(0xCD9E8D57)
+W0 = 0x9E3779B9
+W1 = 0xBB67AE85
+MASK = np.uint64(0xFFFFFFFF)
+SQRT3 = np.sqrt(3.0)
+
+
+def philox4x32_10(c0, c1, c2, c3, k0, k1):
+    """Vectorised over uint64 arrays holding 32-bit values.  Returns r0..r3."""
+    c0, c1, c2, c3 = (np.asarray(c, dtype=np.uint64) for c in (c0, c1, c2, c3))
+    k0 = int(k0) & 0xFFFFFFFF
+    k1 = int(k1) & 0xFFFFFFFF
+    for _ in range(10):
+        p0 = M0 * c0
+        p1 = M1 * c2
+        hi0, lo0 = p0 >> np.uint64(32), p0 & MASK
+        hi1, lo1 = p1 >> np.uint64(32), p1 & MASK
+        c0, c1, c2, c3 = (hi1 ^ c1 ^ np.uint64(k0)), lo1, (hi0 ^ c3 ^ np.uint64(k1)), lo0
+        k0 = (k0 + W0) & 0xFFFFFFFF
+        k1 = (k1 + W1) & 0xFFFFFFFF
+    return c0, c1, c2, c3
+
+
+def slabs(seed, s0, n, Jp, Kp):
+    """Random slabs [s0, s0+n) of all three components: (n, 3, Jp, Kp) float64 in U(-sqrt3, sqrt3)."""
+    idx = np.arange(Jp * Kp, dtype=np.uint64)
+    out = np.empty((n, 3, Jp, Kp))
+    k0, k1 = seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF
+    rng = SQRT3 - (-SQRT3)
+    for i in range(n):
+        s = s0 + i
+        sp = s >> 1
+        for comp in range(3):
+            r = philox4x32_10(idx & MASK, idx >> np.uint64(32),
+                              np.full_like(idx, sp & 0xFFFFFFFF),
+                              np.full_like(idx, comp + 4 * (sp >> 32)), k0, k1)
+            a, b = (r[0], r[1]) if (s & 1) == 0 else (r[2], r[3])
+            u = ((a >> np.uint64(5)).astype(np.float64) * 67108864.0
+                 + (b >> np.uint64(6)).astype(np.float64)) / 9007199254740992.0
+            out[i, comp] = (-SQRT3 + rng * u).reshape(Jp, Kp)
+    return out

@@ -1,0 +1,42 @@
+"""Replay of the reference CLI's parameter derivation (DF:1244-1354) for the golden `main_*`
+cases, shared by the oracle tests (CPU) and the product parity tests (GPU).  Test helper only."""
+import numpy as np
+
+from oracle import df_oracle as dfo
+
+DEFAULTS = dict(n=20, l=3.0, f=2.0, k=11, j=10, t=0.0, m=20, e=0.9, r=0.1, nx=1.0, ny=0.0, nz=0.0,
+                U0=1.0, u_dash=0.02, ring=0.5, p="hyperbolic-tangent")
+
+
+def parse(argv):
+    o = dict(DEFAULTS)
+    argv = [str(a) for a in argv]
+    i = 0
+    while i < len(argv):
+        key = argv[i].lstrip("-")
+        o[key] = argv[i + 1]
+        i += 2
+    for k in ("n", "k", "j", "m"):
+        o[k] = int(o[k])
+    for k in ("l", "f", "t", "e", "r", "nx", "ny", "nz", "U0", "u_dash", "ring"):
+        o[k] = float(o[k])
+    return o
+
+
+def setup(argv):
+    """Returns dict with everything the DF loop needs for a golden main case."""
+    o = parse(argv)
+    J, K, ns = o["j"], o["k"], o["n"]
+    nrm = np.sqrt(o["nx"] ** 2 + o["ny"] ** 2 + o["nz"] ** 2)          # DF:1291-1293
+    normal = (o["nx"] / nrm, o["ny"] / nrm, o["nz"] / nrm)
+    U, uu, vv, ww, uw = dfo.build_profile(o["p"], "top-hat", o["U0"], o["u_dash"], K)
+    lnx, lny, lnz, nfx, nfy, nfz, dt = dfo.derive_filter_sizes(o["l"], o["f"], o["r"], U, o["t"])
+    for a in (uu, vv, ww):                                                # DF:1347-1354
+        a[a < 0.0] = 0.0
+    if o["p"] in ("double-hyperbolic-tangent", "ring-hyperbolic-tangent", "circular-hyperbolic-tangent"):
+        lund = ("2d", U, uu, vv, ww, uw, o["p"], o["ring"])
+    else:
+        lund = ("1d", U, uu, vv, ww, uw)
+    return dict(J=J, K=K, ns=ns, nm=o["m"], et=o["e"], dt=dt, normal=normal, lund=lund,
+                lnx=lnx, lny=lny, lnz=lnz, nfx=nfx, nfy=nfy, nfz=nfz, profile=(U, uu, vv, ww, uw),
+                mean_profile=o["p"], ring=o["ring"])
