@@ -1,0 +1,152 @@
+/* libpodsdf -- C ABI of the B200-native digital-filter (DF) + PODFS hot paths.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch / numpy types.  The Python
+ * shims in pods-digital-filter_b200/{digitalfilters,PODFS}.py bind it with ctypes and keep the
+ * reference's function names and argument order; INTEGRATION.md shows the stub a maintainer of
+ * the reference would add.  "ref:" comments cite the reference interface each entry replaces
+ * (DF = digitalfilters.py, POD = PODFS.py under /root/reference).
+ *
+ * Conventions
+ *  - every function returns 0 on success, else a PODSDF_ERR_* code; podsdf_last_error() gives
+ *    the text (thread-local).  There is NO CPU fallback: without a usable sm_100 GPU every
+ *    compute entry returns PODSDF_ERR_NO_DEVICE.
+ *  - `_host` entries take host pointers and do the H2D / D2H copies themselves (pinned staging,
+ *    chunked); `_dev` entries take device pointers on the plan's device and a cudaStream_t
+ *    (passed as void*, 0 = default stream) and are asynchronous.
+ *  - all arrays are float64, C order.  J = jma (span), K = kma (wall-normal, fastest axis),
+ *    nf* = HALF filter width (2nf+1 taps), Jp = J+2nfy, Kp = K+2nfz, P = J*K.
+ *  - DF planes use the layout out[t][c][j][k]  (t = step, c = u,v,w): one plane is one column
+ *    A[:, t] of the reference snapshot matrix (DF:1471-1473), i.e. `out` is A transposed.
+ */
+#ifndef PODSDF_H
+#define PODSDF_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define PODSDF_API __attribute__((visibility("default")))
+#else
+#define PODSDF_API
+#endif
+
+#define PODSDF_OK 0
+#define PODSDF_ERR_INVALID 1
+#define PODSDF_ERR_CUDA 2
+#define PODSDF_ERR_NO_DEVICE 3
+#define PODSDF_ERR_UNSUPPORTED 4
+#define PODSDF_ERR_NUMERIC 5
+
+/* snapshot-matrix layouts accepted by the POD entries */
+#define PODSDF_LAYOUT_ROWS_BY_TIME 0 /* reference layout A[row][t], row = c*P+p, time contiguous (DF:1397) */
+#define PODSDF_LAYOUT_TIME_BY_ROWS 1 /* DF-native layout A^T: a[t][row], space contiguous            */
+
+/* kernel selection (testing / profiling): 0 = auto, 1 = generic kernels, 2 = tuned kernels only */
+#define PODSDF_IMPL_AUTO 0
+#define PODSDF_IMPL_GENERIC 1
+#define PODSDF_IMPL_TUNED 2
+
+PODSDF_API const char* podsdf_last_error(void);
+PODSDF_API int podsdf_version(void);
+/* number of usable sm_100 devices (0 and PODSDF_ERR_NO_DEVICE if none) */
+PODSDF_API int podsdf_device_count(int* count);
+/* kernels launched by this library since load (bench.py reports it as gpu_launches) */
+PODSDF_API long long podsdf_launch_count(void);
+/* pinned host memory for async staging (ref: H5:11-64 consumers read results from here) */
+PODSDF_API int podsdf_host_alloc(void** ptr, size_t bytes);
+PODSDF_API int podsdf_host_free(void* ptr);
+
+/* ------------------------------------------------------------------ digital filter (DF) */
+typedef struct podsdf_df_plan podsdf_df_plan;
+
+/* ref: filter sizes/taps DF:73-89 (calccoeff), DF:100-140 (filter3DSciPy1D), DF:1277-1285.
+ * bx,by,bz: host tap vectors of 2nf+1 doubles each (the shim computes them exactly as calccoeff).
+ * The filter is the true convolution of DF:124-137 (taps flipped; identical for symmetric taps). */
+PODSDF_API int podsdf_df_plan_create(int device, int J, int K, int nfx, int nfy, int nfz, const double* bx,
+                          const double* by, const double* bz, podsdf_df_plan** plan);
+PODSDF_API int podsdf_df_plan_destroy(podsdf_df_plan* plan);
+PODSDF_API int podsdf_df_plan_set_impl(podsdf_df_plan* plan, int impl);
+/* planes generated per internal pass (workspace = chunk*3*Jp*Kp doubles); default 512 */
+PODSDF_API int podsdf_df_plan_set_chunk(podsdf_df_plan* plan, int chunk_planes);
+
+/* ref: adapt1d DF:143-178, adapt2prf DF:180-231, adapt2d DF:233-485, rotate_velocity DF:1119-1131.
+ * All four are y = M(j,k) x + m(j,k) with time-invariant M (3x3) and m (3): the shim evaluates
+ * the Cholesky / clamps / splines / rotation once on the host and hands over
+ * coef[12][J*K] = M00,M01,M02,M10,...,M22,m0,m1,m2 planes.  mask bit i set = plane i present
+ * (absent planes are exact zeros and are neither stored nor read).  coef == NULL: identity. */
+PODSDF_API int podsdf_df_set_coefficients(podsdf_df_plan* plan, const double* coef_host, unsigned mask);
+
+/* ref: filter3DSciPy1D(x,y,...) DF:100-140.  x_host (2nfx+1, Jp, Kp) -> y_host (J, K), no Lund. */
+PODSDF_API int podsdf_df_filter_block_host(podsdf_df_plan* plan, const double* x_host, double* y_host);
+/* ref: adapt*(yu,yv,yw,...) in place on three (J,K) host planes, using the plan coefficients. */
+PODSDF_API int podsdf_df_lund_apply_host(podsdf_df_plan* plan, double* yu, double* yv, double* yw);
+
+/* ref: the time loop DF:1403-1477 on an injected random stream.
+ * slabs[n_slabs][3][Jp][Kp]; step i uses slabs i..i+2nfx (DF:1454-1467), so
+ * nsteps = n_slabs - 2nfx planes are written to out[nsteps][3][J][K]. */
+PODSDF_API int podsdf_df_generate_injected_host(podsdf_df_plan* plan, const double* slabs_host, long n_slabs,
+                                     double* out_host);
+PODSDF_API int podsdf_df_generate_injected_dev(podsdf_df_plan* plan, const double* slabs_dev, long n_slabs,
+                                    double* out_dev, void* stream);
+/* same loop with the random stream generated on the device (Philox4x32-10, see csrc/philox.cuh):
+ * planes t0 .. t0+nsteps-1 of the infinite stream `seed` (any shard reproduces its own window). */
+PODSDF_API int podsdf_df_generate_seeded_host(podsdf_df_plan* plan, uint64_t seed, long t0, long nsteps,
+                                   double* out_host);
+PODSDF_API int podsdf_df_generate_seeded_dev(podsdf_df_plan* plan, uint64_t seed, long t0, long nsteps,
+                                  double* out_dev, void* stream);
+/* materialise slabs [s0, s0+n) of the Philox stream: slabs[n][3][Jp][Kp] (tests, halo checks) */
+PODSDF_API int podsdf_df_random_slabs_host(podsdf_df_plan* plan, uint64_t seed, long s0, long n, double* slabs_host);
+PODSDF_API int podsdf_df_random_slabs_dev(podsdf_df_plan* plan, uint64_t seed, long s0, long n, double* slabs_dev,
+                               void* stream);
+/* device time (ms) of the kernels of the last generate_* call on this plan: [0] time filter,
+ * [1] plane filter + Lund, measured with CUDA events on the launching stream */
+PODSDF_API int podsdf_df_last_kernel_ms(podsdf_df_plan* plan, double* ms2);
+
+/* ------------------------------------------------------------------------------ PODFS */
+/* ref: mean removal DF:1492-1495.  mean[M] = mean over time; A -= mean (in place) if subtract. */
+PODSDF_API int podsdf_mean_rows_dev(int device, double* A_dev, long M, long N, int layout, double* mean_dev,
+                         int subtract, void* stream);
+
+/* ref: calculate_correlation_matrix POD:1451-1464.  C[N][N] = scale * A^T diag(w) A, exactly
+ * symmetric (upper triangle computed with FP64 tensor-core MMA, mirrored).  A has M = ncomp*P rows
+ * and N snapshots; w (P doubles, shared by all components) may be NULL ('false' branch).
+ * The reference's scale is 1/num_snapshots.  `_dev` leaves the partial sum of this rank's rows in
+ * C_dev; the caller all-reduces across ranks (NCCL) before the eigen-solve. */
+PODSDF_API int podsdf_gram_host(int device, const double* A_host, long M, long N, int layout, const double* w_host,
+                     long P, double scale, double* C_host);
+PODSDF_API int podsdf_gram_dev(int device, const double* A_dev, long M, long N, int layout, const double* w_dev,
+                    long P, double scale, double* C_dev, void* stream);
+/* device time (ms) of the last Gram kernel on this thread */
+PODSDF_API int podsdf_gram_last_ms(double* ms);
+
+/* ref: linalg.eig(C) POD:1309 on the exactly symmetric C.  Ascending eigenvalues lambda[N] and
+ * orthonormal eigenvectors V[N][N] (column j of the row-major V is eigenvector j).  The sort /
+ * NaN guard / validity count / scaling of POD:1310-1327, 1430-1447 stay in the Python shim. */
+PODSDF_API int podsdf_eig_sym_host(int device, const double* C_host, long N, double* lambda_host, double* V_host);
+PODSDF_API int podsdf_eig_sym_dev(int device, double* C_dev_inout_V, long N, double* lambda_dev, void* stream);
+
+/* ref: projection POD:1329-1333.  Phi[M][nm] = A (M x N) . T (N x nm) . diag(dinv) * scale,
+ * T = scaled temporal modes (row-major N x ldT, first nm columns used), dinv[nm] = 1/lambda. */
+PODSDF_API int podsdf_project_host(int device, const double* A_host, long M, long N, int layout, const double* T_host,
+                        long ldT, const double* dinv_host, int nm, double scale, double* Phi_host);
+PODSDF_API int podsdf_project_dev(int device, const double* A_dev, long M, long N, int layout, const double* T_dev,
+                       long ldT, const double* dinv_dev, int nm, double scale, double* Phi_dev,
+                       void* stream);
+
+/* ref: fourier_coefficients POD:1562-1573.  c[n][i] = (1/N) sum_j a[j][i] exp(-2 pi i (n - N/2) j / N)
+ * for the first nm columns of the row-major (N x ld) matrix a.  Output interleaved complex128
+ * c[N][nm][2].  The complex64 cast, ranking and energy cut (POD:1577-1593) stay in the shim. */
+PODSDF_API int podsdf_dft_modes_host(int device, const double* a_host, long N, long ld, int nm, double* c_host);
+PODSDF_API int podsdf_dft_modes_dev(int device, const double* a_dev, long N, long ld, int nm, double* c_dev,
+                         void* stream);
+
+/* ref: the PODFS reconstruction of docs/usage/CFDCodeIntegration.rst:85-91 is a "next" row. */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PODSDF_H */

@@ -7,9 +7,10 @@ its CPU restatement (Salmon et al. 2011, Random123 constants).
 
 Layout (shared with pods-digital-filter_b200/csrc/philox.cuh):
   key     = (seed & 0xffffffff, seed >> 32)
-  counter = (idx & 0xffffffff, idx >> 32, (s >> 1) & 0xffffffff, comp + 4*((s >> 1) >> 32))
-            idx = p*Kp + q in the padded plane (Jp x Kp), s = global slab index, comp in 0..2
-  output words r0..r3:  slab s even -> (r0, r1),  s odd -> (r2, r3)
+  counter = (pair & 0xffffffff, pair >> 32, s & 0xffffffff, comp + 4*(s >> 32))
+            pair = idx // 2, idx = p*Kp + q in the padded plane (Jp x Kp), s = global slab index,
+            comp in 0..2
+  output words r0..r3:  (r0, r1) -> point idx = 2*pair,  (r2, r3) -> point 2*pair + 1
   u = ((a >> 5) * 2^26 + (b >> 6)) / 2^53          (numpy's 53-bit double, random_sample)
   x = -sqrt(3) + (2 sqrt(3)) * u                   (np.random.uniform(low, high): low + (high-low)*u)
 """
@@ -41,19 +42,26 @@ def philox4x32_10(c0, c1, c2, c3, k0, k1):
 
 def slabs(seed, s0, n, Jp, Kp):
     """Random slabs [s0, s0+n) of all three components: (n, 3, Jp, Kp) float64 in U(-sqrt3, sqrt3)."""
-    idx = np.arange(Jp * Kp, dtype=np.uint64)
+    npts = Jp * Kp
+    npair = (npts + 1) // 2
+    pair = np.arange(npair, dtype=np.uint64)
     out = np.empty((n, 3, Jp, Kp))
     k0, k1 = seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF
     rng = SQRT3 - (-SQRT3)
+
+    def uni(a, b):
+        u = ((a >> np.uint64(5)).astype(np.float64) * 67108864.0
+             + (b >> np.uint64(6)).astype(np.float64)) * (1.0 / 9007199254740992.0)
+        return -SQRT3 + rng * u
+
     for i in range(n):
         s = s0 + i
-        sp = s >> 1
         for comp in range(3):
-            r = philox4x32_10(idx & MASK, idx >> np.uint64(32),
-                              np.full_like(idx, sp & 0xFFFFFFFF),
-                              np.full_like(idx, comp + 4 * (sp >> 32)), k0, k1)
-            a, b = (r[0], r[1]) if (s & 1) == 0 else (r[2], r[3])
-            u = ((a >> np.uint64(5)).astype(np.float64) * 67108864.0
-                 + (b >> np.uint64(6)).astype(np.float64)) / 9007199254740992.0
-            out[i, comp] = (-SQRT3 + rng * u).reshape(Jp, Kp)
+            r = philox4x32_10(pair & MASK, pair >> np.uint64(32),
+                              np.full_like(pair, s & 0xFFFFFFFF),
+                              np.full_like(pair, comp + 4 * (s >> 32)), k0, k1)
+            flat = np.empty(2 * npair)
+            flat[0::2] = uni(r[0], r[1])
+            flat[1::2] = uni(r[2], r[3])
+            out[i, comp] = flat[:npts].reshape(Jp, Kp)
     return out

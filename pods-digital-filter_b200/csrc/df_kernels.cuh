@@ -1,0 +1,41 @@
+// Launchers of the digital-filter kernels (implemented in df_kernels.cu).
+//
+// Data layout in HBM (all float64):
+//   X   [s][c][Jp*Kp]   random slabs (injected) -- s = slab, c = u,v,w
+//   T1  [t][c][Jp*Kp]   time-filtered padded planes (workspace, one chunk of steps)
+//   out [t][c][J*K]     finished planes (Lund-transformed), the transposed snapshot matrix
+//   coef[12][J*K]       M00..M22, m0..m2 planes of the time-invariant Lund/rotation transform
+#pragma once
+#include "common.cuh"
+
+namespace podsdf {
+
+struct DfGeom {
+  int J, K, nfx, nfy, nfz;
+  int Jp, Kp;     // padded plane
+  long Np, P;     // Jp*Kp, J*K
+};
+
+// true when a tuned (compile-time tap count) kernel exists for this size
+bool df_time_has_tuned(int ntx);
+bool df_plane_has_tuned(int nty, int ntz);
+
+// T1[t] = sum_m bx[m] X[t + (NTX-1-m)] for t in [0, nsteps);  X has nsteps + NTX - 1 slabs.
+// gen != 0: X is ignored and slab s is Philox(seed, s_base + s) (generated mode, tuned kernels only).
+int launch_df_time(const DfGeom& g, const Taps& bx, const double* X, double* T1, int nsteps, bool gen,
+                   uint64_t seed, long s_base, bool tuned, cudaStream_t st);
+
+// out[t][c][j][k] = sum_c' M[c][c'] * (by (*) bz (*) T1[t][c'])[j][k] + m[c]   for t in [0, nplanes)
+// ncomp_in = 3 normally; lund = false writes the filtered field unchanged (coef ignored).
+// T2 is the generic path's workspace [nplanes][3][Jp][K] (may be null for the tuned path).
+int launch_df_plane(const DfGeom& g, const Taps& by, const Taps& bz, const double* T1, double* out,
+                    int nplanes, int ncomp, const double* coef, unsigned mask, bool lund, double* T2,
+                    bool tuned, cudaStream_t st);
+
+// in-place y = M x + m on three planes (backs adapt*): planes[3][P]
+int launch_df_lund(const DfGeom& g, double* planes, const double* coef, unsigned mask, cudaStream_t st);
+
+// materialise Philox slabs [s0, s0+n) -> X[n][3][Np]
+int launch_df_random_slabs(const DfGeom& g, uint64_t seed, long s0, long n, double* X, cudaStream_t st);
+
+}  // namespace podsdf

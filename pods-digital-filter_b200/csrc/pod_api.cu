@@ -1,0 +1,234 @@
+// C ABI of the PODFS path (include/podsdf.h).
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <mutex>
+#include <vector>
+
+#include "../../include/podsdf.h"
+#include "pod_kernels.cuh"
+
+using namespace podsdf;
+
+namespace {
+
+thread_local double g_gram_ms = 0.0;
+
+struct DevBuf {  // RAII device allocation
+  double* p = nullptr;
+  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 8); }
+  ~DevBuf() {
+    if (p) cudaFree(p);
+  }
+};
+
+// ---- cuSOLVER, bound at run time -------------------------------------------------------------
+// The dense symmetric eigen-solve (PODFS.py:1309) is the one library call on this path.  cuSOLVER is
+// dlopen()ed so the library has no link-time dependency on a particular cuBLAS/cuSOLVER build: inside
+// a PyTorch process the copy PyTorch already loaded is reused, otherwise the toolkit's is taken.
+typedef void* cusolverDnHandle_t;
+typedef int cusolverStatus_t;
+struct Cusolver {
+  void* lib = nullptr;
+  cusolverStatus_t (*create)(cusolverDnHandle_t*) = nullptr;
+  cusolverStatus_t (*destroy)(cusolverDnHandle_t) = nullptr;
+  cusolverStatus_t (*set_stream)(cusolverDnHandle_t, cudaStream_t) = nullptr;
+  cusolverStatus_t (*bufsize)(cusolverDnHandle_t, int, int, int, const double*, int, const double*, int*) = nullptr;
+  cusolverStatus_t (*syevd)(cusolverDnHandle_t, int, int, int, double*, int, double*, double*, int, int*) = nullptr;
+  std::string err;
+};
+
+Cusolver& cusolver() {
+  static Cusolver cs;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    const char* names[] = {"libcusolver.so.11", "/usr/local/cuda/lib64/libcusolver.so.11", "libcusolver.so.12",
+                           "libcusolver.so"};
+    for (const char* n : names) {
+      cs.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+      if (cs.lib) break;
+    }
+    if (!cs.lib) {
+      cs.err = std::string("cannot dlopen libcusolver: ") + (dlerror() ? dlerror() : "?");
+      return;
+    }
+    cs.create = (decltype(cs.create))dlsym(cs.lib, "cusolverDnCreate");
+    cs.destroy = (decltype(cs.destroy))dlsym(cs.lib, "cusolverDnDestroy");
+    cs.set_stream = (decltype(cs.set_stream))dlsym(cs.lib, "cusolverDnSetStream");
+    cs.bufsize = (decltype(cs.bufsize))dlsym(cs.lib, "cusolverDnDsyevd_bufferSize");
+    cs.syevd = (decltype(cs.syevd))dlsym(cs.lib, "cusolverDnDsyevd");
+    if (!cs.create || !cs.destroy || !cs.set_stream || !cs.bufsize || !cs.syevd) cs.err = "libcusolver lacks Dsyevd";
+  });
+  return cs;
+}
+
+// eigen-decomposition in place: on exit row j of C is eigenvector j (ascending eigenvalues)
+int eig_inplace(double* C_dev, long N, double* lambda_dev, cudaStream_t st) {
+  if (N > 46340) return fail(PODSDF_ERR_UNSUPPORTED, "N too large for the 32-bit cuSOLVER interface");
+  Cusolver& cs = cusolver();
+  if (!cs.err.empty()) return fail(PODSDF_ERR_CUDA, cs.err);
+  cusolverDnHandle_t h = nullptr;
+  if (cs.create(&h) != 0) return fail(PODSDF_ERR_CUDA, "cusolverDnCreate failed");
+  int rc = 0, lwork = 0;
+  DevBuf work, info;
+  const int n = (int)N;
+  // CUSOLVER_EIG_MODE_VECTOR = 1, CUBLAS_FILL_MODE_LOWER = 0 (column-major view of a symmetric matrix)
+  if (cs.set_stream(h, st) != 0) rc = fail(PODSDF_ERR_CUDA, "cusolverDnSetStream failed");
+  if (!rc && cs.bufsize(h, 1, 0, n, C_dev, n, lambda_dev, &lwork) != 0)
+    rc = fail(PODSDF_ERR_CUDA, "cusolverDnDsyevd_bufferSize failed");
+  if (!rc && (work.alloc(sizeof(double) * (size_t)lwork) != cudaSuccess || info.alloc(8) != cudaSuccess))
+    rc = fail(PODSDF_ERR_CUDA, "eigen-solver workspace allocation failed");
+  if (!rc) {
+    const cusolverStatus_t s = cs.syevd(h, 1, 0, n, C_dev, n, lambda_dev, work.p, lwork, (int*)info.p);
+    int hinfo = -1;
+    cudaError_t e = cudaMemcpyAsync(&hinfo, info.p, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) rc = cuda_fail(e, "Dsyevd", __FILE__, __LINE__);
+    else if (s != 0) rc = fail(PODSDF_ERR_CUDA, "cusolverDnDsyevd returned status " + std::to_string(s));
+    else if (hinfo != 0) rc = fail(PODSDF_ERR_NUMERIC, "Dsyevd did not converge, info = " + std::to_string(hinfo));
+  }
+  cs.destroy(h);
+  return rc;
+}
+
+}  // namespace
+
+extern "C" {
+
+int podsdf_mean_rows_dev(int device, double* A_dev, long M, long N, int layout, double* mean_dev, int subtract,
+                         void* stream) {
+  if (!A_dev || !mean_dev || M < 1 || N < 1 || (layout != 0 && layout != 1)) return fail(PODSDF_ERR_INVALID, "bad argument");
+  PODSDF_TRY(check_device(device));
+  DeviceGuard guard(device);
+  return launch_mean_rows(A_dev, M, N, layout, mean_dev, subtract, (cudaStream_t)stream);
+}
+
+int podsdf_gram_dev(int device, const double* A_dev, long M, long N, int layout, const double* w_dev, long P,
+                    double scale, double* C_dev, void* stream) {
+  if (!A_dev || !C_dev || M < 1 || N < 1 || (layout != 0 && layout != 1)) return fail(PODSDF_ERR_INVALID, "bad argument");
+  if (w_dev && (P < 1 || M % P != 0)) return fail(PODSDF_ERR_INVALID, "weights need M = ncomp * P");
+  PODSDF_TRY(check_device(device));
+  DeviceGuard guard(device);
+  cudaStream_t st = (cudaStream_t)stream;
+  DevBuf ws;
+  const size_t wb = gram_workspace_bytes(M, N);
+  PODSDF_CUDA(ws.alloc(wb));
+  cudaEvent_t e0, e1;
+  PODSDF_CUDA(cudaEventCreate(&e0));
+  PODSDF_CUDA(cudaEventCreate(&e1));
+  cudaEventRecord(e0, st);
+  int rc = launch_gram(A_dev, M, N, layout, w_dev, P > 0 ? P : 1, scale, C_dev, ws.p, wb, st);
+  cudaEventRecord(e1, st);
+  cudaError_t e = cudaEventSynchronize(e1);  // workspace is freed on return
+  float ms = 0;
+  if (e == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
+  g_gram_ms = ms;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (!rc && e != cudaSuccess) rc = cuda_fail(e, "gram", __FILE__, __LINE__);
+  return rc;
+}
+
+int podsdf_gram_last_ms(double* ms) {
+  if (!ms) return fail(PODSDF_ERR_INVALID, "null argument");
+  *ms = g_gram_ms;
+  return 0;
+}
+
+int podsdf_gram_host(int device, const double* A_host, long M, long N, int layout, const double* w_host, long P,
+                     double scale, double* C_host) {
+  if (!A_host || !C_host || M < 1 || N < 1) return fail(PODSDF_ERR_INVALID, "bad argument");
+  PODSDF_TRY(check_device(device));
+  DeviceGuard guard(device);
+  DevBuf A, C, w;
+  PODSDF_CUDA(A.alloc(sizeof(double) * (size_t)M * N));
+  PODSDF_CUDA(C.alloc(sizeof(double) * (size_t)N * N));
+  PODSDF_CUDA(cudaMemcpy(A.p, A_host, sizeof(double) * (size_t)M * N, cudaMemcpyHostToDevice));
+  if (w_host) {
+    PODSDF_CUDA(w.alloc(sizeof(double) * (size_t)P));
+    PODSDF_CUDA(cudaMemcpy(w.p, w_host, sizeof(double) * (size_t)P, cudaMemcpyHostToDevice));
+  }
+  PODSDF_TRY(podsdf_gram_dev(device, A.p, M, N, layout, w_host ? w.p : nullptr, P, scale, C.p, nullptr));
+  PODSDF_CUDA(cudaMemcpy(C_host, C.p, sizeof(double) * (size_t)N * N, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int podsdf_eig_sym_dev(int device, double* C_dev_inout_V, long N, double* lambda_dev, void* stream) {
+  if (!C_dev_inout_V || !lambda_dev || N < 1) return fail(PODSDF_ERR_INVALID, "bad argument");
+  PODSDF_TRY(check_device(device));
+  DeviceGuard guard(device);
+  return eig_inplace(C_dev_inout_V, N, lambda_dev, (cudaStream_t)stream);
+}
+
+int podsdf_eig_sym_host(int device, const double* C_host, long N, double* lambda_host, double* V_host) {
+  if (!C_host || !lambda_host || !V_host || N < 1) return fail(PODSDF_ERR_INVALID, "bad argument");
+  PODSDF_TRY(check_device(device));
+  DeviceGuard guard(device);
+  DevBuf C, V, lam;
+  const size_t nn = sizeof(double) * (size_t)N * N;
+  PODSDF_CUDA(C.alloc(nn));
+  PODSDF_CUDA(V.alloc(nn));
+  PODSDF_CUDA(lam.alloc(sizeof(double) * (size_t)N));
+  PODSDF_CUDA(cudaMemcpy(C.p, C_host, nn, cudaMemcpyHostToDevice));
+  PODSDF_TRY(eig_inplace(C.p, N, lam.p, nullptr));
+  PODSDF_TRY(launch_transpose(C.p, V.p, N, nullptr));  // rows = vectors  ->  columns = vectors
+  PODSDF_CUDA(cudaMemcpy(V_host, V.p, nn, cudaMemcpyDeviceToHost));
+  PODSDF_CUDA(cudaMemcpy(lambda_host, lam.p, sizeof(double) * (size_t)N, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int podsdf_project_dev(int device, const double* A_dev, long M, long N, int layout, const double* T_dev, long ldT,
+                       const double* dinv_dev, int nm, double scale, double* Phi_dev, void* stream) {
+  if (!A_dev || !T_dev || !dinv_dev || !Phi_dev || M < 1 || N < 1 || nm < 1 || ldT < nm)
+    return fail(PODSDF_ERR_INVALID, "bad argument");
+  PODSDF_TRY(check_device(device));
+  DeviceGuard guard(device);
+  return launch_project(A_dev, M, N, layout, T_dev, ldT, dinv_dev, nm, scale, Phi_dev, (cudaStream_t)stream);
+}
+
+int podsdf_project_host(int device, const double* A_host, long M, long N, int layout, const double* T_host, long ldT,
+                        const double* dinv_host, int nm, double scale, double* Phi_host) {
+  if (!A_host || !T_host || !dinv_host || !Phi_host || M < 1 || N < 1 || nm < 1 || ldT < nm)
+    return fail(PODSDF_ERR_INVALID, "bad argument");
+  PODSDF_TRY(check_device(device));
+  DeviceGuard guard(device);
+  DevBuf A, T, d, Phi;
+  PODSDF_CUDA(A.alloc(sizeof(double) * (size_t)M * N));
+  PODSDF_CUDA(T.alloc(sizeof(double) * (size_t)N * ldT));
+  PODSDF_CUDA(d.alloc(sizeof(double) * (size_t)nm));
+  PODSDF_CUDA(Phi.alloc(sizeof(double) * (size_t)M * nm));
+  PODSDF_CUDA(cudaMemcpy(A.p, A_host, sizeof(double) * (size_t)M * N, cudaMemcpyHostToDevice));
+  PODSDF_CUDA(cudaMemcpy(T.p, T_host, sizeof(double) * (size_t)N * ldT, cudaMemcpyHostToDevice));
+  PODSDF_CUDA(cudaMemcpy(d.p, dinv_host, sizeof(double) * (size_t)nm, cudaMemcpyHostToDevice));
+  PODSDF_TRY(launch_project(A.p, M, N, layout, T.p, ldT, d.p, nm, scale, Phi.p, nullptr));
+  PODSDF_CUDA(cudaMemcpy(Phi_host, Phi.p, sizeof(double) * (size_t)M * nm, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int podsdf_dft_modes_dev(int device, const double* a_dev, long N, long ld, int nm, double* c_dev, void* stream) {
+  if (!a_dev || !c_dev || N < 1 || nm < 1 || ld < nm) return fail(PODSDF_ERR_INVALID, "bad argument");
+  PODSDF_TRY(check_device(device));
+  DeviceGuard guard(device);
+  cudaStream_t st = (cudaStream_t)stream;
+  DevBuf tw;
+  PODSDF_CUDA(tw.alloc(sizeof(double) * 2 * (size_t)N));
+  int rc = launch_dft(a_dev, N, ld, nm, tw.p, c_dev, st);
+  cudaError_t e = cudaStreamSynchronize(st);  // twiddle table is freed on return
+  if (!rc && e != cudaSuccess) rc = cuda_fail(e, "dft", __FILE__, __LINE__);
+  return rc;
+}
+
+int podsdf_dft_modes_host(int device, const double* a_host, long N, long ld, int nm, double* c_host) {
+  if (!a_host || !c_host || N < 1 || nm < 1 || ld < nm) return fail(PODSDF_ERR_INVALID, "bad argument");
+  PODSDF_TRY(check_device(device));
+  DeviceGuard guard(device);
+  DevBuf a, c;
+  PODSDF_CUDA(a.alloc(sizeof(double) * (size_t)N * ld));
+  PODSDF_CUDA(c.alloc(sizeof(double) * 2 * (size_t)N * nm));
+  PODSDF_CUDA(cudaMemcpy(a.p, a_host, sizeof(double) * (size_t)N * ld, cudaMemcpyHostToDevice));
+  PODSDF_TRY(podsdf_dft_modes_dev(device, a.p, N, ld, nm, c.p, nullptr));
+  PODSDF_CUDA(cudaMemcpy(c_host, c.p, sizeof(double) * 2 * (size_t)N * nm, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,475 @@
+// PODFS kernels for sm_100a: weighted Gram X^T W X (FP64 tensor-core MMA), mode projection,
+// direct DFT of the temporal modes, row means.
+//
+// Reference behaviour being replaced (file:line under /root/reference):
+//   PODFS.py:1451-1464  calculate_correlation_matrix (np.dot(A.T, A)/ns, or the weighted loop)
+//   PODFS.py:1329-1333  spatial modes = A . a[:, :nm] . diag(1/lambda) / ns
+//   PODFS.py:1562-1573  O(ns^2) Python DFT of every temporal mode
+//   digitalfilters.py:1492-1495 mean over time, subtracted column by column
+//
+// FP64 tensor path on sm_100a: tcgen05 has no f64 kind, so the FP64 tensor instruction is the
+// warp-level mma.sync m8n8k4 (SASS DMMA.8x8x4).  A-fragment (8x4, row-major): lane l holds
+// A[l/4][l%4]; B-fragment (4x8, col-major): lane l holds B[l%4][l/4]; C-fragment (8x8): lane l
+// holds C[l/4][2*(l%4) + {0,1}].  Shared-memory pitches are = 4 (mod 16) doubles, which makes
+// every fragment load of a half-warp hit 16 distinct 8-byte banks.
+#include "pod_kernels.cuh"
+
+namespace podsdf {
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, const double a, const double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void cp_async_8(void* smem_dst, const void* gsrc, bool valid) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int bytes = valid ? 8 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(d), "l"(gsrc), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc, bool valid) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int bytes = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gsrc), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// Gram: W[split][tile][128][128] partial = sum over this split's rows of  A_i^T diag(w) A_j
+//   tile = (ib <= jb) pair of 128-snapshot blocks (upper triangle only); 8 warps, warp tile 64 x 32.
+//   LAYOUT 0: A[row][t] (reference, time contiguous): smem tiles [KB rows][128 + 4]
+//   LAYOUT 1: a[t][row] (DF-native, space contiguous): smem tiles [128 t][KB + 4]
+// ------------------------------------------------------------------------------------------------
+constexpr int GT = 128;   // snapshots per tile side
+constexpr int GKB = 16;   // rows (reduction depth) per pipeline stage
+constexpr int GST = 3;    // cp.async stages
+constexpr int GP0 = GT + 4;   // layout-0 pitch (132 = 4 mod 16)
+constexpr int GP1 = GKB + 4;  // layout-1 pitch (20 = 4 mod 16)
+
+template <int LAYOUT>
+struct GramSmem {
+  static constexpr int TILE = (LAYOUT == 0) ? GKB * GP0 : GT * GP1;  // doubles per operand per stage
+  static constexpr size_t BYTES = (size_t)GST * (2 * TILE + GKB) * sizeof(double);
+};
+
+template <int LAYOUT, bool VEC, bool WEIGHT>
+__global__ void __launch_bounds__(256, 1)
+gram_dmma_kernel(const double* __restrict__ A, const long M, const long N, const double* __restrict__ w,
+                 const long P, double* __restrict__ W, const int ntile_side, const long rows_per_split) {
+  extern __shared__ double smem[];
+  constexpr int TILE = GramSmem<LAYOUT>::TILE;
+  double* sA = smem;                      // [GST][TILE]  i-block operand
+  double* sB = smem + GST * TILE;         // [GST][TILE]  j-block operand
+  double* sW = smem + 2 * GST * TILE;     // [GST][GKB]   row weights
+
+  // linear tile id -> (ib, jb) with ib <= jb
+  int ib = 0, rem = blockIdx.x;
+  while (rem >= ntile_side - ib) { rem -= ntile_side - ib; ++ib; }
+  const int jb = ib + rem;
+  const long i0 = (long)ib * GT, j0 = (long)jb * GT;
+  const long r_begin = (long)blockIdx.y * rows_per_split;
+  const long r_end = min(M, r_begin + rows_per_split);
+  const int nchunks = (int)((r_end - r_begin + GKB - 1) / GKB);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = (warp >> 2) * 64, wn = (warp & 3) * 32;  // warp tile origin inside the CTA tile
+  const int lr = lane & 3, lc = lane >> 2;
+
+  auto load_stage = [&](int chunk, int stage) {
+    const long r0 = r_begin + (long)chunk * GKB;
+    double* a = sA + stage * TILE;
+    double* b = sB + stage * TILE;
+    if (LAYOUT == 0) {
+      if (VEC) {  // 16-byte copies: GKB rows x 64 pairs per operand
+        for (int e = tid; e < GKB * (GT / 2); e += 256) {
+          const int r = e / (GT / 2), x = (e % (GT / 2)) * 2;
+          const bool rok = r0 + r < r_end;
+          cp_async_16(a + r * GP0 + x, A + (r0 + r) * N + i0 + x, rok && (i0 + x < N));
+          cp_async_16(b + r * GP0 + x, A + (r0 + r) * N + j0 + x, rok && (j0 + x < N));
+        }
+      } else {
+        for (int e = tid; e < GKB * GT; e += 256) {
+          const int r = e / GT, x = e % GT;
+          const bool rok = r0 + r < r_end;
+          cp_async_8(a + r * GP0 + x, A + (r0 + r) * N + i0 + x, rok && (i0 + x < N));
+          cp_async_8(b + r * GP0 + x, A + (r0 + r) * N + j0 + x, rok && (j0 + x < N));
+        }
+      }
+    } else {
+      if (VEC) {
+        for (int e = tid; e < GT * (GKB / 2); e += 256) {
+          const int t = e / (GKB / 2), r = (e % (GKB / 2)) * 2;
+          const bool rok = r0 + r < r_end;  // M even and r0 even under VEC, so pairs never straddle
+          cp_async_16(a + t * GP1 + r, A + (i0 + t) * M + r0 + r, rok && (i0 + t < N));
+          cp_async_16(b + t * GP1 + r, A + (j0 + t) * M + r0 + r, rok && (j0 + t < N));
+        }
+      } else {
+        for (int e = tid; e < GT * GKB; e += 256) {
+          const int t = e / GKB, r = e % GKB;
+          const bool rok = r0 + r < r_end;
+          cp_async_8(a + t * GP1 + r, A + (i0 + t) * M + r0 + r, rok && (i0 + t < N));
+          cp_async_8(b + t * GP1 + r, A + (j0 + t) * M + r0 + r, rok && (j0 + t < N));
+        }
+      }
+    }
+    if (WEIGHT && tid < GKB) {
+      const long r = r0 + tid;
+      cp_async_8(sW + stage * GKB + tid, w + (r < r_end ? r % P : 0), r < r_end);
+    }
+  };
+
+  double acc[8][4][2];
+#pragma unroll
+  for (int a = 0; a < 8; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+
+  for (int s = 0; s < GST - 1; ++s) {
+    if (s < nchunks) load_stage(s, s);
+    cp_async_commit();
+  }
+  for (int c = 0; c < nchunks; ++c) {
+    cp_async_wait<GST - 2>();
+    __syncthreads();
+    if (c + GST - 1 < nchunks) load_stage(c + GST - 1, (c + GST - 1) % GST);
+    cp_async_commit();
+    const double* a = sA + (c % GST) * TILE;
+    const double* b = sB + (c % GST) * TILE;
+    const double* ws = sW + (c % GST) * GKB;
+#pragma unroll
+    for (int k4 = 0; k4 < GKB; k4 += 4) {
+      double af[8], bf[4];
+      const int r = k4 + lr;
+#pragma unroll
+      for (int mt = 0; mt < 8; ++mt)
+        af[mt] = (LAYOUT == 0) ? a[r * GP0 + wm + mt * 8 + lc] : a[(wm + mt * 8 + lc) * GP1 + r];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        bf[nt] = (LAYOUT == 0) ? b[r * GP0 + wn + nt * 8 + lc] : b[(wn + nt * 8 + lc) * GP1 + r];
+        if (WEIGHT) bf[nt] *= ws[r];
+      }
+#pragma unroll
+      for (int mt = 0; mt < 8; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
+    }
+  }
+  cp_async_wait<0>();
+
+  // partial tile -> workspace [split][tile][128][128]
+  double* Wt = W + ((long)blockIdx.y * gridDim.x + blockIdx.x) * (GT * GT);
+#pragma unroll
+  for (int mt = 0; mt < 8; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const int row = wm + mt * 8 + lc, col = wn + nt * 8 + 2 * lr;
+      *reinterpret_cast<double2*>(Wt + row * GT + col) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+    }
+}
+
+// C[i][j] = C[j][i] = scale * sum_split W[split][tile][i-i0][j-j0]   (deterministic reduction order)
+__global__ void __launch_bounds__(256)
+gram_reduce_kernel(const double* __restrict__ W, const int nsplit, const int ntiles, const int ntile_side,
+                   const long N, const double scale, double* __restrict__ C) {
+  int ib = 0, rem = blockIdx.x;
+  while (rem >= ntile_side - ib) { rem -= ntile_side - ib; ++ib; }
+  const int jb = ib + rem;
+  for (int e = threadIdx.x; e < GT * GT; e += 256) {
+    const int r = e / GT, c = e % GT;
+    const long i = (long)ib * GT + r, j = (long)jb * GT + c;
+    if (i >= N || j >= N) continue;
+    if (ib == jb && c < r) continue;  // diagonal tile: take the upper half, mirror below
+    double s = 0.0;
+    for (int sp = 0; sp < nsplit; ++sp) s += W[((long)sp * ntiles + blockIdx.x) * (GT * GT) + e];
+    s *= scale;
+    C[i * N + j] = s;
+    C[j * N + i] = s;
+  }
+}
+
+int launch_gram(const double* A, long M, long N, int layout, const double* w, long P, double scale, double* C,
+                double* W, size_t W_bytes, cudaStream_t st) {
+  const int side = ceil_div(N, GT);
+  const int ntiles = side * (side + 1) / 2;
+  // split the reduction over rows until ~2 waves of CTAs exist; keep splits 16-row aligned
+  int nsplit = 1;
+  while ((long)ntiles * nsplit < 2L * 148 && M / (nsplit * 2) >= 4 * GKB) nsplit *= 2;
+  long rows_per_split = ((M + nsplit - 1) / nsplit + GKB - 1) / GKB * GKB;
+  nsplit = ceil_div(M, rows_per_split);
+  const size_t need = (size_t)nsplit * ntiles * GT * GT * sizeof(double);
+  if (need > W_bytes) return fail(PODSDF_ERR_INVALID, "gram workspace too small");
+  const bool aligned = (((uintptr_t)A) & 15) == 0;
+  const bool vec = aligned && ((layout == 0) ? (N % 2 == 0) : (M % 2 == 0));
+  dim3 grid(ntiles, nsplit);
+#define LAUNCH(L, V, WT)                                                                                     \
+  do {                                                                                                       \
+    auto k = gram_dmma_kernel<L, V, WT>;                                                                     \
+    PODSDF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GramSmem<L>::BYTES)); \
+    k<<<grid, 256, GramSmem<L>::BYTES, st>>>(A, M, N, w, P, W, side, rows_per_split);                        \
+  } while (0)
+  if (layout == 0) {
+    if (vec) { if (w) LAUNCH(0, true, true); else LAUNCH(0, true, false); }
+    else     { if (w) LAUNCH(0, false, true); else LAUNCH(0, false, false); }
+  } else {
+    if (vec) { if (w) LAUNCH(1, true, true); else LAUNCH(1, true, false); }
+    else     { if (w) LAUNCH(1, false, true); else LAUNCH(1, false, false); }
+  }
+#undef LAUNCH
+  count_launch();
+  gram_reduce_kernel<<<ntiles, 256, 0, st>>>(W, nsplit, ntiles, side, N, scale, C);
+  count_launch();
+  PODSDF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+size_t gram_workspace_bytes(long M, long N) {
+  const int side = ceil_div(N, GT);
+  const long ntiles = (long)side * (side + 1) / 2;
+  int nsplit = 1;
+  while (ntiles * nsplit < 2L * 148 && M / (nsplit * 2) >= 4 * GKB) nsplit *= 2;
+  long rows_per_split = ((M + nsplit - 1) / nsplit + GKB - 1) / GKB * GKB;
+  nsplit = ceil_div(M, rows_per_split);
+  return (size_t)nsplit * ntiles * GT * GT * sizeof(double);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Projection: Phi[row][m] = scale * dinv[m] * sum_t A[row][t] T[t][m]     (PODFS.py:1329-1333)
+//   CTA = 128 rows x 64 modes (grid.y walks mode blocks); 8 warps, warp tile 16 rows x 64 modes.
+// ------------------------------------------------------------------------------------------------
+constexpr int PR = 128, PM = 64, PKB = 16, PST = 3;
+constexpr int PPA0 = PKB + 4;  // layout 0: A tile [128 rows][PKB + 4]
+constexpr int PPA1 = PR + 4;   // layout 1: A tile [PKB t][128 + 4]
+constexpr int PPT = PM + 4;    // T tile [PKB t][64 + 4]
+
+template <int LAYOUT>
+struct ProjSmem {
+  static constexpr int ATILE = (LAYOUT == 0) ? PR * PPA0 : PKB * PPA1;
+  static constexpr int TTILE = PKB * PPT;
+  static constexpr size_t BYTES = (size_t)PST * (ATILE + TTILE) * sizeof(double);
+};
+
+template <int LAYOUT>
+__global__ void __launch_bounds__(256, 1)
+project_dmma_kernel(const double* __restrict__ A, const long M, const long N, const double* __restrict__ T,
+                    const long ldT, const double* __restrict__ dinv, const int nm, const double scale,
+                    double* __restrict__ Phi) {
+  extern __shared__ double smem[];
+  constexpr int ATILE = ProjSmem<LAYOUT>::ATILE, TTILE = ProjSmem<LAYOUT>::TTILE;
+  double* sA = smem;
+  double* sT = smem + PST * ATILE;
+  const long row0 = (long)blockIdx.x * PR;
+  const int m0 = blockIdx.y * PM;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lr = lane & 3, lc = lane >> 2;
+  const int wr = warp * 16;
+  const int nchunks = (int)((N + PKB - 1) / PKB);
+
+  auto load_stage = [&](int chunk, int stage) {
+    const long t0 = (long)chunk * PKB;
+    double* a = sA + stage * ATILE;
+    double* tt = sT + stage * TTILE;
+    if (LAYOUT == 0) {
+      for (int e = tid; e < PR * PKB; e += 256) {
+        const int r = e / PKB, t = e % PKB;
+        cp_async_8(a + r * PPA0 + t, A + (row0 + r) * N + t0 + t, (row0 + r < M) && (t0 + t < N));
+      }
+    } else {
+      for (int e = tid; e < PKB * PR; e += 256) {
+        const int t = e / PR, r = e % PR;
+        cp_async_8(a + t * PPA1 + r, A + (t0 + t) * M + row0 + r, (row0 + r < M) && (t0 + t < N));
+      }
+    }
+    for (int e = tid; e < PKB * PM; e += 256) {
+      const int t = e / PM, m = e % PM;
+      cp_async_8(tt + t * PPT + m, T + (t0 + t) * ldT + m0 + m, (t0 + t < N) && (m0 + m < nm));
+    }
+  };
+
+  double acc[2][8][2];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 8; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+
+  for (int s = 0; s < PST - 1; ++s) {
+    if (s < nchunks) load_stage(s, s);
+    cp_async_commit();
+  }
+  for (int c = 0; c < nchunks; ++c) {
+    cp_async_wait<PST - 2>();
+    __syncthreads();
+    if (c + PST - 1 < nchunks) load_stage(c + PST - 1, (c + PST - 1) % PST);
+    cp_async_commit();
+    const double* a = sA + (c % PST) * ATILE;
+    const double* tt = sT + (c % PST) * TTILE;
+#pragma unroll
+    for (int k4 = 0; k4 < PKB; k4 += 4) {
+      double af[2], bf[8];
+      const int t = k4 + lr;
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+        af[mt] = (LAYOUT == 0) ? a[(wr + mt * 8 + lc) * PPA0 + t] : a[t * PPA1 + wr + mt * 8 + lc];
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) bf[nt] = tt[t * PPT + nt * 8 + lc];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
+    }
+  }
+  cp_async_wait<0>();
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const long row = row0 + wr + mt * 8 + lc;
+      const int m = m0 + nt * 8 + 2 * lr;
+      if (row < M) {
+        if (m < nm) Phi[row * nm + m] = acc[mt][nt][0] * dinv[m] * scale;
+        if (m + 1 < nm) Phi[row * nm + m + 1] = acc[mt][nt][1] * dinv[m + 1] * scale;
+      }
+    }
+}
+
+int launch_project(const double* A, long M, long N, int layout, const double* T, long ldT, const double* dinv,
+                   int nm, double scale, double* Phi, cudaStream_t st) {
+  dim3 grid(ceil_div(M, PR), ceil_div(nm, PM));
+  if (layout == 0) {
+    auto k = project_dmma_kernel<0>;
+    PODSDF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ProjSmem<0>::BYTES));
+    k<<<grid, 256, ProjSmem<0>::BYTES, st>>>(A, M, N, T, ldT, dinv, nm, scale, Phi);
+  } else {
+    auto k = project_dmma_kernel<1>;
+    PODSDF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ProjSmem<1>::BYTES));
+    k<<<grid, 256, ProjSmem<1>::BYTES, st>>>(A, M, N, T, ldT, dinv, nm, scale, Phi);
+  }
+  count_launch();
+  PODSDF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// DFT of the temporal modes (PODFS.py:1562-1573): c[n][i] = (1/N) sum_j a[j][i] e^{-2 pi i k j / N},
+// k = n - N/2.  Twiddles come from an exact table tw[r] = e^{-2 pi i r / N} indexed with (k j) mod N,
+// so the phase never loses accuracy to large arguments.  Thread = (mode i, 4 frequencies).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dft_twiddle_kernel(double2* __restrict__ tw, const long N) {
+  const long r = blockIdx.x * 256L + threadIdx.x;
+  if (r >= N) return;
+  double s, c;
+  sincospi(-2.0 * (double)r / (double)N, &s, &c);
+  tw[r] = make_double2(c, s);
+}
+
+constexpr int DF_NF = 4;  // frequencies per thread
+__global__ void __launch_bounds__(128)
+dft_modes_kernel(const double* __restrict__ a, const long N, const long ld, const int nm,
+                 const double2* __restrict__ tw, double2* __restrict__ c) {
+  const int i = blockIdx.x * 32 + (threadIdx.x & 31);          // mode
+  const long nb = ((long)blockIdx.y * 4 + (threadIdx.x >> 5)) * DF_NF;  // first frequency index
+  if (nb >= N) return;
+  const long half = N / 2;
+  long step[DF_NF], idx[DF_NF];
+  double re[DF_NF], im[DF_NF];
+#pragma unroll
+  for (int f = 0; f < DF_NF; ++f) {
+    const long k = (nb + f) - half;
+    step[f] = ((k % N) + N) % N;
+    idx[f] = 0;
+    re[f] = im[f] = 0.0;
+  }
+  const bool ok = i < nm;
+  for (long j = 0; j < N; ++j) {
+    const double v = ok ? a[j * ld + i] : 0.0;
+#pragma unroll
+    for (int f = 0; f < DF_NF; ++f) {
+      const double2 t = tw[idx[f]];
+      re[f] = fma(v, t.x, re[f]);
+      im[f] = fma(v, t.y, im[f]);
+      idx[f] += step[f];
+      if (idx[f] >= N) idx[f] -= N;
+    }
+  }
+  if (!ok) return;
+  const double inv = 1.0 / (double)N;
+#pragma unroll
+  for (int f = 0; f < DF_NF; ++f)
+    if (nb + f < N) c[(nb + f) * nm + i] = make_double2(re[f] * inv, im[f] * inv);
+}
+
+int launch_dft(const double* a, long N, long ld, int nm, double* tw_ws, double* c, cudaStream_t st) {
+  dft_twiddle_kernel<<<ceil_div(N, 256), 256, 0, st>>>(reinterpret_cast<double2*>(tw_ws), N);
+  count_launch();
+  dim3 grid(ceil_div(nm, 32), ceil_div(N, 4 * DF_NF));
+  dft_modes_kernel<<<grid, 128, 0, st>>>(a, N, ld, nm, reinterpret_cast<const double2*>(tw_ws),
+                                         reinterpret_cast<double2*>(c));
+  count_launch();
+  PODSDF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Row means over time and in-place subtraction (digitalfilters.py:1492-1495)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+mean_rows_l0_kernel(double* __restrict__ A, const long M, const long N, double* __restrict__ mean, const int sub) {
+  const long row = blockIdx.x * 8L + (threadIdx.x >> 5);  // warp per row, time contiguous
+  if (row >= M) return;
+  const int lane = threadIdx.x & 31;
+  double* p = A + row * N;
+  double s = 0.0;
+  for (long t = lane; t < N; t += 32) s += p[t];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const double m = s / (double)N;
+  if (lane == 0) mean[row] = m;
+  if (sub)
+    for (long t = lane; t < N; t += 32) p[t] -= m;
+}
+
+__global__ void __launch_bounds__(256)
+mean_rows_l1_kernel(double* __restrict__ A, const long M, const long N, double* __restrict__ mean, const int sub) {
+  const long row = blockIdx.x * 256L + threadIdx.x;  // thread per row, rows contiguous
+  if (row >= M) return;
+  double s = 0.0;
+  for (long t = 0; t < N; ++t) s += A[t * M + row];
+  const double m = s / (double)N;
+  mean[row] = m;
+  if (sub)
+    for (long t = 0; t < N; ++t) A[t * M + row] -= m;
+}
+
+int launch_mean_rows(double* A, long M, long N, int layout, double* mean, int subtract, cudaStream_t st) {
+  if (layout == 0)
+    mean_rows_l0_kernel<<<ceil_div(M, 8), 256, 0, st>>>(A, M, N, mean, subtract);
+  else
+    mean_rows_l1_kernel<<<ceil_div(M, 256), 256, 0, st>>>(A, M, N, mean, subtract);
+  count_launch();
+  PODSDF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// out[c][r] = in[r][c]  (n x n), used to hand eigenvectors back as columns
+__global__ void __launch_bounds__(256) transpose_kernel(const double* __restrict__ in, double* __restrict__ out, const long n) {
+  __shared__ double tile[32][33];
+  const long bx = blockIdx.x * 32L, by = blockIdx.y * 32L;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8)
+    if (by + r < n && bx + tx < n) tile[r][tx] = in[(by + r) * n + bx + tx];
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8)
+    if (bx + r < n && by + tx < n) out[(bx + r) * n + by + tx] = tile[tx][r];
+}
+
+int launch_transpose(const double* in, double* out, long n, cudaStream_t st) {
+  dim3 grid(ceil_div(n, 32), ceil_div(n, 32));
+  transpose_kernel<<<grid, 256, 0, st>>>(in, out, n);
+  count_launch();
+  PODSDF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace podsdf

@@ -1,0 +1,248 @@
+"""GPU parity of the digital-filter path (through the C ABI) against the CPU oracle and the golden
+vectors made by the reference's own code.  Tolerance: 1e-10 relative (FP64), the north-star bar;
+actual differences are ~1e-15 (re-association of the separable sums only)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import df_oracle as dfo
+from oracle import philox as ophilox
+from tests import replay
+from tests.util import TOL, golden, pkg, rel_err
+
+pytestmark = pytest.mark.gpu
+
+IMPLS = [1, 0]   # generic kernels, auto (tuned where a compile-time tap count exists)
+
+
+@pytest.fixture(scope="module")
+def P():
+    p = pkg()
+    p._capi.require_device()
+    return p
+
+
+@pytest.mark.parametrize("tag", ["iso", "aniso", "wide"])
+def test_filter_block_matches_reference(P, tag):
+    g = golden("filter.npz")
+    nfx, nfy, nfz, J, K = (int(v) for v in g["in_%s_params" % tag][:5])
+    lnx, lny, lnz = g["in_%s_params" % tag][5:]
+    x = g["in_%s_x" % tag]
+    y = np.zeros((J, K))
+    P.digitalfilters.filter3DSciPy1D(x, y, None, J, K, lnx, lny, lnz, nfx, nfy, nfz)
+    assert rel_err(y, g["out_%s_sep" % tag]) < 1e-13
+    y2 = np.zeros((J, K))
+    P.digitalfilters.filter3D(x, y2, g["out_%s_a" % tag], J, K, nfx, nfy, nfz)   # DF:1407-1438 A/B check
+    assert rel_err(y2, g["out_%s_dense" % tag]) < 1e-13
+
+
+def test_adapt_variants_match_reference(P):
+    df = P.digitalfilters
+    g = golden("lund.npz")
+    J, K = 9, 11
+    U, uu, vv, ww, uw = g["out_build_profile"]
+    P2 = g["in_profile2"]
+    y0 = g["in_y"]
+
+    def run(fn, *args):
+        y = [y0[c].copy() for c in range(3)]
+        fn(y[0], y[1], y[2], *args)
+        return np.stack(y)
+
+    assert rel_err(run(df.adapt1d, U, uu, vv, ww, uw, J, K), g["out_adapt1d_tophat"]) < 1e-14
+    ref = g["out_adapt1d_shear"]
+    assert np.isnan(ref).any()
+    assert rel_err(run(df.adapt1d, *P2, J, K), ref) < 1e-14          # NaN where the reference has NaN
+    for mp in ("double", "circular", "ring"):
+        for tag, prof in (("tophat", (U, uu, vv, ww, uw)), ("shear", tuple(P2))):
+            got = run(df.adapt2d, *prof, J, K, mp + "-hyperbolic-tangent", 0.5)
+            assert rel_err(got, g["out_adapt2d_%s_%s" % (mp, tag)]) < 1e-14, (mp, tag)
+    assert rel_err(run(df.adapt2prf, *g["in_prf"], J, K), g["out_adapt2prf"]) < 1e-14
+    for n, rot in zip(g["in_normals"], g["out_rotated"]):
+        assert rel_err(df.rotate_velocity(g["in_col"], *n), rot) < 1e-14
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("tag", ["default", "rotated", "roundjet", "square", "ring", "dt"])
+def test_time_loop_matches_reference_main(P, tag, impl):
+    """The fused device loop on the reference's own random draws == the A the reference's main() built."""
+    g = golden("main_%s.npz" % tag)
+    s = replay.setup(g["in_argv"])
+    J, K, ns = s["J"], s["K"], s["ns"]
+    X = dfo.reference_stream(int(g["in_seed"]), ns, J, K, s["nfx"], s["nfy"], s["nfz"])
+    slabs = np.ascontiguousarray(np.moveaxis(X, 0, 1))
+    lund = P._lund
+    if s["lund"][0] == "2d":
+        fm = lund.lund_2d(*s["profile"], J, K, s["mean_profile"], s["ring"])
+    else:
+        fm = lund.lund_1d(*s["profile"], J, K)
+    R = P.digitalfilters.prof_rotation_matrix(*s["normal"])
+    planes = P.digitalfilters.generate(ns, J, K, s["lnx"], s["lny"], s["lnz"], s["nfx"], s["nfy"], s["nfz"],
+                                       fm, R, slabs=slabs, impl=impl, chunk=5)
+    A = planes.reshape(ns, -1).T
+    ref = g["out_A"] + g["out_mean_field"][:, None]
+    assert rel_err(A, ref) < 1e-13
+    mean, A2 = dfo.remove_mean(np.array(A))
+    assert rel_err(A2, g["out_A"]) < 1e-12
+
+
+def _config(J, K, nfx, nfy, nfz, lnx, lny, lnz, ns, seed, lund):
+    X = dfo.reference_stream(seed, ns, J, K, nfx, nfy, nfz)
+    return X, dfo.generate(X, ns, J, K, lnx, lny, lnz, nfx, nfy, nfz, lund, rotate=None)
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_config1_isotropic_64(P, impl):
+    """BASELINE config 1 shape: 64x64, nf=10, ln=5, hyperbolic-tangent profile (adapt1d) + rotation."""
+    J = K = 64
+    nf, ln, ns = 10, 5.0, 24
+    U, uu, vv, ww, uw = dfo.build_profile("hyperbolic-tangent", "top-hat", 1.0, 0.02, K)
+    X = dfo.reference_stream(0, ns, J, K, nf, nf, nf)
+    ref = dfo.generate(X, ns, J, K, ln, ln, ln, nf, nf, nf, ("1d", U, uu, vv, ww, uw), rotate=(0.6, -0.48, 0.64))
+    fm = P._lund.lund_1d(U, uu, vv, ww, uw, J, K)
+    R = P.digitalfilters.prof_rotation_matrix(0.6, -0.48, 0.64)
+    planes = P.digitalfilters.generate(ns, J, K, ln, ln, ln, nf, nf, nf, fm, R,
+                                       slabs=np.ascontiguousarray(np.moveaxis(X, 0, 1)), impl=impl, chunk=16)
+    assert rel_err(planes.reshape(ns, -1).T, ref) < TOL * 1e-2
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_config2_channel_anisotropic(P, impl):
+    """BASELINE config 2 shape: 256x128, (nfx,nfy,nfz)=(16,8,4), (ln)=(8,4,2), channel profile, adapt1d."""
+    J, K, ns = 256, 128, 6
+    nfx, nfy, nfz, lnx, lny, lnz = 16, 8, 4, 8.0, 4.0, 2.0
+    prof = dfo.channel_profile(K)
+    X, ref = _config(J, K, nfx, nfy, nfz, lnx, lny, lnz, ns, 1, ("1d",) + prof)
+    fm = P._lund.lund_1d(*prof, J, K)
+    planes = P.digitalfilters.generate(ns, J, K, lnx, lny, lnz, nfx, nfy, nfz, fm, None,
+                                       slabs=np.ascontiguousarray(np.moveaxis(X, 0, 1)), impl=impl)
+    assert rel_err(planes.reshape(ns, -1).T, ref) < TOL * 1e-2
+
+
+def test_config3_round_jet_512(P):
+    """BASELINE config 3 shape at full plane size: 512x512, nf=10, round jet (adapt2d), injected window."""
+    J = K = 512
+    nf, ln, ns = 10, 5.0, 3
+    U, uu, vv, ww, uw = dfo.build_profile("circular-hyperbolic-tangent", "top-hat", 1.0, 0.05, K)
+    lund = ("2d", U, uu, vv, ww, uw, "circular-hyperbolic-tangent", 0.5)
+    X, ref = _config(J, K, nf, nf, nf, ln, ln, ln, ns, 2, lund)
+    fm = P._lund.lund_2d(U, uu, vv, ww, uw, J, K, "circular-hyperbolic-tangent", 0.5)
+    planes = P.digitalfilters.generate(ns, J, K, ln, ln, ln, nf, nf, nf, fm, None,
+                                       slabs=np.ascontiguousarray(np.moveaxis(X, 0, 1)))
+    assert rel_err(planes.reshape(ns, -1).T, ref) < TOL * 1e-2
+
+
+@pytest.mark.parametrize("J,K,nfx,nfy,nfz", [(1, 37, 3, 0, 4), (5, 1, 2, 3, 0), (7, 131, 4, 4, 4), (70, 65, 10, 10, 10),
+                                             (9, 200, 6, 6, 6), (33, 40, 24, 5, 20), (3, 3, 0, 0, 0)])
+def test_ragged_and_degenerate_planes(P, J, K, nfx, nfy, nfz):
+    """2-D inflow (jma=1, nfy=0 -- DF:1264), single rows/columns, odd padded sizes, strips that end
+    mid-tile, filter widths without a tuned kernel, and the identity filter."""
+    ns = 2 * (2 * nfx + 1) + 3
+    ln = lambda n: max(n / 2.0, 0.7)
+    rs = np.random.RandomState(J * 1000 + K)
+    X = rs.uniform(-dfo.SQRT3, dfo.SQRT3, (3, ns + 2 * nfx, J + 2 * nfy, K + 2 * nfz))
+    ref = dfo.generate(X, ns, J, K, ln(nfx), ln(nfy), ln(nfz), nfx, nfy, nfz, None)
+    for impl in IMPLS:
+        planes = P.digitalfilters.generate(ns, J, K, ln(nfx), ln(nfy), ln(nfz), nfx, nfy, nfz, None, None,
+                                           slabs=np.ascontiguousarray(np.moveaxis(X, 0, 1)), impl=impl, chunk=7)
+        assert rel_err(planes.reshape(ns, -1).T, ref) < 1e-12, impl
+
+
+def test_filter_is_linear(P):
+    """Size-independent property: F(a x1 + b x2) = a F(x1) + b F(x2)."""
+    J, K, nf, ns = 96, 80, 8, 20
+    rs = np.random.RandomState(4)
+    x1 = rs.standard_normal((ns + 2 * nf, 3, J + 2 * nf, K + 2 * nf))
+    x2 = rs.standard_normal(x1.shape)
+    gen = lambda x: P.digitalfilters.generate(ns, J, K, 4.0, 4.0, 4.0, nf, nf, nf, None, None, slabs=x)
+    lhs = gen(2.5 * x1 - 0.75 * x2)
+    rhs = 2.5 * gen(x1) - 0.75 * gen(x2)
+    assert rel_err(lhs, rhs) < 1e-13
+
+
+def test_philox_stream_and_time_shards(P):
+    """Generated-RNG mode: the device stream equals its numpy restatement bit for bit; seeded generation
+    equals injection of the materialised stream; any time shard reproduces its own window."""
+    J, K, nf = 20, 27, 4
+    df = P.digitalfilters
+    p = df._plan(J, K, nf, nf, nf, df._taps(nf, 2.0), df._taps(nf, 2.0), df._taps(nf, 2.0))
+    seed = 0x1234567890ABCDEF
+    dev = p.random_slabs(seed, 5, 9)
+    assert np.array_equal(dev, ophilox.slabs(seed, 5, 9, J + 2 * nf, K + 2 * nf))
+    big = p.random_slabs(seed, (1 << 33) + 1, 2)       # slab index beyond 32 bits
+    assert np.array_equal(big, ophilox.slabs(seed, (1 << 33) + 1, 2, J + 2 * nf, K + 2 * nf))
+    ns = 30
+    p.set_coefficients(None, 0)
+    for impl in IMPLS:
+        p.set_impl(impl)
+        p.set_chunk(11)
+        whole = p.generate_seeded(seed, 0, ns)
+        inj = p.generate_injected(p.random_slabs(seed, 0, ns + 2 * nf))
+        assert np.array_equal(whole, inj)
+        shard = p.generate_seeded(seed, 17, ns - 17)
+        assert np.array_equal(shard, whole[17:])
+    ref = dfo.generate(np.moveaxis(ophilox.slabs(seed, 0, ns + 2 * nf, J + 2 * nf, K + 2 * nf), 1, 0),
+                       ns, J, K, 2.0, 2.0, 2.0, nf, nf, nf, None)
+    assert rel_err(whole.reshape(ns, -1).T, ref) < 1e-13
+
+
+def test_generated_field_statistics(P):
+    """unit variance, two-point correlations sum_j b_j b_{j+r} along y, z and t, and the
+    prescribed Reynolds stresses / mean after the Lund transform (k = 4 sigma bands)."""
+    J = K = 128
+    nf, ln, ns = 6, 3.0, 600
+    df = P.digitalfilters
+    b = df._taps(nf, ln)
+    planes = df.generate(ns, J, K, ln, ln, ln, nf, nf, nf, None, None, seed=11)
+    f = planes[:, 0]
+    n_eff = ns * J * K / (8.0 * ln ** 3)
+    tol = 4.0 * np.sqrt(2.0 / n_eff) + 2e-3
+    assert abs(f.mean()) < 4.0 / np.sqrt(n_eff)
+    assert abs(f.var() - 1.0) < tol
+    for r in (1, 2, 4, 7):
+        rho = float(np.sum(b[:-r] * b[r:]))
+        assert abs(np.mean(f[:, :-r, :] * f[:, r:, :]) - rho) < tol, ("y", r)
+        assert abs(np.mean(f[:, :, :-r] * f[:, :, r:]) - rho) < tol, ("z", r)
+        assert abs(np.mean(f[:-r] * f[r:]) - rho) < tol, ("t", r)
+    # independent components
+    assert abs(np.mean(planes[:, 0] * planes[:, 1])) < tol
+    # Lund: channel-like profile with shear stress
+    prof = dfo.channel_profile(K)
+    fm = P._lund.lund_1d(*prof, J, K)
+    pl = df.generate(ns, J, K, ln, ln, ln, nf, nf, nf, fm, None, seed=12)
+    U, uu, vv, ww, uw = prof
+    up = pl - pl.mean(axis=(0, 2), keepdims=True)
+    band = 6.0 / np.sqrt(ns * J / (4.0 * ln * ln))
+    assert np.abs(pl[:, 0].mean(axis=(0, 1)) - U).max() < band * np.sqrt(uu.max())
+    assert np.abs((up[:, 0] ** 2).mean(axis=(0, 1)) - uu).max() < band * uu.max() * 2
+    assert np.abs((up[:, 1] ** 2).mean(axis=(0, 1)) - vv).max() < band * vv.max() * 2
+    assert np.abs((up[:, 2] ** 2).mean(axis=(0, 1)) - ww).max() < band * ww.max() * 2
+    assert np.abs((up[:, 0] * up[:, 2]).mean(axis=(0, 1)) - uw).max() < band * np.sqrt(uu.max() * ww.max()) * 2
+
+
+def test_device_pointer_entries_and_kernel_timers(P):
+    """The *_dev entries (device pointers + stream) give the same planes as the *_host entries."""
+    torch = pytest.importorskip("torch")
+    J, K, nf, ns = 64, 96, 10, 40
+    df = P.digitalfilters
+    p = df._plan(J, K, nf, nf, nf, df._taps(nf, 5.0), df._taps(nf, 5.0), df._taps(nf, 5.0))
+    p.set_impl(0)
+    p.set_chunk(16)
+    p.set_coefficients(None, 0)
+    host = p.generate_seeded(5, 3, ns)
+    out = torch.empty((ns, 3, J, K), dtype=torch.float64, device="cuda:0")
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        p.generate_seeded_dev(5, 3, ns, out.data_ptr(), st.cuda_stream)
+    st.synchronize()
+    assert np.array_equal(out.cpu().numpy(), host)
+    t_time, t_plane = p.last_kernel_ms()
+    assert t_time > 0 and t_plane > 0
+    slabs = torch.empty((ns + 2 * nf, 3, J + 2 * nf, K + 2 * nf), dtype=torch.float64, device="cuda:0")
+    p.random_slabs_dev(5, 3, ns + 2 * nf, slabs.data_ptr(), 0)
+    out2 = torch.empty_like(out)
+    p.generate_injected_dev(slabs.data_ptr(), ns + 2 * nf, out2.data_ptr(), 0)
+    torch.cuda.synchronize()
+    assert torch.equal(out, out2)
+    assert P._capi.launch_count() > 0

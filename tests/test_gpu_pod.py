@@ -1,0 +1,197 @@
+"""GPU parity of the PODFS path (through the C ABI) against the CPU oracle and the golden vectors."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import pod_oracle as podo
+from tests import replay
+from tests.util import TOL, fix_signs, golden, pkg, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def P():
+    p = pkg()
+    p._capi.require_device()
+    return p
+
+
+def test_correlation_matrix_matches_reference(P):
+    g = golden("pod_parts.npz")
+    A, w = g["in_A"], g["in_w"]
+    ns, npts = A.shape[1], A.shape[0] // 3
+    for layout_view in (A, np.ascontiguousarray(A.T).T):      # reference layout and transposed planes
+        C = np.zeros((ns, ns))
+        P.PODFS.calculate_correlation_matrix(ns, npts, 3, "false", [], layout_view, C)
+        assert rel_err(C, g["out_C_false"]) < 1e-13
+        assert np.array_equal(C, C.T)                          # exactly symmetric, like dsyrk
+        P.PODFS.calculate_correlation_matrix(ns, npts, 3, "true", w, layout_view, C)
+        assert rel_err(C, g["out_C_true"]) < 1e-13
+        assert np.array_equal(C, C.T)
+    C[:, :] = 7.0
+    P.PODFS.calculate_correlation_matrix(ns, npts, 3, "maybe", [], A, C)
+    assert not C.any()                                         # unknown flag leaves zeros (POD:1453-1456)
+
+
+@pytest.mark.parametrize("M,N", [(12288, 1000), (3 * 1111, 257), (300, 129), (48, 5), (5000, 128)])
+def test_gram_sizes_and_layouts(P, M, N):
+    rs = np.random.RandomState(M + N)
+    A = rs.standard_normal((M, N))
+    ref = np.zeros((N, N))
+    podo.calculate_correlation_matrix(N, M // 3, 3, "false", [], A, ref)
+    capi = P._capi
+    assert rel_err(capi.gram(A, capi.LAYOUT_ROWS_BY_TIME, None, 1.0 / N), ref) < 1e-12
+    assert rel_err(capi.gram(np.ascontiguousarray(A.T), capi.LAYOUT_TIME_BY_ROWS, None, 1.0 / N), ref) < 1e-12
+    w = rs.uniform(0.5, 2.0, M // 3)
+    refw = (A * np.tile(w, 3)[:, None]).T @ A / N
+    assert rel_err(capi.gram(A, capi.LAYOUT_ROWS_BY_TIME, w, 1.0 / N), refw) < 1e-12
+    assert rel_err(capi.gram(np.ascontiguousarray(A.T), capi.LAYOUT_TIME_BY_ROWS, w, 1.0 / N), refw) < 1e-12
+
+
+def test_eigen_solver(P):
+    rs = np.random.RandomState(2)
+    N = 300
+    B = rs.standard_normal((N, 2 * N))
+    C = B @ B.T / N
+    lam, V = P._capi.eig_sym(C)
+    ref = np.linalg.eigvalsh(C)
+    assert np.abs(lam - ref).max() < 1e-12 * ref.max()
+    assert np.abs(V.T @ V - np.eye(N)).max() < 1e-12
+    assert np.abs(C @ V - V * lam[None, :]).max() < 1e-11 * ref.max()
+
+
+def test_projection_and_dft(P):
+    rs = np.random.RandomState(3)
+    M, N, nm = 1000, 333, 37
+    A = rs.standard_normal((M, N))
+    T = rs.standard_normal((N, N))
+    lam = rs.uniform(0.5, 2.0, nm)
+    ref = (A @ T[:, :nm]) @ np.diag(1.0 / lam) / N
+    capi = P._capi
+    assert rel_err(capi.project(A, T, 1.0 / lam, nm, 1.0 / N), ref) < 1e-12
+    assert rel_err(capi.project(np.ascontiguousarray(A.T), T, 1.0 / lam, nm, 1.0 / N, capi.LAYOUT_TIME_BY_ROWS), ref) < 1e-12
+    for n in (333, 1000, 64):
+        a = rs.standard_normal((n, 50))
+        c = capi.dft_modes(a, 23)
+        ref128, _, _ = podo.dft_coefficients(a, n, 23, 0.01, direct=False)
+        assert np.abs(c - ref128).max() < 1e-13
+    a = rs.standard_normal((40, 6))
+    ref128, _, _ = podo.dft_coefficients(a, 40, 6, 0.37, direct=True)      # the reference's own loop
+    assert np.abs(capi.dft_modes(a, 6) - ref128).max() < 1e-14
+
+
+def _check_pod(P, A, ns, npts, nm, dt, et, ref, ref_fc, weights=None, tol=1e-9):
+    df, pod = P.digitalfilters, P.PODFS
+    i_d = df.obj()
+    i_d.verbose, i_d.hdf5, i_d.ns, i_d.dt, i_d.nm, i_d.et = False, True, ns, dt, nm, et
+    cwd = os.getcwd()
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        os.chdir(tmp)
+        try:
+            os.mkdir("PODFS")
+            pod.POD(A, ns, npts, 3, "true" if weights is not None else "false", weights if weights is not None else [],
+                    "PODFS/", "false", 1.0e-15, nm, 0, "false", "false", None, None, dt, "velocity", 1, ns, 1, 1, i_d)
+            pod.fourier_coefficients(i_d)
+            dat = open("PODFS/PODFS.dat").read()
+            assert os.path.exists("PODFS/POD.eigenvalues.dat")
+        finally:
+            os.chdir(cwd)
+    nmr = ref["nm"]
+    assert i_d.nm == nmr
+    e_ref = ref["energy"].real
+    assert np.abs(i_d.energy[:nmr] - e_ref[:nmr]).max() < TOL * e_ref[0]
+    tm_ref = ref["temporal_modes"].real[:, :nmr]
+    tm = fix_signs(i_d.temporal_modes[:, :nmr], tm_ref)
+    sm = fix_signs(i_d.spatial_modes, ref["spatial_modes"])
+    # eigenvector accuracy scales with 1/gap: use the gap-aware bound of SURVEY section 7
+    gaps = np.minimum(np.abs(np.diff(e_ref[:nmr + 1])), np.abs(np.diff(np.r_[np.inf, e_ref[:nmr]]))) / e_ref[0]
+    bound = tol / np.maximum(gaps, 1e-6)
+    assert (np.abs(tm - tm_ref).max(axis=0) / np.abs(tm_ref).max(axis=0) < np.maximum(bound, 1e-9)).all()
+    assert (np.abs(sm - ref["spatial_modes"]).max(axis=0) / np.abs(ref["spatial_modes"]).max(axis=0)
+            < np.maximum(bound, 1e-9)).all()
+    # invariants (appendix F-6): orthonormal spatial modes, mean(a_i^2) = lambda_i, rank-nm reconstruction
+    if weights is None:
+        assert np.abs(i_d.spatial_modes.T @ i_d.spatial_modes - np.eye(nmr)).max() < 1e-9
+    assert np.abs(np.mean(i_d.temporal_modes[:, :nmr] ** 2, axis=0) - e_ref[:nmr]).max() < 1e-9 * e_ref[0]
+    recon = i_d.spatial_modes @ i_d.temporal_modes[:, :nmr].T
+    recon_ref = ref["spatial_modes"] @ tm_ref.T
+    assert rel_err(recon, recon_ref) < 1e-8
+    return i_d, dat
+
+
+@pytest.mark.parametrize("tag", ["default", "rotated", "roundjet", "square", "ring", "dt"])
+def test_pod_and_fourier_match_reference_main(P, tag):
+    """POD + Fourier fit of the reference's own snapshot matrix == what the reference's main() produced."""
+    g = golden("main_%s.npz" % tag)
+    s = replay.setup(g["in_argv"])
+    ns, npts = s["ns"], s["J"] * s["K"]
+    A = g["out_A"]
+    ref = dict(nm=int(g["out_nm"]), temporal_modes=g["out_temporal_modes"], spatial_modes=g["out_spatial_modes"],
+               energy=np.mean(g["out_temporal_modes"].real ** 2, axis=0))
+    i_d, dat = _check_pod(P, A, ns, npts, s["nm"], s["dt"], s["et"], ref, None)
+    # Fourier coefficients: |c| is sign-invariant, the coefficients follow the mode's sign
+    sign = np.sign(np.sum(i_d.temporal_modes[:, :ref["nm"]] * g["out_temporal_modes"].real[:, :ref["nm"]], axis=0))
+    assert np.array_equal(i_d.N_FC, g["out_N_FC"])
+    FC, FCr = i_d.FC, g["out_FC"]
+    row = 0
+    for i in range(ref["nm"]):
+        n = int(i_d.N_FC[i])
+        assert np.array_equal(FC[row:row + n, 0], FCr[row:row + n, 0])          # same harmonics, same order
+        assert np.abs(sign[i] * FC[row:row + n, 1:] - FCr[row:row + n, 1:]).max() < 2e-7 * np.abs(FCr[row:row + n, 1:]).max()
+        row += n
+    assert i_d.period == float(g["out_period"])
+    assert dat.split("\n")[:2 + ref["nm"]] == str(g["out_podfs_dat"]).split("\n")[:2 + ref["nm"]]
+
+
+def test_pod_config1_shape_against_oracle(P):
+    """12 288 x 1000 snapshot matrix (config 1's POD), 20 modes, against the numpy oracle -- both layouts."""
+    M, N, nm = 12288, 1000, 20
+    A = podo.synthetic_snapshots(M, N, seed=1)
+    _, A = (A.mean(1), A - A.mean(1)[:, None])
+    ref = podo.pod(A, N, M // 3, 3, "false", [], 1.0e-15, nm, eig=np.linalg.eigh)
+    f = podo.fourier_coefficients(ref["temporal_modes"], N, ref["nm"], 0.01, 0.9, direct=False)
+    for view in (A, np.ascontiguousarray(A.T).T):
+        i_d, dat = _check_pod(P, view, N, M // 3, nm, 0.01, 0.9, ref, f)
+        sign = np.sign(np.sum(i_d.temporal_modes[:, :nm] * ref["temporal_modes"].real[:, :nm], axis=0))
+        assert np.abs(i_d.c128 * sign[None, :] - f["c128"]).max() < TOL * np.abs(f["c128"]).max() * 10
+        assert np.array_equal(i_d.c_count, f["c_count"])
+
+
+def test_pod_weighted_branch_against_oracle(P):
+    M, N, nm = 3 * 700, 40, 6
+    A = podo.synthetic_snapshots(M, N, seed=5, rank_r=12)
+    A = A - A.mean(1)[:, None]
+    w = np.random.RandomState(1).uniform(0.5, 2.0, M // 3)
+    ref = podo.pod(A, N, M // 3, 3, "true", w, 1.0e-15, nm)
+    _check_pod(P, A, N, M // 3, nm, 0.02, 0.9, ref, None, weights=w)
+
+
+def test_device_entries_mean_gram_project(P):
+    torch = pytest.importorskip("torch")
+    capi = P._capi
+    L = capi.lib()
+    rs = np.random.RandomState(9)
+    M, N, nm = 3 * 500, 200, 16
+    A = rs.standard_normal((M, N)) + rs.standard_normal((M, 1)) * 3
+    for layout, arr in ((0, A), (1, np.ascontiguousarray(A.T))):
+        d = torch.from_numpy(arr.copy()).cuda()
+        mean = torch.empty(M, dtype=torch.float64, device="cuda")
+        capi.check(L.podsdf_mean_rows_dev(0, d.data_ptr(), M, N, layout, mean.data_ptr(), 1, 0))
+        torch.cuda.synchronize()
+        assert np.abs(mean.cpu().numpy() - A.mean(1)).max() < 1e-13
+        Ac = A - A.mean(1)[:, None]
+        got = d.cpu().numpy() if layout == 0 else d.cpu().numpy().T
+        assert np.abs(got - Ac).max() < 1e-13
+        C = torch.empty((N, N), dtype=torch.float64, device="cuda")
+        capi.check(L.podsdf_gram_dev(0, d.data_ptr(), M, N, layout, None, 0, 1.0 / N, C.data_ptr(), 0))
+        torch.cuda.synchronize()
+        assert rel_err(C.cpu().numpy(), Ac.T @ Ac / N) < 1e-12
+        lam = torch.empty(N, dtype=torch.float64, device="cuda")
+        Cv = C.clone()
+        capi.check(L.podsdf_eig_sym_dev(0, Cv.data_ptr(), N, lam.data_ptr(), 0))
+        V = Cv.cpu().numpy()          # rows are eigenvectors
+        assert np.abs(V @ V.T - np.eye(N)).max() < 1e-12
+        assert np.abs(lam.cpu().numpy() - np.linalg.eigvalsh(Ac.T @ Ac / N)).max() < 1e-11

@@ -1,0 +1,120 @@
+"""Host-side logic of the shims (no GPU): taps, Lund coefficient set-up, eigenvalue sorting, CLI table,
+inlet-plane geometry -- each against the oracle / the golden vectors made by the reference."""
+import numpy as np
+import pytest
+
+from oracle import df_oracle as dfo
+from oracle import pod_oracle as podo
+from tests.util import golden, pkg
+
+
+def test_calccoeff_and_coeff3d_bit_exact():
+    df = pkg().digitalfilters
+    g = golden("taps.npz")
+    for key in g.files:
+        n, ln = key[len("out_b_n"):].split("_ln")
+        assert np.array_equal(df.calccoeff(np.zeros(2 * int(n) + 1), int(n), float(ln)), g[key])
+    f = golden("filter.npz")
+    nfx, nfy, nfz = (int(v) for v in f["in_aniso_params"][:3])
+    a = np.zeros((1, 2 * nfx + 1, 2 * nfy + 1, 2 * nfz + 1))
+    df.coeff3D(a, nfx, nfy, nfz, *f["in_aniso_params"][5:])
+    assert np.array_equal(a, f["out_aniso_a"])
+
+
+def _dense(coef, J, K):
+    M = coef[:9].reshape(3, 3, J, K)
+    m = coef[9:].reshape(3, J, K)
+    return M, m
+
+
+def test_lund_coefficients_reproduce_reference_outputs():
+    """y = M x + m evaluated on the host from the packed planes equals the reference's adapt* outputs."""
+    lund = pkg()._lund
+    g = golden("lund.npz")
+    J, K = 9, 11
+    y0 = g["in_y"]
+    U, uu, vv, ww, uw = g["out_build_profile"]
+    P2 = g["in_profile2"]
+
+    def apply(fac_mean, rotation=None):
+        coef, mask = lund.pack(fac_mean[0], fac_mean[1], J, K, rotation)
+        for i in range(12):
+            assert bool(mask >> i & 1) == bool(np.any(coef[i] != 0.0))
+        M, m = _dense(coef, J, K)
+        with np.errstate(invalid="ignore"):
+            return np.einsum("abjk,bjk->ajk", M, y0) + m
+
+    def close(a, b):
+        assert np.array_equal(np.isnan(a), np.isnan(b))
+        ok = ~np.isnan(b)
+        assert np.abs(a[ok] - b[ok]).max() < 1e-14
+
+    close(apply(lund.lund_1d(U, uu, vv, ww, uw, J, K)), g["out_adapt1d_tophat"])
+    close(apply(lund.lund_1d(*P2, J, K)), g["out_adapt1d_shear"])
+    for mp in ("double", "circular", "ring"):
+        for tag, prof in (("tophat", (U, uu, vv, ww, uw)), ("shear", tuple(P2))):
+            close(apply(lund.lund_2d(*prof, J, K, mp + "-hyperbolic-tangent", 0.5)), g["out_adapt2d_%s_%s" % (mp, tag)])
+    close(apply(lund.lund_prf(*g["in_prf"])), g["out_adapt2prf"])
+
+
+def test_rotation_matrix_and_profiles_bit_exact():
+    df = pkg().digitalfilters
+    g = golden("lund.npz")
+    for n, R in zip(g["in_normals"], g["out_rotmat"]):
+        assert np.array_equal(df.prof_rotation_matrix(*n), R)
+    got = df.build_profile("hyperbolic-tangent", "top-hat", 1.3, 0.05, 11)
+    assert np.array_equal(np.stack(got), g["out_build_profile"])
+    with pytest.raises(Exception):
+        df.build_profile("parabola", "top-hat", 1.0, 0.1, 5)
+
+
+def test_sort_eigenvalues_matches_reference():
+    pod = pkg().PODFS
+    g = golden("pod_parts.npz")
+    en, tm = g["in_energy"].copy(), g["in_tm"].copy()
+    pod.sort_eigenvalues(len(en), en, tm)
+    assert np.array_equal(en, g["out_energy_sorted"])
+    assert np.array_equal(tm, g["out_tm_sorted"])
+
+
+def test_count_valid_modes_matches_oracle():
+    pod = pkg().PODFS
+    rs = np.random.RandomState(0)
+    for n in (5, 12, 40):
+        e = np.sort(rs.uniform(0.1, 2.0, n))[::-1].copy()
+        assert pod._count_valid(e, n, 1e-15) == podo.count_valid_modes(e, n, 1e-15)
+        e[n // 2:] = -1e-3
+        assert pod._count_valid(e, n, 1e-15) == podo.count_valid_modes(e, n, 1e-15)
+
+
+def test_cli_flag_table_matches_reference_names():
+    df = pkg().digitalfilters
+    opts, _ = df._parser().parse_args(["-n", "5"])
+    # defaults documented in SURVEY section 5 (DF:1143-1237)
+    assert (opts.nsteps, opts.lengthscale, opts.fwidth, opts.kma, opts.jma) == (5, 3.0, 2.0, 11, 10)
+    assert (opts.dt, opts.nm, opts.et, opts.res, opts.nx, opts.bulk_velocity) == (0.0, 20, 0.9, 0.1, 1.0, 1.0)
+    assert (opts.turbulence_intensity, opts.ring, opts.mean_profile) == (0.02, 0.5, "hyperbolic-tangent")
+    for flag in ["--u_dash", "--nsteps", "--fwidth", "--nm", "--U0", "--bulk_velocity", "--turb_profile",
+                 "--rotate", "--massflow", "--density", "--hdf5", "--test_gradients", "--non_dim", "--ring"]:
+        assert df._parser().has_option(flag), flag
+
+
+def test_inflow_plane_matches_doc_fixture():
+    """docs/usage/CFDCodeIntegration.rst:53 -- first cell of the default 10x11 plane is
+    (0, -0.5, 0.55) and prints as 0.550000011921 (float32 points, "%0.12f")."""
+    p = pkg()
+    i_d = p.digitalfilters.obj()
+    i_d.jma, i_d.kma, i_d.res, i_d.n, i_d.rot, i_d.t_o = 10, 11, 0.1, [1.0, 0.0, 0.0], 0.0, [0, 0, 0]
+    grid = p.PODFS.make_inflow_plane(i_d)
+    assert grid.GetNumberOfCells() == 110
+    c = grid.centers[0]
+    assert [p.PODFS._fmt(v) for v in c] == ["0.000000000000", "-0.500000000000", "0.550000011921"]
+    # cell id = k + j*K: the second cell moves along -z
+    assert grid.centers[1][2] < grid.centers[0][2] and grid.centers[1][1] == grid.centers[0][1]
+
+
+def test_reference_stream_draw_order():
+    df = pkg().digitalfilters
+    np.random.seed(3)
+    X = df.reference_stream(5, 4, 6, 2, 1, 3)
+    assert np.array_equal(np.moveaxis(X, 1, 0), dfo.reference_stream(3, 5, 4, 6, 2, 1, 3))
