@@ -170,6 +170,27 @@ def write_temporal_modes(num_valid_modes, num_snapshots, dt, temporal_modes, rdi
 
 
 # =====================================================================================
+def select_fourier(c128, energy_target):
+    """POD:1547, 1577-1593: complex64 storage, ranking by magnitude (ties: higher index first) and the
+    smallest leading set whose magnitude sum reaches energy_target * total.
+    Returns (c complex64 (ns,nm), c_ind (nm,ns) int32, c_count (nm,) int64)."""
+    num_fcs, num_modes = c128.shape
+    c = c128.astype(np.complex64)                                          # POD:1547
+    c_count = np.zeros(num_modes, dtype=np.int64)
+    c_ind = np.zeros((num_modes, num_fcs), dtype=np.int32)
+    for i in range(num_modes):
+        cmod = np.abs(c[:, i])                                             # float32 magnitudes
+        order = np.lexsort((-np.arange(num_fcs), -cmod))                   # POD:1584 tuple sort, reversed
+        c_ind[i, :] = order
+        # POD:1588-1593 under the numpy-1.x casting the reference ran with: float64 running sum of the
+        # float32 magnitudes against float64(float32 total) * et
+        thresh = float(np.sum(cmod)) * energy_target
+        if thresh > 0.0:
+            run = np.cumsum(cmod[order].astype(np.float64))
+            c_count[i] = min(int(np.searchsorted(run, thresh, side="left")) + 1, num_fcs)
+    return c, c_ind, c_count
+
+
 def fourier_coefficients(i_d):
     """POD:1523-1659.  DFT of the first i_d.nm temporal modes on the GPU, then the reference's
     complex64 storage, magnitude ranking and energy cut; writes ./PODFS/PODFS.dat and, when
@@ -185,19 +206,8 @@ def fourier_coefficients(i_d):
     period = time[-1] + (time[1] - time[0])
 
     c128 = _capi.dft_modes(i_d.temporal_modes, num_modes, device=DEVICE)   # (ns, nm), k = n - ns//2
-    c = c128.astype(np.complex64)                                          # POD:1547
-    c_count = np.zeros(num_modes, dtype=np.int64)
-    c_ind = np.zeros((num_modes, num_fcs), dtype=np.int32)
+    c, c_ind, c_count = select_fourier(c128, energy_target)
     for i in range(num_modes):
-        cmod = np.abs(c[:, i])                                             # float32 magnitudes
-        order = np.lexsort((-np.arange(num_fcs), -cmod))                   # POD:1584 tuple sort, reversed
-        c_ind[i, :] = order
-        # POD:1588-1593 under the numpy-1.x casting the reference ran with: float64 running sum of the
-        # float32 magnitudes against float64(float32 total) * et
-        thresh = float(np.sum(cmod)) * energy_target
-        if thresh > 0.0:
-            run = np.cumsum(cmod[order].astype(np.float64))
-            c_count[i] = min(int(np.searchsorted(run, thresh, side="left")) + 1, num_fcs)
         print("The number of fourier coeffients used for mode ", i + 1, " is ", c_count[i])
 
     i_d.c = c

@@ -9,5 +9,6 @@ from . import _lund          # noqa: F401
 from . import PODFS          # noqa: F401
 from . import HDF5           # noqa: F401
 from . import digitalfilters  # noqa: F401
+from . import pipeline       # noqa: F401  (torch is imported lazily, only by the device drivers)
 
-__all__ = ["_capi", "_lund", "PODFS", "HDF5", "digitalfilters"]
+__all__ = ["_capi", "_lund", "PODFS", "HDF5", "digitalfilters", "pipeline"]

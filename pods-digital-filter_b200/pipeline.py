@@ -1,0 +1,159 @@
+"""Device-resident and multi-GPU drivers of the two hot paths (one process per GPU).
+
+PyTorch is used here for plumbing only -- device buffers, streams and `torch.distributed` (NCCL on
+GPUs, gloo in the CPU tests); every FLOP of the hot paths runs in libpodsdf's kernels through the
+C ABI (`_capi`).
+
+Sharding:
+  DF    time-sharded: rank r generates steps [t0_r, t1_r).  Step t needs random slabs t..t+2nfx
+        (DF:1454-1467), so a shard needs a 2nfx-slab halo from its right neighbour.  In the
+        generated-RNG mode the halo is regenerated from the counter-based stream (no traffic); in
+        the injected mode it is exchanged over NVLink (`exchange_halo`, NCCL send/recv).
+  POD   the Gram matrix is a sum over spatial rows: rank r holds rows [m0_r, m1_r) of the snapshot
+        matrix, forms its N x N partial and one all-reduce (sum, float64) completes C on every
+        rank; the eigen-solve is replicated, the projection is local to the row shard.
+"""
+import numpy as np
+
+try:
+    from . import _capi
+except ImportError:
+    import _capi
+
+
+def shard_range(n, rank, world):
+    """Contiguous block partition of range(n): the first n % world ranks get one extra item."""
+    base, extra = divmod(n, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+# ------------------------------------------------------------------------------------- DF
+def exchange_halo(slabs, halo, rank=None, world=None, group=None):
+    """Injected mode.  `slabs` (n_local, 3, Jp, Kp) holds this rank's own slabs [t0_r, t1_r) of the global
+    random stream; returns the tensor extended by the first `halo` (= 2 nfx) slabs of the right neighbour,
+    which the last `halo` steps of this shard need.  The last rank gets no extension: its window is
+    truncated (the global stream must therefore carry 2 nfx slabs more than the steps wanted, exactly as
+    the reference's initial block does, DF:1361-1366).  Works on CUDA tensors over NCCL and on CPU
+    tensors over gloo (the unit tests)."""
+    import torch
+    import torch.distributed as dist
+    rank = dist.get_rank(group) if rank is None else rank
+    world = dist.get_world_size(group) if world is None else world
+    if world == 1 or halo == 0:
+        return slabs
+    if slabs.shape[0] < halo:
+        raise ValueError("a shard must hold at least 2*nfx slabs to serve its neighbour's halo")
+    ops = []
+    recv = None
+    if rank > 0:                     # my first `halo` slabs are the left neighbour's halo
+        ops.append(dist.P2POp(dist.isend, slabs[:halo].contiguous(), rank - 1, group))
+    if rank < world - 1:
+        recv = torch.empty((halo,) + tuple(slabs.shape[1:]), dtype=slabs.dtype, device=slabs.device)
+        ops.append(dist.P2POp(dist.irecv, recv, rank + 1, group))
+    for req in dist.batch_isend_irecv(ops):
+        req.wait()
+    return slabs if recv is None else torch.cat([slabs, recv], dim=0)
+
+
+class DfShard(object):
+    """One rank's share of a DF run, resident on its GPU."""
+
+    def __init__(self, plan, nsteps_local, device):
+        import torch
+        self.plan = plan
+        self.n = int(nsteps_local)
+        self.device = device
+        self.out = torch.empty((self.n, 3, plan.J, plan.K), dtype=torch.float64, device=device)
+
+    def generate_seeded(self, seed, t0, stream=None):
+        import torch
+        st = torch.cuda.current_stream(self.device) if stream is None else stream
+        self.plan.generate_seeded_dev(seed, t0, self.n, self.out.data_ptr(), st.cuda_stream)
+        return self.out
+
+    def generate_injected(self, slabs, stream=None):
+        import torch
+        st = torch.cuda.current_stream(self.device) if stream is None else stream
+        n_slabs = slabs.shape[0]
+        assert n_slabs - 2 * self.plan.nfx <= self.n
+        self.plan.generate_injected_dev(slabs.data_ptr(), n_slabs, self.out.data_ptr(), st.cuda_stream)
+        return self.out[:n_slabs - 2 * self.plan.nfx]
+
+
+# ------------------------------------------------------------------------------------ POD
+def allreduce_gram(C, group=None):
+    """Sum of the per-rank N x N partial Gram matrices (float64) on every rank."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(C, op=dist.ReduceOp.SUM, group=group)
+    return C
+
+
+def select_modes(lam_asc, V_rows, ns, nm, tol_CN=1.0e-15):
+    """Host-side post-processing of the eigen-solve, restating POD:1310-1327 for the device pipeline:
+    descending order, validity count, truncation, and the scale factors a_j = v_j sqrt(lambda_j ns/|v_j|^2).
+    lam_asc (N,) ascending eigenvalues; V_rows(j) returns eigenvector j (of the ascending order) as (N,).
+    Returns (energy_desc (N,), nm, T (N, nm) scaled temporal modes)."""
+    try:
+        from . import PODFS as pod
+    except ImportError:
+        import PODFS as pod
+    N = lam_asc.shape[0]
+    vals = np.where(np.isnan(lam_asc), -1.0e10, lam_asc)
+    order = np.lexsort((-np.arange(N), -vals))
+    energy = vals[order]
+    nv = pod._count_valid(energy, ns, tol_CN)
+    if nm < 0 or nm > nv:
+        nm = nv
+    T = np.empty((N, nm))
+    for j in range(nm):
+        v = V_rows(int(order[j]))
+        T[:, j] = v * np.sqrt(energy[j] / (np.sum(v * v) / ns))
+    return energy, nm, T
+
+
+def pod_resident(A, M, N, layout, nm, dt, et, device_index=0, group=None, timers=None):
+    """PODFS of a device-resident (row shard of a) snapshot matrix: mean removal, Gram (+ all-reduce),
+    eigen-solve, projection, Fourier fit.  A: CUDA float64 tensor, modified in place (mean removed).
+    Returns dict(mean, energy, nm, T, Phi, c128) with Phi (M, nm) on the device."""
+    import torch
+    L = _capi.lib()
+    dev = A.device
+    st = torch.cuda.current_stream(dev).cuda_stream
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    marks = [ev() for _ in range(6)]
+    mean = torch.empty(M, dtype=torch.float64, device=dev)
+    marks[0].record()
+    _capi.check(L.podsdf_mean_rows_dev(device_index, A.data_ptr(), M, N, layout, mean.data_ptr(), 1, st))
+    C = torch.empty((N, N), dtype=torch.float64, device=dev)
+    marks[1].record()
+    _capi.check(L.podsdf_gram_dev(device_index, A.data_ptr(), M, N, layout, None, 0, 1.0 / N, C.data_ptr(), st))
+    allreduce_gram(C, group)
+    marks[2].record()
+    lam = torch.empty(N, dtype=torch.float64, device=dev)
+    _capi.check(L.podsdf_eig_sym_dev(device_index, C.data_ptr(), N, lam.data_ptr(), st))   # rows of C = vectors
+    marks[3].record()
+    lam_h = lam.cpu().numpy()
+    energy, nm, T = select_modes(lam_h, lambda j: C[j].cpu().numpy(), N, nm)
+    T_d = torch.from_numpy(np.ascontiguousarray(T)).to(dev)
+    dinv = torch.from_numpy(1.0 / energy[:nm]).to(dev)
+    Phi = torch.empty((M, nm), dtype=torch.float64, device=dev)
+    _capi.check(L.podsdf_project_dev(device_index, A.data_ptr(), M, N, layout, T_d.data_ptr(), nm, dinv.data_ptr(),
+                                     nm, 1.0 / N, Phi.data_ptr(), st))
+    marks[4].record()
+    c = torch.empty((N, nm, 2), dtype=torch.float64, device=dev)
+    _capi.check(L.podsdf_dft_modes_dev(device_index, T_d.data_ptr(), N, nm, nm, c.data_ptr(), st))
+    c128 = c.cpu().numpy().view(np.complex128).reshape(N, nm)
+    try:
+        from . import PODFS as pod
+    except ImportError:
+        import PODFS as pod
+    c64, c_ind, c_count = pod.select_fourier(c128, et)
+    marks[5].record()
+    torch.cuda.synchronize(dev)
+    if timers is not None:
+        names = ["mean", "gram", "eig", "select_project", "dft"]
+        for i, name in enumerate(names):
+            timers[name] = timers.get(name, 0.0) + marks[i].elapsed_time(marks[i + 1])
+    return dict(mean=mean, energy=energy, nm=nm, T=T, Phi=Phi, c128=c128, c_ind=c_ind, c_count=c_count)

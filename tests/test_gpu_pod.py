@@ -35,7 +35,7 @@ def test_correlation_matrix_matches_reference(P):
     assert not C.any()                                         # unknown flag leaves zeros (POD:1453-1456)
 
 
-@pytest.mark.parametrize("M,N", [(12288, 1000), (3 * 1111, 257), (300, 129), (48, 5), (5000, 128)])
+@pytest.mark.parametrize("M,N", [(12288, 1000), (3 * 1111, 257), (300, 129), (48, 5), (4998, 128)])
 def test_gram_sizes_and_layouts(P, M, N):
     rs = np.random.RandomState(M + N)
     A = rs.standard_normal((M, N))
