@@ -76,9 +76,16 @@ bool use_tuned_time(const podsdf_df_plan* p) {
   if (p->impl == PODSDF_IMPL_GENERIC) return false;
   return df_time_has_tuned(2 * p->g.nfx + 1);
 }
+// the tuned plane kernel reads the column-panel layout only the tuned time kernel writes, with
+// 16-byte pieces: both kernels must exist for these widths and the padded row length must be even
 bool use_tuned_plane(const podsdf_df_plan* p) {
   if (p->impl == PODSDF_IMPL_GENERIC) return false;
-  return df_plane_has_tuned(2 * p->g.nfy + 1, 2 * p->g.nfz + 1);
+  return use_tuned_time(p) && df_plane_has_tuned(2 * p->g.nfy + 1, 2 * p->g.nfz + 1) && (p->g.Kp % 2 == 0);
+}
+PanelGeom panel_of(const podsdf_df_plan* p) { return use_tuned_plane(p) ? make_panel_geom(p->g) : PanelGeom(); }
+size_t t1_doubles_per_plane(const podsdf_df_plan* p) {
+  const PanelGeom pg = panel_of(p);
+  return 3 * (size_t)(pg.PB > 0 ? pg.comp_stride : p->g.Np);
 }
 
 int free_workspace(podsdf_df_plan* p) {
@@ -94,7 +101,7 @@ int free_workspace(podsdf_df_plan* p) {
 int ensure_core_ws(podsdf_df_plan* p) {
   if (p->ws_chunk != p->chunk) free_workspace(p);
   const DfGeom& g = p->g;
-  if (!p->d_T1) PODSDF_CUDA(cudaMalloc(&p->d_T1, sizeof(double) * 3 * g.Np * (size_t)p->chunk));
+  if (!p->d_T1) PODSDF_CUDA(cudaMalloc(&p->d_T1, sizeof(double) * t1_doubles_per_plane(p) * (size_t)p->chunk));
   if (!use_tuned_plane(p) && !p->d_T2)
     PODSDF_CUDA(cudaMalloc(&p->d_T2, sizeof(double) * 3 * (size_t)g.Jp * g.K * (size_t)p->chunk));
   p->ws_chunk = p->chunk;
@@ -135,9 +142,10 @@ int run_chunk(podsdf_df_plan* p, const double* X_dev, bool gen, uint64_t seed, l
   }
   cudaEvent_t e0 = next_event(p), e1 = next_event(p), e2 = next_event(p);
   PODSDF_CUDA(cudaEventRecord(e0, st));
-  PODSDF_TRY(launch_df_time(p->g, p->bx, X, p->d_T1, nsteps, gen, seed, s_base, tt, st));
+  const PanelGeom pg = panel_of(p);
+  PODSDF_TRY(launch_df_time(p->g, pg, p->bx, X, p->d_T1, nsteps, gen, seed, s_base, tt, st));
   PODSDF_CUDA(cudaEventRecord(e1, st));
-  PODSDF_TRY(launch_df_plane(p->g, p->by, p->bz, p->d_T1, out_dev, nsteps, 3, p->d_coef, p->mask, p->have_coef,
+  PODSDF_TRY(launch_df_plane(p->g, pg, p->by, p->bz, p->d_T1, out_dev, nsteps, 3, p->d_coef, p->mask, p->have_coef,
                              p->d_T2, tp, st));
   PODSDF_CUDA(cudaEventRecord(e2, st));
   return 0;
@@ -281,7 +289,7 @@ int podsdf_df_filter_block_host(podsdf_df_plan* p, const double* x_host, double*
   };
   // layout trick: replicate the block into the 3-component slab layout expected by the time kernel
   PODSDF_CUDA(cudaMalloc(&dX, sizeof(double) * 3 * g.Np * nt));
-  cudaError_t e = cudaMalloc(&dT1, sizeof(double) * 3 * g.Np);
+  cudaError_t e = cudaMalloc(&dT1, sizeof(double) * t1_doubles_per_plane(p));
   if (e == cudaSuccess) e = cudaMalloc(&dT2, sizeof(double) * 3 * (size_t)g.Jp * g.K);
   if (e == cudaSuccess) e = cudaMalloc(&dY, sizeof(double) * 3 * g.P);
   if (e == cudaSuccess) e = cudaMemsetAsync(dX, 0, sizeof(double) * 3 * g.Np * nt, st);
@@ -293,8 +301,9 @@ int podsdf_df_filter_block_host(podsdf_df_plan* p, const double* x_host, double*
     return cuda_fail(e, "filter_block staging", __FILE__, __LINE__);
   }
   const bool tt = use_tuned_time(p), tp = use_tuned_plane(p);
-  rc = launch_df_time(g, p->bx, dX, dT1, 1, false, 0, 0, tt, st);
-  if (!rc) rc = launch_df_plane(g, p->by, p->bz, dT1, dY, 1, 3, nullptr, 0, false, dT2, tp, st);
+  const PanelGeom pg = panel_of(p);
+  rc = launch_df_time(g, pg, p->bx, dX, dT1, 1, false, 0, 0, tt, st);
+  if (!rc) rc = launch_df_plane(g, pg, p->by, p->bz, dT1, dY, 1, 3, nullptr, 0, false, dT2, tp, st);
   if (!rc) {
     e = cudaMemcpyAsync(y_host, dY, sizeof(double) * g.P, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);

@@ -9,10 +9,11 @@
 // B200 design: the contraction is linear and separable, so it is split as
 //   K-time : T1[t] = sum_m bx[m] X[t+m]      per padded point, sliding window of raw randoms in
 //            REGISTERS (one new slab read or Philox-generated per step, each random touched once)
-//   K-plane: out[t] = Lund( by (*) bz (*) T1[t] )   marching down the rows of a 64-column strip:
-//            z-pass from a cp.async-staged row block into a shared-memory ring of z-filtered rows,
-//            y-pass as register-blocked column windows over that ring, fused with the 3x3
-//            Lund/rotation transform and the mean add, so every output plane is written once.
+//   K-plane: out[t] = Lund( by (*) bz (*) T1[t] )   marching along the columns of a 64-row strip:
+//            bulk-copied (cp.async.bulk + mbarrier) 16-column panels of T1, y-pass from the panel
+//            into a shared-memory ring of y-filtered columns, z-pass as register-blocked windows
+//            over that ring, fused with the 3x3 Lund/rotation transform and the mean add, so every
+//            output plane is written once, in 64-byte runs per thread.
 // Both are FP64-FMA work at the DFMA pipe rate with HBM traffic = algorithmic bytes; no GEMM shape.
 #include "df_kernels.cuh"
 #include "philox.cuh"
@@ -23,13 +24,13 @@ namespace podsdf {
 // Philox slabs
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) df_random_slabs_kernel(double* __restrict__ X, long Np, long npair,
-                                                              uint64_t seed, long s0) {
+                                                              const PhiloxKeys keys, long s0) {
   const long pair = blockIdx.x * 256L + threadIdx.x;
   if (pair >= npair) return;
   const int c = blockIdx.y;
   const long s = blockIdx.z;
   double a, b;
-  philox_pair(seed, (uint64_t)pair, (uint64_t)(s0 + s), c, a, b);
+  philox_pair(keys, (uint64_t)pair, (uint64_t)(s0 + s), c, a, b);
   double* dst = X + (s * 3 + c) * Np + 2 * pair;
   dst[0] = a;
   if (2 * pair + 1 < Np) dst[1] = b;
@@ -41,7 +42,7 @@ int launch_df_random_slabs(const DfGeom& g, uint64_t seed, long s0, long n, doub
   for (long done = 0; done < n; done += 32768) {  // gridDim.z limit
     const long cnt = (n - done < 32768) ? n - done : 32768;
     dim3 grid(ceil_div(npair, 256), 3, (unsigned)cnt);
-    df_random_slabs_kernel<<<grid, 256, 0, st>>>(X + done * 3 * g.Np, g.Np, npair, seed, s0 + done);
+    df_random_slabs_kernel<<<grid, 256, 0, st>>>(X + done * 3 * g.Np, g.Np, npair, philox_keys(seed), s0 + done);
     count_launch();
   }
   PODSDF_CUDA(cudaGetLastError());
@@ -51,26 +52,50 @@ int launch_df_random_slabs(const DfGeom& g, uint64_t seed, long s0, long n, doub
 // ------------------------------------------------------------------------------------------------
 // K-time, tuned: window of NT raw randoms per point in registers (static indices via unroll by NT)
 // ------------------------------------------------------------------------------------------------
+// T1 is written either in the canonical plane layout [p][q] (panel.PB == 0) or in the row-panel layout
+// [pb][q][16] the tuned plane kernel bulk-copies from (PanelGeom); thread L owns the two points (p, q), (p, q+1)
+// either way (one Philox call / one 16-byte read), and a warp's writes are whole 128-byte lines in both.
 template <int NT, bool GEN>
 __global__ void __launch_bounds__(256, (NT <= 21 ? 2 : 1))
-df_time_tuned_kernel(const double* __restrict__ X, double* __restrict__ T1, const Taps bx, const long Np,
-                     const long npair, const int nsteps, const int tchunk, const uint64_t seed,
-                     const long s_base) {
-  const long pair = blockIdx.x * 256L + threadIdx.x;
-  if (pair >= npair) return;
+df_time_tuned_kernel(const double* __restrict__ X, double* __restrict__ T1, const Taps bx, const DfGeom g,
+                     const PanelGeom panel, const long nthread, const int nsteps, const int tchunk,
+                     const PhiloxKeys keys, const long s_base) {
+  const long L = blockIdx.x * 256L + threadIdx.x;
+  if (L >= nthread) return;
   const int c = blockIdx.y;
   const int t0 = blockIdx.z * tchunk;
   const int t1 = min(t0 + tchunk, nsteps);
-  const bool has2 = 2 * pair + 1 < Np;
-  const bool vec = (Np & 1) == 0;  // every [s][c] plane stays 16-byte aligned
+  const long Np = g.Np;
+  long ridx, widx, wstride;    // canonical point index (reads / Philox), write offset, write plane stride
+  bool valid, has2, vec;
+  if (panel.PB > 0) {          // panel layout: L = (pb * QP + qp) * 16 + r, two columns q, q+1 of plane row p
+    const int r = (int)(L & 15);
+    const long colp = L >> 4;
+    const int QP = panel.Qpad >> 1;
+    const int pb = (int)(colp / QP), q = 2 * (int)(colp % QP);
+    const int p = pb * 16 + r;
+    valid = (p < g.Jp) && (q < g.Kp);   // Kp is even here: both points of the pair are valid together
+    has2 = valid;
+    vec = true;
+    ridx = (long)p * g.Kp + q;
+    widx = ((long)pb * panel.Qpad + q) * 16 + r;
+    wstride = panel.comp_stride;
+  } else {
+    valid = true;
+    has2 = 2 * L + 1 < Np;
+    vec = (Np & 1) == 0;       // every [s][c] plane stays 16-byte aligned
+    ridx = widx = 2 * L;
+    wstride = Np;
+  }
+  const bool paneled = panel.PB > 0;
   const int last_slab = nsteps + NT - 2;
 
   double w0[NT], w1[NT];
   auto load = [&](int s, double& a, double& b) {
     if (GEN) {
-      philox_pair(seed, (uint64_t)pair, (uint64_t)(s_base + s), c, a, b);
+      philox_pair(keys, (uint64_t)(ridx >> 1), (uint64_t)(s_base + s), c, a, b);
     } else {
-      const double* p = X + ((long)s * 3 + c) * Np + 2 * pair;
+      const double* p = X + ((long)s * 3 + c) * Np + ridx;
       if (vec) {
         const double2 v = __ldcs(reinterpret_cast<const double2*>(p));  // read once: streaming
         a = v.x;
@@ -81,6 +106,14 @@ df_time_tuned_kernel(const double* __restrict__ X, double* __restrict__ T1, cons
       }
     }
   };
+  if (!valid) {                // panel padding: zeros, so the plane kernel never sees garbage
+    for (int t = t0; t < t1; ++t) {
+      double* q = T1 + ((long)t * 3 + c) * wstride + widx;
+      q[0] = 0.0;
+      q[16] = 0.0;
+    }
+    return;
+  }
 #pragma unroll
   for (int i = 0; i < NT - 1; ++i) load(t0 + i, w0[i], w1[i]);
 
@@ -103,8 +136,11 @@ df_time_tuned_kernel(const double* __restrict__ X, double* __restrict__ T1, cons
         }
       }
       if (tt < t1) {
-        double* q = T1 + ((long)tt * 3 + c) * Np + 2 * pair;
-        if (vec) {
+        double* q = T1 + ((long)tt * 3 + c) * wstride + widx;
+        if (paneled) {         // lanes <-> 16 consecutive rows: two coalesced 128-byte lines per half-warp
+          q[0] = a0 + a1;
+          q[16] = b0 + b1;
+        } else if (vec) {
           *reinterpret_cast<double2*>(q) = make_double2(a0 + a1, b0 + b1);
         } else {
           q[0] = a0 + a1;
@@ -139,37 +175,39 @@ bool df_time_has_tuned(int ntx) {
 }
 
 template <int NT>
-static void launch_time_tuned(const Taps& bx, const double* X, double* T1, long Np, int nsteps, bool gen,
-                              uint64_t seed, long s_base, cudaStream_t st) {
-  const long npair = (Np + 1) / 2;
+static void launch_time_tuned(const DfGeom& g, const PanelGeom& panel, const Taps& bx, const double* X, double* T1,
+                              int nsteps, bool gen, uint64_t seed, long s_base, cudaStream_t st) {
+  const long nthread = panel.PB > 0 ? (long)panel.PB * (panel.Qpad / 2) * 16 : (g.Np + 1) / 2;
   // time chunks: enough CTAs to smooth the tail, few enough that the NT-1 slab warm-up stays small
   int nchunk = 1;
-  const long ctas_per_chunk = 3L * ceil_div(npair, 256);
+  const long ctas_per_chunk = 3L * ceil_div(nthread, 256);
   while (nchunk < 64 && ctas_per_chunk * nchunk < 148L * 2 * 8 && nsteps / (nchunk * 2) >= 8 * NT) nchunk *= 2;
   int tchunk = ceil_div(nsteps, nchunk);
   tchunk = ceil_div(tchunk, NT) * NT;
   nchunk = ceil_div(nsteps, tchunk);
-  dim3 grid(ceil_div(npair, 256), 3, nchunk);
+  dim3 grid(ceil_div(nthread, 256), 3, nchunk);
+  const PhiloxKeys keys = philox_keys(seed);
   if (gen)
-    df_time_tuned_kernel<NT, true><<<grid, 256, 0, st>>>(X, T1, bx, Np, npair, nsteps, tchunk, seed, s_base);
+    df_time_tuned_kernel<NT, true><<<grid, 256, 0, st>>>(X, T1, bx, g, panel, nthread, nsteps, tchunk, keys, s_base);
   else
-    df_time_tuned_kernel<NT, false><<<grid, 256, 0, st>>>(X, T1, bx, Np, npair, nsteps, tchunk, seed, s_base);
+    df_time_tuned_kernel<NT, false><<<grid, 256, 0, st>>>(X, T1, bx, g, panel, nthread, nsteps, tchunk, keys, s_base);
   count_launch();
 }
 
-int launch_df_time(const DfGeom& g, const Taps& bx, const double* X, double* T1, int nsteps, bool gen,
-                   uint64_t seed, long s_base, bool tuned, cudaStream_t st) {
+int launch_df_time(const DfGeom& g, const PanelGeom& panel, const Taps& bx, const double* X, double* T1, int nsteps,
+                   bool gen, uint64_t seed, long s_base, bool tuned, cudaStream_t st) {
   if (nsteps <= 0) return 0;
   const int nt = 2 * g.nfx + 1;
   if (tuned) {
     switch (nt) {
-#define F(N) case N: launch_time_tuned<N>(bx, X, T1, g.Np, nsteps, gen, seed, s_base, st); break;
+#define F(N) case N: launch_time_tuned<N>(g, panel, bx, X, T1, nsteps, gen, seed, s_base, st); break;
       PODSDF_TIME_TAPS(F)
 #undef F
       default: return fail(PODSDF_ERR_UNSUPPORTED, "no tuned time-filter kernel for this nfx");
     }
   } else {
     if (gen) return fail(PODSDF_ERR_INVALID, "generic time filter needs materialised slabs");
+    if (panel.PB > 0) return fail(PODSDF_ERR_INVALID, "generic time filter writes the canonical layout only");
     int zt = nsteps < 1024 ? nsteps : 1024;
     dim3 grid(ceil_div(g.Np, 256), 3, zt);
     df_time_generic_kernel<<<grid, 256, 0, st>>>(X, T1, bx, nt, g.Np, nsteps);
@@ -217,96 +255,71 @@ int launch_df_lund(const DfGeom& g, double* planes, const double* coef, unsigned
 }
 
 // ------------------------------------------------------------------------------------------------
-// K-plane, tuned: marching strip kernel
-//   CTA = (64-column strip, plane), 128 threads, marches down the padded rows SJ = 16 at a time:
-//     stage  : cp.async of the 16 new input rows x (64 + NTZ-1) columns x 3 components
-//     z-pass : thread = (row, 8-column segment): 8 outputs from a (8+NTZ-1)-value register window,
-//              written to a shared ring of z-filtered rows (NB blocks of 16 rows)
-//     y-pass : thread = (column, 8-row segment) for all 3 components: register windows down the
-//              ring column; block/row offsets are compile-time (only NB block bases rotate)
-//     Lund   : y = M x + m with the coefficient planes, streaming stores of the finished rows
-//   Odd shared-memory pitches make both lane<->row (z) and lane<->column (y) access conflict free.
-//   Taps live in registers (2 x <=33 doubles); every DFMA has register operands only.
+// K-plane, tuned: row-marching strip kernel over the row-panel layout
+//   CTA = (64-column strip, plane): 4 compute warps + 1 producer warp, marches down the padded rows one
+//   16-row panel per step:
+//     stage  : ONE cp.async.bulk per component ((64 + NTZ-1) columns x 16 rows, contiguous in the panel
+//              layout) completing on an mbarrier, issued by the producer warp
+//     z-pass : thread = (row, 8-column segment) x 3 components: 8 outputs from a (8+NTZ-1)-value register
+//              window along the staged columns (lanes <-> the 16 contiguous rows of a column: conflict
+//              free), written to a shared ring of z-filtered rows (NB blocks of 16 rows, odd pitch)
+//     y-pass : thread = (column, 8-row segment) x 3 components: register windows down the ring column
+//              (lanes <-> consecutive columns: conflict free); block/row offsets are compile-time
+//     Lund   : y = M x + m on the thread's 8 output points; lanes <-> consecutive k, so coefficient loads
+//              and the streaming stores of the finished rows are whole 128-byte lines; for the common
+//              sparsity pattern (PAT 1) the coefficient loads are issued before the y-pass
 // ------------------------------------------------------------------------------------------------
 template <int NTY, int NTZ>
-struct PlaneCfg {
-  static constexpr int TK = 64;    // output columns per strip
-  static constexpr int SJ = 16;    // rows per marching step
-  static constexpr int R = 8;      // outputs per thread along the filtered axis (register window)
-  static constexpr int NTHR = 128;
-  static constexpr int TKIN = TK + NTZ - 1;
-  static constexpr int PIN = TKIN | 1;   // odd pitch: lanes <-> rows are bank-conflict free
-  static constexpr int NB = (SJ + NTY - 1 + SJ - 1) / SJ;  // ring blocks of SJ rows
+struct PanelCfg {
+  static constexpr int TK = 64;     // output columns per strip
+  static constexpr int SJ = 16;     // rows per marching step (= panel height)
+  static constexpr int R = 8;       // outputs per thread along the filtered axis (register window)
+  static constexpr int NCOMPUTE = 128;
+  static constexpr int NTHR = NCOMPUTE + 32;                 // + producer warp
+  static constexpr int TKIN = TK + NTZ - 1;                  // staged columns
+  static constexpr int NB = (SJ + NTY - 1 + SJ - 1) / SJ;    // ring blocks of SJ rows
   static constexpr int RJ = NB * SJ;
-  static constexpr int PT2 = TK + 1;
-  static constexpr int STAGE = 3 * SJ * PIN;
-  static constexpr int RING = 3 * RJ * PT2;
-  static constexpr size_t SMEM = (size_t)(STAGE + RING) * sizeof(double);
-  static constexpr int QL = (TKIN + 31) / 32;  // cp.async per lane per staged row
-  static_assert(SJ * (TK / R) == NTHR, "z-pass: one item per thread per component");
-  static_assert(TK * (SJ / R) == NTHR, "y-pass: one item per thread");
+  static constexpr int PK = TK + 1;                          // ring pitch (odd)
+  static constexpr int STAGE = 3 * TKIN * SJ;                // doubles
+  static constexpr int RING = 3 * RJ * PK;
+  static constexpr size_t SMEM = (size_t)(STAGE + RING) * sizeof(double) + 16;
+  static constexpr unsigned COPY_BYTES = TKIN * SJ * sizeof(double);
+  static_assert(SJ * (TK / R) == NCOMPUTE, "z-pass: one item per thread");
+  static_assert(TK * (SJ / R) == NCOMPUTE, "y-pass: one item per thread");
+  static_assert(COPY_BYTES % 16 == 0, "bulk copy size");
   static_assert(SMEM <= 113 * 1024, "two CTAs per SM");
 };
 
-__device__ __forceinline__ void cp_async8(unsigned smem_dst, const double* gsrc, bool valid) {
-  const int bytes = valid ? 8 : 0;  // src-size 0 => zero fill
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(smem_dst), "l"(gsrc), "r"(bytes) : "memory");
+__device__ __forceinline__ void mbar_init(unsigned mbar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(mbar), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
 }
-__device__ __forceinline__ void cp_async_commit_wait_all() {
-  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+__device__ __forceinline__ void mbar_expect_tx(unsigned mbar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(mbar), "r"(bytes) : "memory");
 }
-
-// Lund / rotation epilogue of one y-pass item: rows o in [olo, ohi) of column k, all 3 components.
-// Plane-major so each mask bit is tested once per item; GUARD = item straddles the plane edge.
-template <int R, bool GUARD>
-__device__ __forceinline__ void plane_epilogue(const double (&f)[3][R], double* __restrict__ dstp,
-                                               const double* __restrict__ coef, const unsigned mask,
-                                               const int lund, const long P, const int K, const int pt0,
-                                               const int olo, const int ohi) {
-  int pt[R];
-#pragma unroll
-  for (int o = 0; o < R; ++o) pt[o] = pt0 + ((GUARD && (o < olo || o >= ohi)) ? olo : o) * K;
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    double y[R];
-    if (lund) {
-#pragma unroll
-      for (int o = 0; o < R; ++o) y[o] = 0.0;
-#pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        if (mask & (1u << (3 * c + d))) {
-          const double* cp = coef + (long)(3 * c + d) * P;
-#pragma unroll
-          for (int o = 0; o < R; ++o) y[o] = fma(__ldg(cp + pt[o]), f[d][o], y[o]);
-        }
-      }
-      if (mask & (1u << (9 + c))) {
-        const double* cp = coef + (long)(9 + c) * P;
-#pragma unroll
-        for (int o = 0; o < R; ++o) y[o] += __ldg(cp + pt[o]);
-      }
-    } else {
-#pragma unroll
-      for (int o = 0; o < R; ++o) y[o] = f[c][o];
-    }
-    double* op = dstp + (long)c * P;
-#pragma unroll
-    for (int o = 0; o < R; ++o)
-      if (!GUARD || (o >= olo && o < ohi)) __stcs(op + pt[o], y[o]);
-  }
+__device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(mbar), "r"(parity) : "memory");
 }
-
-// keep a value in a (non-uniform) register: stops ptxas from re-fetching taps from the constant
-// bank / uniform registers inside the marching loop
-__device__ __forceinline__ void pin_reg(double& v) { asm volatile("" : "+d"(v)); }
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned mbar) {
+  asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
 
 // y-pass of one thread: column kk, output rows j0 .. j0+R-1 (j0 = n*SJ - (NTY-1) + SG*R), 3 comps.
 // blk[d] = ring base (component 0, column kk) of the block written d steps ago.
 template <int NTY, int NTZ, int SG>
-__device__ __forceinline__ void plane_ypass(const double* const (&blk)[PlaneCfg<NTY, NTZ>::NB],
-                                            const double (&ty)[NTY], double (&f)[3][PlaneCfg<NTY, NTZ>::R]) {
-  using C = PlaneCfg<NTY, NTZ>;
-  constexpr int R = C::R, SJ = C::SJ, PT2 = C::PT2, RJ = C::RJ;
+__device__ __forceinline__ void panel_ypass(const double* const (&blk)[PanelCfg<NTY, NTZ>::NB], const Taps& by,
+                                            double (&f)[3][PanelCfg<NTY, NTZ>::R]) {
+  using C = PanelCfg<NTY, NTZ>;
+  constexpr int R = C::R, SJ = C::SJ, PK = C::PK, RJ = C::RJ;
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
 #pragma unroll
@@ -315,121 +328,161 @@ __device__ __forceinline__ void plane_ypass(const double* const (&blk)[PlaneCfg<
       const int off = i + SG * R - D;                       // row relative to n*SJ (compile time)
       const int d = (off >= 0) ? 0 : (-off + SJ - 1) / SJ;  // blocks back
       const int row = off + d * SJ;                         // row inside that block
-      const double v = blk[d][(c * RJ + row) * PT2];
+      const double v = blk[d][(c * RJ + row) * PK];
 #pragma unroll
       for (int o = 0; o < R; ++o) {
         const int m = i - o;
-        if (m == 0) f[c][o] = ty[NTY - 1] * v;
-        else if (m > 0 && m < NTY) f[c][o] = fma(ty[NTY - 1 - m], v, f[c][o]);
+        if (m == 0) f[c][o] = by.b[NTY - 1] * v;
+        else if (m > 0 && m < NTY) f[c][o] = fma(by.b[NTY - 1 - m], v, f[c][o]);
       }
     }
   }
 }
 
-template <int NTY, int NTZ>
-__global__ void __launch_bounds__(128, 2)
-df_plane_tuned_kernel(const double* __restrict__ T1, double* __restrict__ out, const Taps by, const Taps bz,
-                      const DfGeom g, const double* __restrict__ coef, const unsigned mask, const int lund) {
-  using C = PlaneCfg<NTY, NTZ>;
-  constexpr int TK = C::TK, SJ = C::SJ, R = C::R, PIN = C::PIN, RJ = C::RJ, PT2 = C::PT2, NB = C::NB;
-  extern __shared__ double smem[];
-  double* stage = smem;
-  double* ring = smem + C::STAGE;
+// coefficient patterns with a specialised epilogue
+//   PAT 0: no transform (identity), PAT 1: mask within {M00, M11, M20, M22, m0} -- adapt1d / adapt2d
+//   without a rotation (digitalfilters.py:143-178, 233-485), PAT 2: anything (full 3x3 + means)
+constexpr unsigned kPat1Mask = (1u << 0) | (1u << 4) | (1u << 6) | (1u << 8) | (1u << 9);
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+template <int NTY, int NTZ, int PAT>
+__global__ void __launch_bounds__(160, 2)
+df_plane_panel_kernel(const double* __restrict__ T1, double* __restrict__ out, const Taps by, const Taps bz,
+                      const DfGeom g, const PanelGeom panel, const double* __restrict__ coef, const unsigned mask) {
+  using C = PanelCfg<NTY, NTZ>;
+  constexpr int TK = C::TK, SJ = C::SJ, R = C::R, TKIN = C::TKIN, RJ = C::RJ, PK = C::PK, NB = C::NB;
+  extern __shared__ __align__(128) double smem[];
+  double* stage = smem;                      // [3][TKIN][SJ]
+  double* ring = smem + C::STAGE;            // [3][RJ][PK]
+  const unsigned mbar = (unsigned)__cvta_generic_to_shared(smem + C::STAGE + C::RING);
+
+  const int tid = threadIdx.x;
   const int k0 = blockIdx.x * TK;
   const long plane = blockIdx.y;
-  const double* src = T1 + plane * 3 * g.Np;
-  double* dstp = out + plane * 3 * g.P;
-  const int nsteps = (g.Jp + SJ - 1) / SJ;
+  const int nsteps = panel.PB;
 
-  double ty[NTY], tz[NTZ];
-#pragma unroll
-  for (int m = 0; m < NTY; ++m) { ty[m] = by.b[m]; pin_reg(ty[m]); }
-#pragma unroll
-  for (int m = 0; m < NTZ; ++m) { tz[m] = bz.b[m]; pin_reg(tz[m]); }
+  if (tid == 0) mbar_init(mbar, 1);
+  __syncthreads();
 
-  // staging: warp w copies rows rc = w + 4*it (rc = c*SJ + r  =>  c = it/4, r = w + 4*(it%4));
-  // out-of-range rows / columns are zero-filled (cp.async src-size 0, address never dereferenced)
-  const unsigned stage_s = (unsigned)__cvta_generic_to_shared(stage) + (unsigned)((warp * PIN + lane) * 8);
-  const long row4 = 4L * g.Kp;
-  bool colok[C::QL];
+  if (tid >= C::NCOMPUTE) {
+    // ---- producer warp: one lane issues the three bulk copies of every step and follows the barriers
+    const unsigned stage_s = (unsigned)__cvta_generic_to_shared(stage);
+    const double* src = T1 + plane * 3 * panel.comp_stride + (long)k0 * SJ;   // panel 0, first staged column
+    const long panel_stride = (long)panel.Qpad * SJ;
+    auto issue = [&](int n) {
+      if (tid == C::NCOMPUTE) {
+        mbar_expect_tx(mbar, 3 * C::COPY_BYTES);
 #pragma unroll
-  for (int jj = 0; jj < C::QL; ++jj) colok[jj] = (lane + 32 * jj < C::TKIN) && (k0 + lane + 32 * jj < g.Kp);
-  const double* gstage = src + (long)warp * g.Kp + k0 + lane;  // advanced by SJ rows per step
-  auto issue_stage = [&](int n) {
-    const int rows_left = g.Jp - n * SJ - warp;  // row r = warp + 4*rr valid iff 4*rr < rows_left
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const double* gr = gstage + (long)c * g.Np;
-#pragma unroll
-      for (int rr = 0; rr < SJ / 4; ++rr) {
-        const bool rowok = 4 * rr < rows_left;
-#pragma unroll
-        for (int jj = 0; jj < C::QL; ++jj) {
-          if (lane + 32 * jj < C::TKIN)
-            cp_async8(stage_s + (unsigned)(((4 * (c * (SJ / 4) + rr)) * PIN + 32 * jj) * 8), gr + 32 * jj,
-                      rowok && colok[jj]);
-        }
-        gr += row4;
+        for (int c = 0; c < 3; ++c)
+          bulk_g2s(stage_s + c * C::COPY_BYTES, src + c * panel.comp_stride + n * panel_stride, C::COPY_BYTES, mbar);
       }
+    };
+    issue(0);
+    for (int n = 0; n < nsteps; ++n) {
+      __syncthreads();                // (A) the compute warps have consumed stage n
+      if (n + 1 < nsteps) {
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic reads before async writes
+        issue(n + 1);
+      }
+      __syncthreads();                // (B)
     }
-    gstage += (long)SJ * g.Kp;
-  };
+    return;
+  }
 
-  // z-pass role: row r, column segment sgm
+  double* dstp = out + plane * 3 * g.P;
+  // z-pass role: panel row zr, column segment zs
   const int zr = tid & (SJ - 1), zs = tid / SJ;
-  const double* zsrc = stage + zr * PIN + zs * R;
-  double* zdst = ring + zr * PT2 + zs * R;
-  // y-pass role: column kk, row segment sg
+  const double* zsrc = stage + (zs * R) * SJ + zr;
+  double* zdst = ring + zr * PK + zs * R;
+  // y-pass role: strip column kk, row segment sg
   const int kk = tid & (TK - 1), sg = tid / TK;
   const int k = k0 + kk;
+  const bool kok = k < g.K;
 
-  issue_stage(0);
   for (int n = 0; n < nsteps; ++n) {
-    cp_async_commit_wait_all();
-    __syncthreads();  // stage(n) landed; previous y-pass done with the ring block rewritten now
+    mbar_wait(mbar, n & 1);           // panel n has landed
     const int bn = n % NB;
+    {
+      double acc[3][R];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const double* srow = zsrc + c * SJ * PIN;
-      double acc[R];
+      for (int c = 0; c < 3; ++c) {
+        const double* col = zsrc + c * TKIN * SJ;
 #pragma unroll
-      for (int i = 0; i < NTZ + R - 1; ++i) {
-        const double v = srow[i];
+        for (int i = 0; i < NTZ + R - 1; ++i) {
+          const double v = col[i * SJ];
 #pragma unroll
-        for (int o = 0; o < R; ++o) {
-          const int m = i - o;
-          if (m == 0) acc[o] = tz[NTZ - 1] * v;
-          else if (m > 0 && m < NTZ) acc[o] = fma(tz[NTZ - 1 - m], v, acc[o]);
+          for (int o = 0; o < R; ++o) {
+            const int m = i - o;
+            if (m == 0) acc[c][o] = bz.b[NTZ - 1] * v;
+            else if (m > 0 && m < NTZ) acc[c][o] = fma(bz.b[NTZ - 1 - m], v, acc[c][o]);
+          }
         }
       }
-      double* dst = zdst + (c * RJ + bn * SJ) * PT2;
 #pragma unroll
-      for (int o = 0; o < R; ++o) dst[o] = acc[o];
-    }
-    __syncthreads();  // ring block of this step complete, stage free
-    if (n + 1 < nsteps) issue_stage(n + 1);
-
-    const int j0 = n * SJ - (NTY - 1) + sg * R;
-    if (j0 + R > 0 && j0 < g.J) {
-      const double* blk[NB];
+      for (int c = 0; c < 3; ++c) {   // stores after all loads: no load is ordered behind a store
+        double* dst = zdst + (c * RJ + bn * SJ) * PK;
 #pragma unroll
-      for (int d = 0; d < NB; ++d) blk[d] = ring + ((n + NB - d) % NB) * SJ * PT2 + kk;
-      double f[3][R];
-      if (sg == 0)
-        plane_ypass<NTY, NTZ, 0>(blk, ty, f);
-      else
-        plane_ypass<NTY, NTZ, 1>(blk, ty, f);
-      if (k < g.K) {
-        // 32-bit point indices (P < 2^31): one IMAD.WIDE per access instead of 64-bit pointer chains
-        const int pt0 = j0 * g.K + k;
-        if (j0 >= 0 && j0 + R <= g.J)
-          plane_epilogue<R, false>(f, dstp, coef, mask, lund, g.P, g.K, pt0, 0, R);
-        else
-          plane_epilogue<R, true>(f, dstp, coef, mask, lund, g.P, g.K, pt0, max(0, -j0), min(R, g.J - j0));
+        for (int o = 0; o < R; ++o) dst[o] = acc[c][o];
       }
     }
+    __syncthreads();                  // (A) ring block n complete; the stage is free for panel n+1
+
+    const int j0 = n * SJ - (NTY - 1) + sg * R;
+    const bool item = (j0 + R > 0) && (j0 < g.J);
+    const bool fast = item && kok && (j0 >= 0) && (j0 + R <= g.J);
+    const int pt0 = j0 * g.K + k;
+    double cf[5][R];
+    if (PAT == 1) {                   // coefficient loads in flight during the y-pass
+      constexpr int bit[5] = {0, 4, 6, 8, 9};
+#pragma unroll
+      for (int q = 0; q < 5; ++q) {
+        if (fast && (mask & (1u << bit[q]))) {
+          const double* cp = coef + (long)bit[q] * g.P + pt0;
+#pragma unroll
+          for (int o = 0; o < R; ++o) cf[q][o] = __ldg(cp + (long)o * g.K);
+        } else {
+#pragma unroll
+          for (int o = 0; o < R; ++o) cf[q][o] = 0.0;
+        }
+      }
+    }
+    if (item) {
+      const double* blk[NB];
+#pragma unroll
+      for (int d = 0; d < NB; ++d) blk[d] = ring + ((n + NB - d) % NB) * SJ * PK + kk;
+      double f[3][R];
+      if (sg == 0)
+        panel_ypass<NTY, NTZ, 0>(blk, by, f);
+      else
+        panel_ypass<NTY, NTZ, 1>(blk, by, f);
+      if (fast && PAT <= 1) {
+#pragma unroll
+        for (int o = 0; o < R; ++o) {
+          double y0 = f[0][o], y1 = f[1][o], y2 = f[2][o];
+          if (PAT == 1) {
+            y0 = fma(cf[0][o], f[0][o], cf[4][o]);
+            y1 = cf[1][o] * f[1][o];
+            y2 = fma(cf[3][o], f[2][o], cf[2][o] * f[0][o]);
+          }
+          double* op = dstp + pt0 + (long)o * g.K;
+          __stcs(op, y0);
+          __stcs(op + g.P, y1);
+          __stcs(op + 2 * g.P, y2);
+        }
+      } else if (kok) {               // general pattern, or a strip edge: guarded
+#pragma unroll
+        for (int o = 0; o < R; ++o) {
+          const int j = j0 + o;
+          if (j >= 0 && j < g.J) {
+            const int pt = pt0 + o * g.K;
+            double y[3] = {f[0][o], f[1][o], f[2][o]};
+            if (PAT != 0) lund_point(coef, mask, g.P, pt, f[0][o], f[1][o], f[2][o], y);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) __stcs(dstp + (long)c * g.P + pt, y[c]);
+          }
+        }
+      }
+    }
+    __syncthreads();                  // (B) y-pass done with the ring block the next z-pass overwrites
   }
 }
 
@@ -481,11 +534,19 @@ bool df_plane_has_tuned(int nty, int ntz) {
   return false;
 }
 
-template <int NTY, int NTZ>
-static int launch_plane_tuned(const DfGeom& g, const Taps& by, const Taps& bz, const double* T1, double* out,
-                              int nplanes, const double* coef, unsigned mask, bool lund, cudaStream_t st) {
-  using C = PlaneCfg<NTY, NTZ>;
-  auto kern = df_plane_tuned_kernel<NTY, NTZ>;
+PanelGeom make_panel_geom(const DfGeom& g) {
+  PanelGeom p;
+  p.PB = (g.Jp + 15) / 16;
+  p.Qpad = ((g.K + 63) / 64) * 64 + 2 * g.nfz;
+  p.comp_stride = (long)p.PB * p.Qpad * 16;
+  return p;
+}
+
+template <int NTY, int NTZ, int PAT>
+static int launch_plane_panel(const DfGeom& g, const PanelGeom& panel, const Taps& by, const Taps& bz, const double* T1,
+                              double* out, int nplanes, const double* coef, unsigned mask, cudaStream_t st) {
+  using C = PanelCfg<NTY, NTZ>;
+  auto kern = df_plane_panel_kernel<NTY, NTZ, PAT>;
   static bool configured[64] = {};
   int dev = 0;
   PODSDF_CUDA(cudaGetDevice(&dev));
@@ -496,24 +557,29 @@ static int launch_plane_tuned(const DfGeom& g, const Taps& by, const Taps& bz, c
   for (int done = 0; done < nplanes; done += 65535) {
     const int cnt = (nplanes - done < 65535) ? nplanes - done : 65535;
     dim3 grid(ceil_div(g.K, C::TK), cnt);
-    kern<<<grid, C::NTHR, C::SMEM, st>>>(T1 + (long)done * 3 * g.Np, out + (long)done * 3 * g.P, by, bz, g, coef,
-                                         mask, lund ? 1 : 0);
+    kern<<<grid, C::NTHR, C::SMEM, st>>>(T1 + (long)done * 3 * panel.comp_stride, out + (long)done * 3 * g.P, by, bz, g,
+                                         panel, coef, mask);
     count_launch();
   }
   PODSDF_CUDA(cudaGetLastError());
   return 0;
 }
 
-int launch_df_plane(const DfGeom& g, const Taps& by, const Taps& bz, const double* T1, double* out, int nplanes,
-                    int ncomp, const double* coef, unsigned mask, bool lund, double* T2, bool tuned,
-                    cudaStream_t st) {
+int launch_df_plane(const DfGeom& g, const PanelGeom& panel, const Taps& by, const Taps& bz, const double* T1,
+                    double* out, int nplanes, int ncomp, const double* coef, unsigned mask, bool lund, double* T2,
+                    bool tuned, cudaStream_t st) {
   if (nplanes <= 0) return 0;
   if (lund && ncomp != 3) return fail(PODSDF_ERR_INVALID, "Lund transform needs 3 components");
   const int nty = 2 * g.nfy + 1, ntz = 2 * g.nfz + 1;
   if (tuned) {
-    if (ncomp != 3) return fail(PODSDF_ERR_UNSUPPORTED, "tuned plane kernel handles 3 components");
-#define F(A, B) \
-  if (nty == A && ntz == B) return launch_plane_tuned<A, B>(g, by, bz, T1, out, nplanes, coef, mask, lund, st);
+    if (ncomp != 3 || panel.PB == 0) return fail(PODSDF_ERR_UNSUPPORTED, "tuned plane kernel: 3 components, panel layout");
+    const int pat = !lund ? 0 : ((mask & ~kPat1Mask) == 0 ? 1 : 2);
+#define F(A, B)                                                                                            \
+  if (nty == A && ntz == B) {                                                                              \
+    if (pat == 0) return launch_plane_panel<A, B, 0>(g, panel, by, bz, T1, out, nplanes, coef, mask, st);  \
+    if (pat == 1) return launch_plane_panel<A, B, 1>(g, panel, by, bz, T1, out, nplanes, coef, mask, st);  \
+    return launch_plane_panel<A, B, 2>(g, panel, by, bz, T1, out, nplanes, coef, mask, st);                \
+  }
     PODSDF_PLANE_TAPS(F)
 #undef F
     return fail(PODSDF_ERR_UNSUPPORTED, "no tuned plane-filter kernel for this (nfy, nfz)");

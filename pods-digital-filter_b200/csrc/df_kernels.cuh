@@ -16,20 +16,31 @@ struct DfGeom {
   long Np, P;     // Jp*Kp, J*K
 };
 
+// Row-panel layout of the workspace T1 between the two tuned kernels: [t][c][pb][q][16], i.e. panels of 16
+// plane rows; inside a panel the 16 rows of one column q are contiguous (128 bytes) and columns follow each
+// other, so the (64 + 2 nfz) columns x 16 rows a strip needs per marching step are ONE contiguous run.
+// PB == 0 means the canonical [p][q] layout.
+struct PanelGeom {
+  int PB = 0;            // number of 16-row panels covering Jp
+  int Qpad = 0;          // columns per panel: 64*ceil(K/64) + 2 nfz (every 64-column strip can read its window)
+  long comp_stride = 0;  // doubles per (plane, component) = PB * Qpad * 16
+};
+PanelGeom make_panel_geom(const DfGeom& g);
+
 // true when a tuned (compile-time tap count) kernel exists for this size
 bool df_time_has_tuned(int ntx);
 bool df_plane_has_tuned(int nty, int ntz);
 
 // T1[t] = sum_m bx[m] X[t + (NTX-1-m)] for t in [0, nsteps);  X has nsteps + NTX - 1 slabs.
 // gen != 0: X is ignored and slab s is Philox(seed, s_base + s) (generated mode, tuned kernels only).
-int launch_df_time(const DfGeom& g, const Taps& bx, const double* X, double* T1, int nsteps, bool gen,
-                   uint64_t seed, long s_base, bool tuned, cudaStream_t st);
+int launch_df_time(const DfGeom& g, const PanelGeom& panel, const Taps& bx, const double* X, double* T1, int nsteps,
+                   bool gen, uint64_t seed, long s_base, bool tuned, cudaStream_t st);
 
 // out[t][c][j][k] = sum_c' M[c][c'] * (by (*) bz (*) T1[t][c'])[j][k] + m[c]   for t in [0, nplanes)
 // ncomp_in = 3 normally; lund = false writes the filtered field unchanged (coef ignored).
 // T2 is the generic path's workspace [nplanes][3][Jp][K] (may be null for the tuned path).
-int launch_df_plane(const DfGeom& g, const Taps& by, const Taps& bz, const double* T1, double* out,
-                    int nplanes, int ncomp, const double* coef, unsigned mask, bool lund, double* T2,
+int launch_df_plane(const DfGeom& g, const PanelGeom& panel, const Taps& by, const Taps& bz, const double* T1,
+                    double* out, int nplanes, int ncomp, const double* coef, unsigned mask, bool lund, double* T2,
                     bool tuned, cudaStream_t st);
 
 // in-place y = M x + m on three planes (backs adapt*): planes[3][P]
