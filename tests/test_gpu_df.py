@@ -246,3 +246,32 @@ def test_device_pointer_entries_and_kernel_timers(P):
     torch.cuda.synchronize()
     assert torch.equal(out, out2)
     assert P._capi.launch_count() > 0
+
+
+@pytest.mark.parametrize("tag", ["default", "rotated", "roundjet", "dt"])
+def test_cli_main_is_a_drop_in(P, tag, tmp_path, monkeypatch):
+    """`digitalfilters.main()` with the reference's own flags and a seeded global np.random reproduces what the
+    reference's main() produced (golden): snapshot matrix, mean field, POD modes up to sign, PODFS.dat."""
+    g = golden("main_%s.npz" % tag)
+    monkeypatch.chdir(tmp_path)
+    np.random.seed(int(g["in_seed"]))
+    i_d = P.digitalfilters.main([str(a) for a in g["in_argv"]])
+    assert rel_err(i_d.mean_field, g["out_mean_field"]) < 1e-13
+    nm = int(g["out_nm"])
+    assert i_d.nm == nm
+    tm_ref = g["out_temporal_modes"].real[:, :nm]
+    sign = np.sign(np.sum(i_d.temporal_modes[:, :nm] * tm_ref, axis=0))
+    lam = np.mean(tm_ref ** 2, axis=0)
+    # the last kept modes of these tiny cases sit close to each other: bound scaled by the relative gap
+    gap = np.minimum(np.abs(np.diff(np.r_[lam, 0.0])), np.abs(np.diff(np.r_[np.inf, lam]))) / lam[0]
+    err = np.abs(i_d.temporal_modes[:, :nm] * sign - tm_ref).max(axis=0) / np.abs(tm_ref).max(axis=0)
+    assert (err < 1e-10 / np.maximum(gap, 1e-4)).all()
+    err = np.abs(i_d.spatial_modes * sign - g["out_spatial_modes"]).max(axis=0) / np.abs(g["out_spatial_modes"]).max(axis=0)
+    assert (err < 1e-10 / np.maximum(gap, 1e-4)).all()
+    for name in ["PODFS/PODFS.dat", "PODFS/PODFS_mean.prf", "PODFS/POD.eigenvalues.dat", "PODFS/PODFS_mode_%04d.prf" % nm]:
+        assert (tmp_path / name).exists(), name
+    dat = (tmp_path / "PODFS" / "PODFS.dat").read_text().split("\n")
+    ref = str(g["out_podfs_dat"]).split("\n")
+    assert dat[:2 + nm] == ref[:2 + nm]                  # mode count, period, coefficients kept per mode
+    assert len(dat) == len(ref)
+    assert [l.split("\t")[0] for l in dat] == [l.split("\t")[0] for l in ref]     # same harmonics in the same order
