@@ -286,7 +286,7 @@ def main():
     hbm_peak, hbm_src = measured_peaks()
     achieved = b_plane * n_planes / (t_plane_ms * 1e-3) / 1e9
     roofline = {
-        "kernel": "df_plane_tuned_kernel (z-pass + y-pass + Lund, fused)" if plan_is_tuned(pkg, nf) else "df generic plane kernels",
+        "kernel": "df_plane_panel_kernel (z-pass + y-pass + Lund/rotation + mean, fused)" if plan_is_tuned(pkg, nf) else "df generic plane kernels",
         "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
         "peak_source": hbm_src, "traffic": None,
         "algorithmic_bytes_per_plane": b_plane, "planes_per_launch": min(n_planes, 512),

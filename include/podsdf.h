@@ -123,9 +123,10 @@ PODSDF_API int podsdf_gram_dev(int device, const double* A_dev, long M, long N, 
 /* device time (ms) of the last Gram kernel on this thread */
 PODSDF_API int podsdf_gram_last_ms(double* ms);
 
-/* ref: linalg.eig(C) POD:1309 on the exactly symmetric C.  Ascending eigenvalues lambda[N] and
- * orthonormal eigenvectors V[N][N] (column j of the row-major V is eigenvector j).  The sort /
- * NaN guard / validity count / scaling of POD:1310-1327, 1430-1447 stay in the Python shim. */
+/* ref: linalg.eig(C) POD:1309 on the exactly symmetric C.  Ascending eigenvalues lambda[N] and orthonormal
+ * eigenvectors.  `_host`: V_host[N][N] row-major with eigenvector j in COLUMN j (numpy's convention).
+ * `_dev`: in place -- on exit ROW j of C_dev_inout_V is eigenvector j (no transpose pass).
+ * The sort / NaN guard / validity count / scaling of POD:1310-1327, 1430-1447 stay in the Python shim. */
 PODSDF_API int podsdf_eig_sym_host(int device, const double* C_host, long N, double* lambda_host, double* V_host);
 PODSDF_API int podsdf_eig_sym_dev(int device, double* C_dev_inout_V, long N, double* lambda_dev, void* stream);
 
