@@ -18,6 +18,8 @@
 #include "df_kernels.cuh"
 #include "philox.cuh"
 
+#include <type_traits>
+
 namespace podsdf {
 
 // ------------------------------------------------------------------------------------------------
@@ -343,6 +345,7 @@ __device__ __forceinline__ void panel_ypass(const double* const (&blk)[PanelCfg<
 //   PAT 0: no transform (identity), PAT 1: mask within {M00, M11, M20, M22, m0} -- adapt1d / adapt2d
 //   without a rotation (digitalfilters.py:143-178, 233-485), PAT 2: anything (full 3x3 + means)
 constexpr unsigned kPat1Mask = (1u << 0) | (1u << 4) | (1u << 6) | (1u << 8) | (1u << 9);
+constexpr unsigned kOffDiagMask = (1u << 1) | (1u << 2) | (1u << 3) | (1u << 5) | (1u << 6) | (1u << 7);
 
 template <int NTY, int NTZ, int PAT>
 __global__ void __launch_bounds__(160, 2)
@@ -486,6 +489,158 @@ df_plane_panel_kernel(const double* __restrict__ T1, double* __restrict__ out, c
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// K-plane, tuned, DIAGONAL transform: when M is diagonal (no shear stress, no rotation -- the default
+// `build_profile` inlet, digitalfilters.py:1038-1062 with the default plane normal) the three components
+// never meet, so each (strip, plane, component) is its own CTA: a third of the shared memory (36 KB),
+// 4-5 resident CTAs per SM instead of 2, i.e. twice the warps to hide LDS latency and barriers.
+// Same stage / z-pass / y-pass structure as df_plane_panel_kernel.
+// ------------------------------------------------------------------------------------------------
+template <int NTY, int NTZ>
+struct Panel1Cfg {
+  using B = PanelCfg<NTY, NTZ>;
+  static constexpr int STAGE = B::TKIN * B::SJ;
+  static constexpr int RING = B::RJ * B::PK;
+  static constexpr size_t SMEM = (size_t)(STAGE + RING) * sizeof(double) + 16;
+};
+
+template <int NTY, int NTZ>
+__global__ void __launch_bounds__(128, 6)
+df_plane_panel1_kernel(const double* __restrict__ T1, double* __restrict__ out, const Taps by, const Taps bz,
+                       const DfGeom g, const PanelGeom panel, const double* __restrict__ coef, const unsigned mask,
+                       const int lund) {
+  using C = PanelCfg<NTY, NTZ>;
+  using C1 = Panel1Cfg<NTY, NTZ>;
+  constexpr int TK = C::TK, SJ = C::SJ, R = C::R, RJ = C::RJ, PK = C::PK, NB = C::NB;
+  extern __shared__ __align__(128) double smem[];
+  double* stage = smem;                       // [TKIN][SJ]
+  double* ring = smem + C1::STAGE;            // [RJ][PK]
+  const unsigned mbar = (unsigned)__cvta_generic_to_shared(smem + C1::STAGE + C1::RING);
+
+  const int tid = threadIdx.x;
+  const int k0 = blockIdx.x * TK;
+  const long pc = blockIdx.y;                 // plane * 3 + component
+  const int comp = (int)(pc % 3);
+  const int nsteps = panel.PB;
+
+  // no producer warp here (it would cost every CTA a fifth of its registers): thread 0 issues the one bulk copy
+  const unsigned stage_s = (unsigned)__cvta_generic_to_shared(stage);
+  const double* src = T1 + pc * panel.comp_stride + (long)k0 * SJ;
+  const long panel_stride = (long)panel.Qpad * SJ;
+  if (tid == 0) {
+    mbar_init(mbar, 1);
+    mbar_expect_tx(mbar, C::COPY_BYTES);
+    bulk_g2s(stage_s, src, C::COPY_BYTES, mbar);
+  }
+  __syncthreads();
+
+  double* dstp = out + pc * g.P;
+  const int zr = tid & (SJ - 1), zs = tid / SJ;
+  const double* zsrc = stage + (zs * R) * SJ + zr;
+  double* zdst = ring + zr * PK + zs * R;
+  const int kk = tid & (TK - 1), sg = tid / TK;
+  const int k = k0 + kk;
+  const bool kok = k < g.K;
+  const bool has_m = lund && (mask & (1u << (4 * comp)));       // M_cc plane present
+  const bool has_b = lund && (mask & (1u << (9 + comp)));       // mean plane present
+  const double* cm = coef + (long)(4 * comp) * g.P;
+  const double* cb = coef + (long)(9 + comp) * g.P;
+
+  for (int n = 0; n < nsteps; ++n) {
+    mbar_wait(mbar, n & 1);
+    const int bn = n % NB;
+    {
+      double acc[R];
+#pragma unroll
+      for (int i = 0; i < NTZ + R - 1; ++i) {
+        const double v = zsrc[i * SJ];
+#pragma unroll
+        for (int o = 0; o < R; ++o) {
+          const int m = i - o;
+          if (m == 0) acc[o] = bz.b[NTZ - 1] * v;
+          else if (m > 0 && m < NTZ) acc[o] = fma(bz.b[NTZ - 1 - m], v, acc[o]);
+        }
+      }
+      double* dst = zdst + (bn * SJ) * PK;
+#pragma unroll
+      for (int o = 0; o < R; ++o) dst[o] = acc[o];
+    }
+    __syncthreads();
+    if (tid == 0 && n + 1 < nsteps) {
+      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic reads before async writes
+      mbar_expect_tx(mbar, C::COPY_BYTES);
+      bulk_g2s(stage_s, src + (n + 1) * panel_stride, C::COPY_BYTES, mbar);
+    }
+
+    const int j0 = n * SJ - (NTY - 1) + sg * R;
+    const bool item = (j0 + R > 0) && (j0 < g.J) && kok;
+    const bool fast = item && (j0 >= 0) && (j0 + R <= g.J);
+    const int pt0 = j0 * g.K + k;
+    double cfm[R], cfb[R];
+#pragma unroll
+    for (int o = 0; o < R; ++o) {     // coefficient loads in flight during the y-pass
+      const bool ok = fast || (item && j0 + o >= 0 && j0 + o < g.J);
+      cfm[o] = (ok && has_m) ? __ldg(cm + pt0 + (long)o * g.K) : (lund ? 0.0 : 1.0);
+      cfb[o] = (ok && has_b) ? __ldg(cb + pt0 + (long)o * g.K) : 0.0;
+    }
+    if (item) {
+      double f[R];
+      const double* blk[NB];
+#pragma unroll
+      for (int d = 0; d < NB; ++d) blk[d] = ring + ((n + NB - d) % NB) * SJ * PK + kk;
+      auto ypass = [&](auto SGc) {
+        constexpr int SG = decltype(SGc)::value;
+#pragma unroll
+        for (int i = 0; i < NTY + R - 1; ++i) {
+          constexpr int D = NTY - 1;
+          const int off = i + SG * R - D;
+          const int d = (off >= 0) ? 0 : (-off + SJ - 1) / SJ;
+          const int row = off + d * SJ;
+          const double v = blk[d][row * PK];
+#pragma unroll
+          for (int o = 0; o < R; ++o) {
+            const int m = i - o;
+            if (m == 0) f[o] = by.b[NTY - 1] * v;
+            else if (m > 0 && m < NTY) f[o] = fma(by.b[NTY - 1 - m], v, f[o]);
+          }
+        }
+      };
+      if (sg == 0) ypass(std::integral_constant<int, 0>());
+      else ypass(std::integral_constant<int, 1>());
+#pragma unroll
+      for (int o = 0; o < R; ++o) {
+        const int j = j0 + o;
+        if (fast || (j >= 0 && j < g.J)) __stcs(dstp + pt0 + (long)o * g.K, fma(cfm[o], f[o], cfb[o]));
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <int NTY, int NTZ>
+static int launch_plane_panel1(const DfGeom& g, const PanelGeom& panel, const Taps& by, const Taps& bz, const double* T1,
+                               double* out, int nplanes, const double* coef, unsigned mask, bool lund, cudaStream_t st) {
+  using C = PanelCfg<NTY, NTZ>;
+  using C1 = Panel1Cfg<NTY, NTZ>;
+  auto kern = df_plane_panel1_kernel<NTY, NTZ>;
+  static bool configured[64] = {};
+  int dev = 0;
+  PODSDF_CUDA(cudaGetDevice(&dev));
+  if (!configured[dev & 63]) {
+    PODSDF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C1::SMEM));
+    configured[dev & 63] = true;
+  }
+  for (int done = 0; done < nplanes; done += 21845) {   // grid.y = 3 * planes <= 65535
+    const int cnt = (nplanes - done < 21845) ? nplanes - done : 21845;
+    dim3 grid(ceil_div(g.K, C::TK), 3 * cnt);
+    kern<<<grid, C::NCOMPUTE, C1::SMEM, st>>>(T1 + (long)done * 3 * panel.comp_stride, out + (long)done * 3 * g.P, by, bz,
+                                              g, panel, coef, mask, lund ? 1 : 0);
+    count_launch();
+  }
+  PODSDF_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // K-plane, generic: two plain kernels through a global intermediate (any tap counts)
 __global__ void __launch_bounds__(256)
 df_zpass_generic_kernel(const double* __restrict__ T1, double* __restrict__ T2, const Taps bz, const int ntz,
@@ -574,8 +729,11 @@ int launch_df_plane(const DfGeom& g, const PanelGeom& panel, const Taps& by, con
   if (tuned) {
     if (ncomp != 3 || panel.PB == 0) return fail(PODSDF_ERR_UNSUPPORTED, "tuned plane kernel: 3 components, panel layout");
     const int pat = !lund ? 0 : ((mask & ~kPat1Mask) == 0 ? 1 : 2);
+    // off-diagonal planes of M absent: the components are independent -> one CTA per component
+    const bool diagonal = !lund || (mask & kOffDiagMask) == 0;
 #define F(A, B)                                                                                            \
   if (nty == A && ntz == B) {                                                                              \
+    if (diagonal) return launch_plane_panel1<A, B>(g, panel, by, bz, T1, out, nplanes, coef, mask, lund, st); \
     if (pat == 0) return launch_plane_panel<A, B, 0>(g, panel, by, bz, T1, out, nplanes, coef, mask, st);  \
     if (pat == 1) return launch_plane_panel<A, B, 1>(g, panel, by, bz, T1, out, nplanes, coef, mask, st);  \
     return launch_plane_panel<A, B, 2>(g, panel, by, bz, T1, out, nplanes, coef, mask, st);                \
