@@ -534,7 +534,6 @@ df_plane_panel1_kernel(const double* __restrict__ T1, double* __restrict__ out, 
   }
   __syncthreads();
 
-  double* dstp = out + pc * g.P;
   const int zr = tid & (SJ - 1), zs = tid / SJ;
   const double* zsrc = stage + (zs * R) * SJ + zr;
   double* zdst = ring + zr * PK + zs * R;
@@ -543,12 +542,19 @@ df_plane_panel1_kernel(const double* __restrict__ T1, double* __restrict__ out, 
   const bool kok = k < g.K;
   const bool has_m = lund && (mask & (1u << (4 * comp)));       // M_cc plane present
   const bool has_b = lund && (mask & (1u << (9 + comp)));       // mean plane present
+  const double m_default = lund ? 0.0 : 1.0;                    // absent M_cc plane is an exact zero
+  // per-thread walking pointers: point (j0, k) of this step, advanced by SJ rows per step
+  const long rowK = g.K, stepK = (long)SJ * g.K;
+  long pt = (long)(sg * R - (NTY - 1)) * rowK + k;
   const double* cm = coef + (long)(4 * comp) * g.P;
   const double* cb = coef + (long)(9 + comp) * g.P;
+  double* dstp = out + pc * g.P;
+  const double* ringk = ring + kk;
+  int bn = 0;                                                   // ring block written this step = n % NB
+  int j0 = sg * R - (NTY - 1);
 
-  for (int n = 0; n < nsteps; ++n) {
+  for (int n = 0; n < nsteps; ++n, pt += stepK, j0 += SJ, bn = (bn + 1 == NB) ? 0 : bn + 1) {
     mbar_wait(mbar, n & 1);
-    const int bn = n % NB;
     {
       double acc[R];
 #pragma unroll
@@ -572,22 +578,35 @@ df_plane_panel1_kernel(const double* __restrict__ T1, double* __restrict__ out, 
       bulk_g2s(stage_s, src + (n + 1) * panel_stride, C::COPY_BYTES, mbar);
     }
 
-    const int j0 = n * SJ - (NTY - 1) + sg * R;
-    const bool item = (j0 + R > 0) && (j0 < g.J) && kok;
-    const bool fast = item && (j0 >= 0) && (j0 + R <= g.J);
-    const int pt0 = j0 * g.K + k;
-    double cfm[R], cfb[R];
+    if (kok && (j0 + R > 0) && (j0 < g.J)) {
+      const bool fast = (j0 >= 0) && (j0 + R <= g.J);
+      double cfm[R], cfb[R];
+      if (fast) {                     // coefficient loads in flight during the y-pass
+        const double* pm = cm + pt;
+        const double* pb = cb + pt;
 #pragma unroll
-    for (int o = 0; o < R; ++o) {     // coefficient loads in flight during the y-pass
-      const bool ok = fast || (item && j0 + o >= 0 && j0 + o < g.J);
-      cfm[o] = (ok && has_m) ? __ldg(cm + pt0 + (long)o * g.K) : (lund ? 0.0 : 1.0);
-      cfb[o] = (ok && has_b) ? __ldg(cb + pt0 + (long)o * g.K) : 0.0;
-    }
-    if (item) {
+        for (int o = 0; o < R; ++o) {
+          cfm[o] = has_m ? __ldg(pm) : m_default;
+          cfb[o] = has_b ? __ldg(pb) : 0.0;
+          pm += rowK;
+          pb += rowK;
+        }
+      } else {
+#pragma unroll
+        for (int o = 0; o < R; ++o) {
+          const bool ok = (j0 + o >= 0) && (j0 + o < g.J);
+          cfm[o] = (ok && has_m) ? __ldg(cm + pt + o * rowK) : m_default;
+          cfb[o] = (ok && has_b) ? __ldg(cb + pt + o * rowK) : 0.0;
+        }
+      }
       double f[R];
       const double* blk[NB];
+      int b = bn;
 #pragma unroll
-      for (int d = 0; d < NB; ++d) blk[d] = ring + ((n + NB - d) % NB) * SJ * PK + kk;
+      for (int d = 0; d < NB; ++d) {
+        blk[d] = ringk + b * (SJ * PK);
+        b = (b == 0) ? NB - 1 : b - 1;
+      }
       auto ypass = [&](auto SGc) {
         constexpr int SG = decltype(SGc)::value;
 #pragma unroll
@@ -607,10 +626,17 @@ df_plane_panel1_kernel(const double* __restrict__ T1, double* __restrict__ out, 
       };
       if (sg == 0) ypass(std::integral_constant<int, 0>());
       else ypass(std::integral_constant<int, 1>());
+      double* op = dstp + pt;
+      if (fast) {
 #pragma unroll
-      for (int o = 0; o < R; ++o) {
-        const int j = j0 + o;
-        if (fast || (j >= 0 && j < g.J)) __stcs(dstp + pt0 + (long)o * g.K, fma(cfm[o], f[o], cfb[o]));
+        for (int o = 0; o < R; ++o) {
+          __stcs(op, fma(cfm[o], f[o], cfb[o]));
+          op += rowK;
+        }
+      } else {
+#pragma unroll
+        for (int o = 0; o < R; ++o)
+          if ((j0 + o >= 0) && (j0 + o < g.J)) __stcs(op + o * rowK, fma(cfm[o], f[o], cfb[o]));
       }
     }
     __syncthreads();
