@@ -125,18 +125,20 @@ df_time_tuned_kernel(const double* __restrict__ X, double* __restrict__ T1, cons
       const int tt = t + u;
       load(min(tt + NT - 1, last_slab), w0[(u + NT - 1) % NT], w1[(u + NT - 1) % NT]);
       // true convolution (scipy.signal.convolve flips the taps): tap m meets slab tt + NT-1-m
-      double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+      // three independent partial sums per point: six DFMA chains per thread cover the DFMA latency
+      double pa[3], pb[3];
 #pragma unroll
       for (int m = 0; m < NT; ++m) {
         const int idx = (u + NT - 1 - m) % NT;
-        if (m & 1) {
-          a1 = fma(bx.b[m], w0[idx], a1);
-          b1 = fma(bx.b[m], w1[idx], b1);
+        if (m < 3) {
+          pa[m] = bx.b[m] * w0[idx];
+          pb[m] = bx.b[m] * w1[idx];
         } else {
-          a0 = fma(bx.b[m], w0[idx], a0);
-          b0 = fma(bx.b[m], w1[idx], b0);
+          pa[m % 3] = fma(bx.b[m], w0[idx], pa[m % 3]);
+          pb[m % 3] = fma(bx.b[m], w1[idx], pb[m % 3]);
         }
       }
+      const double a0 = pa[0] + pa[1], a1 = pa[2], b0 = pb[0] + pb[1], b1 = pb[2];
       if (tt < t1) {
         double* q = T1 + ((long)tt * 3 + c) * wstride + widx;
         if (paneled) {         // lanes <-> 16 consecutive rows: two coalesced 128-byte lines per half-warp

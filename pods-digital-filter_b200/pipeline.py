@@ -157,3 +157,22 @@ def pod_resident(A, M, N, layout, nm, dt, et, device_index=0, group=None, timers
         for i, name in enumerate(names):
             timers[name] = timers.get(name, 0.0) + marks[i].elapsed_time(marks[i + 1])
     return dict(mean=mean, energy=energy, nm=nm, T=T, Phi=Phi, c128=c128, c_ind=c_ind, c_count=c_count)
+
+
+# ----------------------------------------------------------------------------- DF -> PODFS
+def df_to_podfs(plan, nsteps, nm, dt, et, seed=None, slabs=None, device_index=0):
+    """Config-1 style run entirely on one GPU: generate `nsteps` inlet planes (generated stream `seed`, or the
+    injected CUDA tensor `slabs`), keep them in HBM in the generator's own layout [t][c][p] -- which IS the
+    snapshot matrix transposed (DF:1471-1473) -- and run PODFS on it without a transpose or a host round
+    trip (DF:1492-1510).  Returns the pod_resident dict plus `planes` (mean already removed)."""
+    import torch
+    dev = torch.device("cuda", device_index)
+    shard = DfShard(plan, nsteps, dev)
+    if slabs is not None:
+        shard.generate_injected(slabs)
+    else:
+        shard.generate_seeded(seed, 0)
+    M = 3 * plan.J * plan.K
+    res = pod_resident(shard.out.view(nsteps, M), M, nsteps, _capi.LAYOUT_TIME_BY_ROWS, nm, dt, et, device_index)
+    res["planes"] = shard.out
+    return res

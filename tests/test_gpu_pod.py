@@ -195,3 +195,41 @@ def test_device_entries_mean_gram_project(P):
         V = Cv.cpu().numpy()          # rows are eigenvectors
         assert np.abs(V @ V.T - np.eye(N)).max() < 1e-12
         assert np.abs(lam.cpu().numpy() - np.linalg.eigvalsh(Ac.T @ Ac / N)).max() < 1e-11
+
+
+def test_config1_df_to_podfs_on_device(P):
+    """BASELINE config 1 end to end on the device: 64x64x3 planes, nf=10, ln=5, hyperbolic-tangent profile,
+    20 POD modes -- DF planes stay in HBM and feed PODFS in the generator's own (transposed) layout.
+    300 steps here (the oracle's scipy loop takes ~10 s); checked against oracle DF -> mean -> POD -> Fourier."""
+    torch = pytest.importorskip("torch")
+    from oracle import df_oracle as dfo
+    df = P.digitalfilters
+    J = K = 64
+    nf, ln, ns, nm = 10, 5.0, 300, 20
+    U, uu, vv, ww, uw = dfo.build_profile("hyperbolic-tangent", "top-hat", 1.0, 0.02, K)
+    _, _, _, _, _, _, dt = dfo.derive_filter_sizes(ln, 2.0, 0.1, U, 0.0)
+    X = dfo.reference_stream(0, ns, J, K, nf, nf, nf)
+    A = dfo.generate(X, ns, J, K, ln, ln, ln, nf, nf, nf, ("1d", U, uu, vv, ww, uw), rotate=(1.0, 0.0, 0.0))
+    mean, A = dfo.remove_mean(A)
+    ref = podo.pod(A, ns, J * K, 3, "false", [], 1.0e-15, nm, eig=np.linalg.eigh)
+    f = podo.fourier_coefficients(ref["temporal_modes"], ns, ref["nm"], dt, 0.9, direct=False)
+
+    plan = df._plan(J, K, nf, nf, nf, df._taps(nf, ln), df._taps(nf, ln), df._taps(nf, ln))
+    plan.set_impl(0)
+    plan.set_coefficients(*P._lund.pack(*P._lund.lund_1d(U, uu, vv, ww, uw, J, K), J, K, df.prof_rotation_matrix(1.0, 0.0, 0.0)))
+    slabs = torch.from_numpy(np.ascontiguousarray(np.moveaxis(X[:, :ns + 2 * nf], 0, 1))).cuda()
+    res = P.pipeline.df_to_podfs(plan, ns, nm, dt, 0.9, slabs=slabs)
+    assert rel_err(res["mean"].cpu().numpy(), mean) < 1e-12
+    assert res["nm"] == ref["nm"]
+    e_ref = ref["energy"].real
+    assert np.abs(res["energy"][:nm] - e_ref[:nm]).max() < TOL * e_ref[0]
+    tm_ref = ref["temporal_modes"].real[:, :nm]
+    sign = np.sign(np.sum(res["T"] * tm_ref, axis=0))
+    gaps = np.minimum(np.abs(np.diff(e_ref[:nm + 1])), np.abs(np.diff(np.r_[np.inf, e_ref[:nm]]))) / e_ref[0]
+    bound = np.maximum(1e-9 / np.maximum(gaps, 1e-6), 1e-9)
+    assert (np.abs(res["T"] * sign - tm_ref).max(axis=0) / np.abs(tm_ref).max(axis=0) < bound).all()
+    phi = res["Phi"].cpu().numpy()
+    assert (np.abs(phi * sign - ref["spatial_modes"]).max(axis=0) / np.abs(ref["spatial_modes"]).max(axis=0) < bound).all()
+    assert np.abs(phi.T @ phi - np.eye(nm)).max() < 1e-9
+    assert (np.abs(res["c128"] * sign - f["c128"]).max(axis=0) / np.abs(f["c128"]).max(axis=0) < bound * 10).all()
+    assert np.array_equal(res["c_count"], f["c_count"])
