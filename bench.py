@@ -358,7 +358,7 @@ def main():
 
 
 def plan_is_tuned(pkg, nf):
-    return (2 * nf + 1) in (9, 13, 17, 21, 25, 33)
+    return (2 * nf + 1) in (9, 13, 17, 21, 25, 33, 49, 65, 97, 129)
 
 
 def run_pod(args, pkg, torch, dist, dev, local_rank, rank, world, barrier, max_over_ranks):

@@ -80,12 +80,14 @@ bool use_tuned_time(const podsdf_df_plan* p) {
 // 16-byte pieces: both kernels must exist for these widths and the padded row length must be even
 bool use_tuned_plane(const podsdf_df_plan* p) {
   if (p->impl == PODSDF_IMPL_GENERIC) return false;
-  return use_tuned_time(p) && df_plane_has_tuned(2 * p->g.nfy + 1, 2 * p->g.nfz + 1) && (p->g.Kp % 2 == 0);
+  return use_tuned_time(p) && (p->g.Kp % 2 == 0) &&
+         df_plane_has_tuned(2 * p->g.nfy + 1, 2 * p->g.nfz + 1, df_transform_is_diagonal(p->have_coef, p->mask));
 }
 PanelGeom panel_of(const podsdf_df_plan* p) { return use_tuned_plane(p) ? make_panel_geom(p->g) : PanelGeom(); }
+// sized for either layout: which one is used can change when the coefficients (coupled / diagonal) change
 size_t t1_doubles_per_plane(const podsdf_df_plan* p) {
-  const PanelGeom pg = panel_of(p);
-  return 3 * (size_t)(pg.PB > 0 ? pg.comp_stride : p->g.Np);
+  const PanelGeom pg = make_panel_geom(p->g);
+  return 3 * (size_t)std::max<long>(pg.comp_stride, p->g.Np);
 }
 
 int free_workspace(podsdf_df_plan* p) {
@@ -102,7 +104,7 @@ int ensure_core_ws(podsdf_df_plan* p) {
   if (p->ws_chunk != p->chunk) free_workspace(p);
   const DfGeom& g = p->g;
   if (!p->d_T1) PODSDF_CUDA(cudaMalloc(&p->d_T1, sizeof(double) * t1_doubles_per_plane(p) * (size_t)p->chunk));
-  if (!use_tuned_plane(p) && !p->d_T2)
+  if (!use_tuned_plane(p) && !p->d_T2)   // generic plane path only (allocated lazily: it is as large as T1)
     PODSDF_CUDA(cudaMalloc(&p->d_T2, sizeof(double) * 3 * (size_t)g.Jp * g.K * (size_t)p->chunk));
   p->ws_chunk = p->chunk;
   return 0;

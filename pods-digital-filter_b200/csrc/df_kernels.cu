@@ -155,6 +155,74 @@ df_time_tuned_kernel(const double* __restrict__ X, double* __restrict__ T1, cons
   }
 }
 
+// K-time for wide filters (nfx = 24 .. 64): one point per thread (the window alone is NT doubles), and the
+// tap vector is cut in passes of <= 65 taps -- T1 = sum of the passes, each the same sliding-window kernel on
+// a shifted slab range (`s_off`), the later ones accumulating.  Config 5's wide end runs here.
+template <int NT, bool GEN>
+__global__ void __launch_bounds__(256, 1)
+df_time_wide_kernel(const double* __restrict__ X, double* __restrict__ T1, const Taps bx, const DfGeom g,
+                    const PanelGeom panel, const long nthread, const int nsteps, const int tchunk,
+                    const PhiloxKeys keys, const long s_base, const int s_off, const int last_slab,
+                    const int accumulate) {
+  const long L = blockIdx.x * 256L + threadIdx.x;
+  if (L >= nthread) return;
+  const int c = blockIdx.y;
+  const int t0 = blockIdx.z * tchunk;
+  const int t1 = min(t0 + tchunk, nsteps);
+  const long Np = g.Np;
+  long ridx, widx, wstride;
+  bool valid = true;
+  if (panel.PB > 0) {          // panel layout: L = (pb * Qpad + q) * 16 + r
+    const int r = (int)(L & 15);
+    const long col = L >> 4;
+    const int pb = (int)(col / panel.Qpad), q = (int)(col % panel.Qpad);
+    const int p = pb * 16 + r;
+    valid = (p < g.Jp) && (q < g.Kp);
+    ridx = (long)p * g.Kp + q;
+    widx = L;
+    wstride = panel.comp_stride;
+  } else {
+    ridx = widx = L;
+    wstride = Np;
+  }
+  if (!valid) {
+    if (!accumulate)
+      for (int t = t0; t < t1; ++t) T1[((long)t * 3 + c) * wstride + widx] = 0.0;
+    return;
+  }
+  auto load = [&](int s) -> double {
+    s = min(s_off + s, last_slab);
+    if (GEN) {
+      double a, b;
+      philox_pair(keys, (uint64_t)(ridx >> 1), (uint64_t)(s_base + s), c, a, b);
+      return (ridx & 1) ? b : a;
+    }
+    return __ldcs(X + ((long)s * 3 + c) * Np + ridx);
+  };
+  double w[NT];
+#pragma unroll
+  for (int i = 0; i < NT - 1; ++i) w[i] = load(t0 + i);
+  for (int t = t0; t < t1; t += NT) {
+#pragma unroll
+    for (int u = 0; u < NT; ++u) {
+      const int tt = t + u;
+      w[(u + NT - 1) % NT] = load(tt + NT - 1);
+      double pa[4];
+#pragma unroll
+      for (int m = 0; m < NT; ++m) {
+        const int idx = (u + NT - 1 - m) % NT;
+        if (m < 4) pa[m] = bx.b[m] * w[idx];
+        else pa[m % 4] = fma(bx.b[m], w[idx], pa[m % 4]);
+      }
+      if (tt < t1) {
+        double* q = T1 + ((long)tt * 3 + c) * wstride + widx;
+        const double v = (pa[0] + pa[1]) + (pa[2] + pa[3]);
+        *q = accumulate ? *q + v : v;
+      }
+    }
+  }
+}
+
 // K-time, generic: any tap count, window re-read from global (L1/L2 catch the re-reads)
 __global__ void __launch_bounds__(256)
 df_time_generic_kernel(const double* __restrict__ X, double* __restrict__ T1, const Taps bx, const int nt,
@@ -170,12 +238,14 @@ df_time_generic_kernel(const double* __restrict__ X, double* __restrict__ T1, co
 }
 
 #define PODSDF_TIME_TAPS(F) F(9) F(13) F(17) F(21) F(25) F(33)
+// wide filters: total tap count -> passes of 49 or 65 taps (the second pass front-padded with one zero tap)
+static int wide_pass_taps(int ntx) { return ntx == 49 || ntx == 97 ? 49 : (ntx == 65 || ntx == 129 ? 65 : 0); }
 
 bool df_time_has_tuned(int ntx) {
 #define F(N) if (ntx == N) return true;
   PODSDF_TIME_TAPS(F)
 #undef F
-  return false;
+  return wide_pass_taps(ntx) != 0;
 }
 
 template <int NT>
@@ -198,6 +268,41 @@ static void launch_time_tuned(const DfGeom& g, const PanelGeom& panel, const Tap
   count_launch();
 }
 
+template <int NT>
+static void launch_time_wide(const DfGeom& g, const PanelGeom& panel, const Taps& bx_total, int nt_total, const double* X,
+                             double* T1, int nsteps, bool gen, uint64_t seed, long s_base, cudaStream_t st) {
+  const long nthread = panel.PB > 0 ? (long)panel.PB * panel.Qpad * 16 : g.Np;
+  int nchunk = 1;
+  const long ctas_per_chunk = 3L * ceil_div(nthread, 256);
+  while (nchunk < 64 && ctas_per_chunk * nchunk < 148L * 8 && nsteps / (nchunk * 2) >= 4 * NT) nchunk *= 2;
+  int tchunk = ceil_div(nsteps, nchunk);
+  tchunk = ceil_div(tchunk, NT) * NT;
+  nchunk = ceil_div(nsteps, tchunk);
+  dim3 grid(ceil_div(nthread, 256), 3, nchunk);
+  const PhiloxKeys keys = philox_keys(seed);
+  const int last_slab = nsteps + nt_total - 2;
+  const int npass = (nt_total + NT - 1) / NT;      // 1 or 2
+  for (int pass = 0; pass < npass; ++pass) {
+    Taps b;
+    for (int i = 0; i < kMaxTaps; ++i) b.b[i] = 0.0;
+    int s_off = 0;
+    if (pass == 0) {                               // taps [0, NT): newest slabs
+      for (int i = 0; i < NT; ++i) b.b[i] = bx_total.b[i];
+      s_off = nt_total - NT;
+    } else {                                       // taps [NT, nt_total), front-padded with zeros to NT
+      const int rest = nt_total - NT;
+      for (int i = 0; i < rest; ++i) b.b[NT - rest + i] = bx_total.b[NT + i];
+    }
+    if (gen)
+      df_time_wide_kernel<NT, true><<<grid, 256, 0, st>>>(X, T1, b, g, panel, nthread, nsteps, tchunk, keys, s_base, s_off,
+                                                           last_slab, pass);
+    else
+      df_time_wide_kernel<NT, false><<<grid, 256, 0, st>>>(X, T1, b, g, panel, nthread, nsteps, tchunk, keys, s_base, s_off,
+                                                            last_slab, pass);
+    count_launch();
+  }
+}
+
 int launch_df_time(const DfGeom& g, const PanelGeom& panel, const Taps& bx, const double* X, double* T1, int nsteps,
                    bool gen, uint64_t seed, long s_base, bool tuned, cudaStream_t st) {
   if (nsteps <= 0) return 0;
@@ -207,7 +312,10 @@ int launch_df_time(const DfGeom& g, const PanelGeom& panel, const Taps& bx, cons
 #define F(N) case N: launch_time_tuned<N>(g, panel, bx, X, T1, nsteps, gen, seed, s_base, st); break;
       PODSDF_TIME_TAPS(F)
 #undef F
-      default: return fail(PODSDF_ERR_UNSUPPORTED, "no tuned time-filter kernel for this nfx");
+      default:
+        if (wide_pass_taps(nt) == 49) launch_time_wide<49>(g, panel, bx, nt, X, T1, nsteps, gen, seed, s_base, st);
+        else if (wide_pass_taps(nt) == 65) launch_time_wide<65>(g, panel, bx, nt, X, T1, nsteps, gen, seed, s_base, st);
+        else return fail(PODSDF_ERR_UNSUPPORTED, "no tuned time-filter kernel for this nfx");
     }
   } else {
     if (gen) return fail(PODSDF_ERR_INVALID, "generic time filter needs materialised slabs");
@@ -290,8 +398,8 @@ struct PanelCfg {
   static constexpr unsigned COPY_BYTES = TKIN * SJ * sizeof(double);
   static_assert(SJ * (TK / R) == NCOMPUTE, "z-pass: one item per thread");
   static_assert(TK * (SJ / R) == NCOMPUTE, "y-pass: one item per thread");
+  static constexpr bool kCoupledFits = SMEM <= 113 * 1024;   // two CTAs of the 3-component kernel per SM
   static_assert(COPY_BYTES % 16 == 0, "bulk copy size");
-  static_assert(SMEM <= 113 * 1024, "two CTAs per SM");
 };
 
 __device__ __forceinline__ void mbar_init(unsigned mbar, int count) {
@@ -354,6 +462,7 @@ __global__ void __launch_bounds__(160, 2)
 df_plane_panel_kernel(const double* __restrict__ T1, double* __restrict__ out, const Taps by, const Taps bz,
                       const DfGeom g, const PanelGeom panel, const double* __restrict__ coef, const unsigned mask) {
   using C = PanelCfg<NTY, NTZ>;
+  static_assert(C::kCoupledFits, "two CTAs per SM");
   constexpr int TK = C::TK, SJ = C::SJ, R = C::R, TKIN = C::TKIN, RJ = C::RJ, PK = C::PK, NB = C::NB;
   extern __shared__ __align__(128) double smem[];
   double* stage = smem;                      // [3][TKIN][SJ]
@@ -709,13 +818,18 @@ df_ypass_generic_kernel(const double* __restrict__ T2, double* __restrict__ out,
 
 // (NTY, NTZ) pairs with a tuned kernel: the isotropic sizes of configs 1, 3, 5 and config 2's (8, 4)
 #define PODSDF_PLANE_TAPS(F) F(9, 9) F(13, 13) F(17, 17) F(21, 21) F(25, 25) F(33, 33) F(17, 9)
+// wider filters (config 5: nf = 24 .. 64) have a tuned kernel for diagonal transforms only: three rings of
+// (16 + 2 nfy) rows do not fit one SM's shared memory
+#define PODSDF_PLANE_TAPS_WIDE(F) F(49, 49) F(65, 65) F(97, 97) F(129, 129)
 
-bool df_plane_has_tuned(int nty, int ntz) {
+bool df_plane_has_tuned(int nty, int ntz, bool diagonal) {
 #define F(A, B) if (nty == A && ntz == B) return true;
   PODSDF_PLANE_TAPS(F)
+  if (diagonal) { PODSDF_PLANE_TAPS_WIDE(F) }
 #undef F
   return false;
 }
+bool df_transform_is_diagonal(bool lund, unsigned mask) { return !lund || (mask & kOffDiagMask) == 0; }
 
 PanelGeom make_panel_geom(const DfGeom& g) {
   PanelGeom p;
@@ -758,10 +872,14 @@ int launch_df_plane(const DfGeom& g, const PanelGeom& panel, const Taps& by, con
     if (ncomp != 3 || panel.PB == 0) return fail(PODSDF_ERR_UNSUPPORTED, "tuned plane kernel: 3 components, panel layout");
     const int pat = !lund ? 0 : ((mask & ~kPat1Mask) == 0 ? 1 : 2);
     // off-diagonal planes of M absent: the components are independent -> one CTA per component
-    const bool diagonal = !lund || (mask & kOffDiagMask) == 0;
+    const bool diagonal = df_transform_is_diagonal(lund, mask);
+#define F(A, B) \
+  if (diagonal && nty == A && ntz == B) return launch_plane_panel1<A, B>(g, panel, by, bz, T1, out, nplanes, coef, mask, lund, st);
+    PODSDF_PLANE_TAPS(F)
+    PODSDF_PLANE_TAPS_WIDE(F)
+#undef F
 #define F(A, B)                                                                                            \
   if (nty == A && ntz == B) {                                                                              \
-    if (diagonal) return launch_plane_panel1<A, B>(g, panel, by, bz, T1, out, nplanes, coef, mask, lund, st); \
     if (pat == 0) return launch_plane_panel<A, B, 0>(g, panel, by, bz, T1, out, nplanes, coef, mask, st);  \
     if (pat == 1) return launch_plane_panel<A, B, 1>(g, panel, by, bz, T1, out, nplanes, coef, mask, st);  \
     return launch_plane_panel<A, B, 2>(g, panel, by, bz, T1, out, nplanes, coef, mask, st);                \

@@ -29,7 +29,9 @@ PanelGeom make_panel_geom(const DfGeom& g);
 
 // true when a tuned (compile-time tap count) kernel exists for this size
 bool df_time_has_tuned(int ntx);
-bool df_plane_has_tuned(int nty, int ntz);
+bool df_plane_has_tuned(int nty, int ntz, bool diagonal);
+// true when the transform never mixes components (no Lund, or no off-diagonal plane of M present)
+bool df_transform_is_diagonal(bool lund, unsigned mask);
 
 // T1[t] = sum_m bx[m] X[t + (NTX-1-m)] for t in [0, nsteps);  X has nsteps + NTX - 1 slabs.
 // gen != 0: X is ignored and slab s is Philox(seed, s_base + s) (generated mode, tuned kernels only).

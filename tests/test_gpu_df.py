@@ -275,3 +275,27 @@ def test_cli_main_is_a_drop_in(P, tag, tmp_path, monkeypatch):
     assert dat[:2 + nm] == ref[:2 + nm]                  # mode count, period, coefficients kept per mode
     assert len(dat) == len(ref)
     assert [l.split("\t")[0] for l in dat] == [l.split("\t")[0] for l in ref]     # same harmonics in the same order
+
+
+@pytest.mark.parametrize("nf", [24, 32, 48, 64])
+def test_wide_filters_config5(P, nf):
+    """BASELINE config 5's wide end (nf = 24..64): the time filter runs in one or two <=65-tap passes, the plane
+    filter in the per-component tuned kernel (diagonal transform) -- against the oracle, tuned and generic."""
+    J, K = 40, 72
+    ln = nf / 2.0
+    ns = 2 * nf + 7
+    U, uu, vv, ww, uw = dfo.build_profile("hyperbolic-tangent", "top-hat", 1.0, 0.05, K)
+    rs = np.random.RandomState(nf)
+    X = rs.uniform(-dfo.SQRT3, dfo.SQRT3, (3, ns + 2 * nf, J + 2 * nf, K + 2 * nf))
+    ref = dfo.generate(X, ns, J, K, ln, ln, ln, nf, nf, nf, ("1d", U, uu, vv, ww, uw))
+    fm = P._lund.lund_1d(U, uu, vv, ww, uw, J, K)
+    slabs = np.ascontiguousarray(np.moveaxis(X, 0, 1))
+    for impl in (2, 1):          # 2 = tuned kernels only (fails loudly if one is missing), 1 = generic
+        planes = P.digitalfilters.generate(ns, J, K, ln, ln, ln, nf, nf, nf, fm, None, slabs=slabs, impl=impl, chunk=50)
+        assert rel_err(planes.reshape(ns, -1).T, ref) < 1e-12, impl
+    # generated stream through the wide kernels == injection of the materialised stream
+    df = P.digitalfilters
+    p = df._plan(J, K, nf, nf, nf, df._taps(nf, ln), df._taps(nf, ln), df._taps(nf, ln))
+    p.set_impl(2)
+    p.set_chunk(64)
+    assert np.array_equal(p.generate_seeded(9, 5, ns), p.generate_injected(p.random_slabs(9, 5, ns + 2 * nf)))
