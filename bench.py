@@ -45,6 +45,19 @@ def measured_peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def kplane_traffic(nf, planes_per_launch):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (nf = 10 only), scaled to
+    this run's planes per launch; None when no capture matches."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_kplane_traffic.json")) as f:
+            d = json.load(f)
+        if nf != 10:
+            return None
+        return d["dram_bytes_per_launch"] * planes_per_launch / d["planes_per_launch"]
+    except Exception:
+        return None
+
+
 def df_algorithmic(J, K, nfx, nfy, nfz):
     """bytes and flops per output plane."""
     Jp, Kp = J + 2 * nfy, K + 2 * nfz
@@ -288,8 +301,9 @@ def main():
     roofline = {
         "kernel": "df_plane_panel_kernel (z-pass + y-pass + Lund/rotation + mean, fused)" if plan_is_tuned(pkg, nf) else "df generic plane kernels",
         "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-        "peak_source": hbm_src, "traffic": None,
+        "peak_source": hbm_src, "traffic": kplane_traffic(nf, min(n_planes, 512)),
         "algorithmic_bytes_per_plane": b_plane, "planes_per_launch": min(n_planes, 512),
+        "algorithmic_bytes_per_launch": b_plane * min(n_planes, 512),
         "kernel_ms_per_step": t_plane_ms,
         "fp64": {"achieved_tflops": fl_plane * n_planes / (t_plane_ms * 1e-3) / 1e12, "peak_tflops": FP64_DFMA_PEAK_TFLOPS,
                  "frac": fl_plane * n_planes / (t_plane_ms * 1e-3) / 1e12 / FP64_DFMA_PEAK_TFLOPS,

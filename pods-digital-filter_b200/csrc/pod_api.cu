@@ -14,6 +14,28 @@ namespace {
 
 thread_local double g_gram_ms = 0.0;
 
+// Grow-only per-device scratch (Gram split-K workspace, eigen-solver workspace): cudaMalloc/cudaFree of
+// hundreds of MB on every call costs more than the small kernels they serve.  One slot per purpose.
+struct Scratch {
+  double* p = nullptr;
+  size_t bytes = 0;
+};
+Scratch g_scratch[64][2];
+std::mutex g_scratch_mu;
+int scratch_get(int device, int slot, size_t bytes, double** out) {
+  std::lock_guard<std::mutex> lk(g_scratch_mu);
+  Scratch& s = g_scratch[device & 63][slot];
+  if (s.bytes < bytes) {
+    if (s.p) cudaFree(s.p);
+    s.p = nullptr;
+    s.bytes = 0;
+    PODSDF_CUDA(cudaMalloc(&s.p, bytes));
+    s.bytes = bytes;
+  }
+  *out = s.p;
+  return 0;
+}
+
 struct DevBuf {  // RAII device allocation
   double* p = nullptr;
   cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 8); }
@@ -63,23 +85,27 @@ Cusolver& cusolver() {
 }
 
 // eigen-decomposition in place: on exit row j of C is eigenvector j (ascending eigenvalues)
-int eig_inplace(double* C_dev, long N, double* lambda_dev, cudaStream_t st) {
+int eig_inplace(int device, double* C_dev, long N, double* lambda_dev, cudaStream_t st) {
   if (N > 46340) return fail(PODSDF_ERR_UNSUPPORTED, "N too large for the 32-bit cuSOLVER interface");
   Cusolver& cs = cusolver();
   if (!cs.err.empty()) return fail(PODSDF_ERR_CUDA, cs.err);
-  cusolverDnHandle_t h = nullptr;
-  if (cs.create(&h) != 0) return fail(PODSDF_ERR_CUDA, "cusolverDnCreate failed");
+  static cusolverDnHandle_t handles[64] = {};
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lk(mu);      // one solve at a time per process: the handle is shared
+  cusolverDnHandle_t& h = handles[device & 63];
+  if (!h && cs.create(&h) != 0) return fail(PODSDF_ERR_CUDA, "cusolverDnCreate failed");
   int rc = 0, lwork = 0;
-  DevBuf work, info;
+  double* work = nullptr;
+  DevBuf info;
   const int n = (int)N;
   // CUSOLVER_EIG_MODE_VECTOR = 1, CUBLAS_FILL_MODE_LOWER = 0 (column-major view of a symmetric matrix)
   if (cs.set_stream(h, st) != 0) rc = fail(PODSDF_ERR_CUDA, "cusolverDnSetStream failed");
   if (!rc && cs.bufsize(h, 1, 0, n, C_dev, n, lambda_dev, &lwork) != 0)
     rc = fail(PODSDF_ERR_CUDA, "cusolverDnDsyevd_bufferSize failed");
-  if (!rc && (work.alloc(sizeof(double) * (size_t)lwork) != cudaSuccess || info.alloc(8) != cudaSuccess))
-    rc = fail(PODSDF_ERR_CUDA, "eigen-solver workspace allocation failed");
+  if (!rc) rc = scratch_get(device, 1, sizeof(double) * (size_t)lwork, &work);
+  if (!rc && info.alloc(8) != cudaSuccess) rc = fail(PODSDF_ERR_CUDA, "eigen-solver workspace allocation failed");
   if (!rc) {
-    const cusolverStatus_t s = cs.syevd(h, 1, 0, n, C_dev, n, lambda_dev, work.p, lwork, (int*)info.p);
+    const cusolverStatus_t s = cs.syevd(h, 1, 0, n, C_dev, n, lambda_dev, work, lwork, (int*)info.p);
     int hinfo = -1;
     cudaError_t e = cudaMemcpyAsync(&hinfo, info.p, sizeof(int), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
@@ -87,7 +113,6 @@ int eig_inplace(double* C_dev, long N, double* lambda_dev, cudaStream_t st) {
     else if (s != 0) rc = fail(PODSDF_ERR_CUDA, "cusolverDnDsyevd returned status " + std::to_string(s));
     else if (hinfo != 0) rc = fail(PODSDF_ERR_NUMERIC, "Dsyevd did not converge, info = " + std::to_string(hinfo));
   }
-  cs.destroy(h);
   return rc;
 }
 
@@ -110,16 +135,16 @@ int podsdf_gram_dev(int device, const double* A_dev, long M, long N, int layout,
   PODSDF_TRY(check_device(device));
   DeviceGuard guard(device);
   cudaStream_t st = (cudaStream_t)stream;
-  DevBuf ws;
   const size_t wb = gram_workspace_bytes(M, N);
-  PODSDF_CUDA(ws.alloc(wb));
+  double* ws = nullptr;
+  PODSDF_TRY(scratch_get(device, 0, wb, &ws));
   cudaEvent_t e0, e1;
   PODSDF_CUDA(cudaEventCreate(&e0));
   PODSDF_CUDA(cudaEventCreate(&e1));
   cudaEventRecord(e0, st);
-  int rc = launch_gram(A_dev, M, N, layout, w_dev, P > 0 ? P : 1, scale, C_dev, ws.p, wb, st);
+  int rc = launch_gram(A_dev, M, N, layout, w_dev, P > 0 ? P : 1, scale, C_dev, ws, wb, st);
   cudaEventRecord(e1, st);
-  cudaError_t e = cudaEventSynchronize(e1);  // workspace is freed on return
+  cudaError_t e = cudaEventSynchronize(e1);  // the shared scratch may be reused by the next call
   float ms = 0;
   if (e == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
   g_gram_ms = ms;
@@ -157,7 +182,7 @@ int podsdf_eig_sym_dev(int device, double* C_dev_inout_V, long N, double* lambda
   if (!C_dev_inout_V || !lambda_dev || N < 1) return fail(PODSDF_ERR_INVALID, "bad argument");
   PODSDF_TRY(check_device(device));
   DeviceGuard guard(device);
-  return eig_inplace(C_dev_inout_V, N, lambda_dev, (cudaStream_t)stream);
+  return eig_inplace(device, C_dev_inout_V, N, lambda_dev, (cudaStream_t)stream);
 }
 
 int podsdf_eig_sym_host(int device, const double* C_host, long N, double* lambda_host, double* V_host) {
@@ -170,7 +195,7 @@ int podsdf_eig_sym_host(int device, const double* C_host, long N, double* lambda
   PODSDF_CUDA(V.alloc(nn));
   PODSDF_CUDA(lam.alloc(sizeof(double) * (size_t)N));
   PODSDF_CUDA(cudaMemcpy(C.p, C_host, nn, cudaMemcpyHostToDevice));
-  PODSDF_TRY(eig_inplace(C.p, N, lam.p, nullptr));
+  PODSDF_TRY(eig_inplace(device, C.p, N, lam.p, nullptr));
   PODSDF_TRY(launch_transpose(C.p, V.p, N, nullptr));  // rows = vectors  ->  columns = vectors
   PODSDF_CUDA(cudaMemcpy(V_host, V.p, nn, cudaMemcpyDeviceToHost));
   PODSDF_CUDA(cudaMemcpy(lambda_host, lam.p, sizeof(double) * (size_t)N, cudaMemcpyDeviceToHost));
