@@ -1,6 +1,7 @@
 // C ABI of the digital-filter path (include/podsdf.h): plan object, host/device entry points.
 #include <algorithm>
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -201,6 +202,7 @@ int podsdf_df_plan_create(int device, int J, int K, int nfx, int nfy, int nfz, c
   if ((long)J * K >= (1L << 31) / 4) return fail(PODSDF_ERR_UNSUPPORTED, "plane too large for 32-bit point indices");
   PODSDF_TRY(check_device(device));
   DeviceGuard guard(device);
+  if (const char* v = getenv("PODSDF_TIME_VARIANT")) df_set_time_variant(atoi(v));   // profiling / A-B switch
   auto* p = new podsdf_df_plan();
   p->device = device;
   p->g = DfGeom{J, K, nfx, nfy, nfz, J + 2 * nfy, K + 2 * nfz, (long)(J + 2 * nfy) * (K + 2 * nfz), (long)J * K};
@@ -252,7 +254,9 @@ int podsdf_df_plan_set_impl(podsdf_df_plan* p, int impl) {
 
 int podsdf_df_plan_set_chunk(podsdf_df_plan* p, int chunk) {
   if (!p || chunk < 1 || chunk > 65535) return fail(PODSDF_ERR_INVALID, "chunk must be in 1..65535");
-  p->chunk = chunk;
+  // multiples of 8: the tensor-path time filter works in 8-step tiles anchored at the start of every pass, so
+  // results are bitwise independent of the chunking (and of any time sharding whose offsets are multiples of 8)
+  p->chunk = chunk < 8 ? 8 : (chunk & ~7);
   return 0;
 }
 

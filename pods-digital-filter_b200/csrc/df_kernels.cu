@@ -303,11 +303,169 @@ static void launch_time_wide(const DfGeom& g, const PanelGeom& panel, const Taps
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// K-time on the FP64 tensor path (panel layout only).  The DFMA kernel above is bound by instruction issue
+// (134 instructions per 64 outputs, Philox included); here the sliding-window sum is a banded Toeplitz
+// matrix product  T1[t0+i][pt] = sum_s A[i][s] X[s][pt],  A[i][s] = bx[NT-1-(s-i)],  done with
+// mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4): one instruction per 256 multiply-adds, 8 output steps x 8 points
+// per tile.  The band wastes (NT+7 rounded up to 4)/NT of the tensor flops (25 % at NT = 21, 6 % at
+// NT = 129) but the instruction count per output drops 1.7x and the window needs 8 doubles per tile and lane.
+//   warp   = (16-row panel, column pair q, q+1) = 32 points = NTILE tiles of (4 rows x 2 columns)
+//   lane l : B operand holds X[slab 4*chunk + (l&3)][point l>>2]; point n = 2*row + col, so lane l^4 is the
+//            other column of the same row: ONE Philox call (two neighbouring columns, one slab) per lane
+//            and one 64-bit shuffle yield the lane's values for the two new chunks of every 8-step tile
+//   C frag : lane holds time t0 + (l>>2), rows 4*tile + (l&3), both columns -> per store instruction every
+//            plane receives one full 32-byte sector, the 4 tiles of the warp complete the 128-byte lines
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dmma884_t(double& c0, double& c1, const double a, const double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+template <int NT, bool GEN>
+__global__ void __launch_bounds__(256, (NT <= 33 ? 3 : 1))
+df_time_mma_kernel(const double* __restrict__ X, double* __restrict__ T1, const Taps bx, const DfGeom g,
+                   const PanelGeom panel, const long nwarp, const int nsteps, const int tchunk,
+                   const PhiloxKeys keys, const long s_base) {
+  constexpr int NCH = (NT + 7 + 3) / 4;        // 4-slab chunks under an 8-step tile
+  constexpr int NSLOT = (NCH + 1) & ~1;        // window slots (even, so it rotates by 2 with a static period)
+  constexpr int PERIOD = NSLOT / 2;            // tile steps until the slot pattern repeats
+  constexpr int NTILE = (NT <= 65) ? 2 : 1;    // tiles (4 rows x 2 columns) per warp; register budget decides
+  constexpr int NPART = 4 / NTILE;             // warps sharing one column pair of the 16-row panel
+  const long W2 = blockIdx.x * 8L + (threadIdx.x >> 5);
+  if (W2 >= nwarp) return;
+  const long W = W2 / NPART;
+  const int row0 = (int)(W2 % NPART) * 4 * NTILE;   // first panel row of this warp
+  const int lane = threadIdx.x & 31;
+  const int k = lane & 3, n = lane >> 2;       // B: slab-in-chunk, point;  A / C: k / column pair, row = time
+  const int c = blockIdx.y;
+  const int tc0 = blockIdx.z * tchunk;
+  const int tc1 = min(tc0 + tchunk, nsteps);
+  const int QP = panel.Qpad >> 1;
+  const int pb = (int)(W / QP), q0 = 2 * (int)(W % QP);
+  const int ro = n >> 1, co = n & 1;
+  const bool colok = q0 < g.Kp;                // Kp is even: the pair is valid together
+  const int last_slab = nsteps + NT - 2;
+
+  double a[NCH];                               // Toeplitz band: A[i][4*cc + k] = bx[NT-1-(4*cc+k-i)]
+#pragma unroll
+  for (int cc = 0; cc < NCH; ++cc) {
+    const int d = 4 * cc + k - n;              // n doubles as the A row (time) index i
+    a[cc] = (d >= 0 && d < NT) ? bx.b[NT - 1 - d] : 0.0;
+  }
+
+  // the two values of this lane's point at slabs S1 = base + k and S2 = base + 4 + k
+  auto load2 = [&](int tile, int base, double& v1, double& v2) {
+    const int p = pb * 16 + row0 + 4 * tile + ro;
+    const bool ok = colok && p < g.Jp;
+    if (GEN) {
+      const long pair = ((long)p * g.Kp + q0) >> 1;
+      const int smine = base + k + 4 * co;     // even column computes slab S1, odd column S2
+      double x0, x1;
+      philox_pair(keys, (uint64_t)pair, (uint64_t)(s_base + smine), c, x0, x1);
+      const double keep = co ? x1 : x0, send = co ? x0 : x1;
+      const double recv = __shfl_xor_sync(0xffffffffu, send, 4);
+      v1 = co ? recv : keep;
+      v2 = co ? keep : recv;
+      if (!ok) v1 = v2 = 0.0;
+    } else {
+      const int s1 = min(max(base + k, 0), last_slab), s2 = min(max(base + 4 + k, 0), last_slab);
+      const long off = (long)p * g.Kp + q0 + co;
+      v1 = ok ? __ldcs(X + ((long)s1 * 3 + c) * g.Np + off) : 0.0;
+      v2 = ok ? __ldcs(X + ((long)s2 * 3 + c) * g.Np + off) : 0.0;
+    }
+  };
+
+  double wb[NTILE][NSLOT];
+  // prefill chunk positions -1 .. NCH-3 (pairs); position cc at tile step u lives in slot (cc + 2u) % NSLOT
+#pragma unroll
+  for (int tile = 0; tile < NTILE; ++tile)
+#pragma unroll
+    for (int cc = -1; cc < NCH - 2; cc += 2) {
+      double v1, v2;
+      load2(tile, tc0 + 4 * cc, v1, v2);
+      wb[tile][(cc + NSLOT) % NSLOT] = v1;
+      if (cc + 1 < NCH - 2) wb[tile][(cc + 1 + NSLOT) % NSLOT] = v2;
+    }
+
+  double* wbase = T1 + (long)c * panel.comp_stride + ((long)pb * panel.Qpad + q0) * 16;
+  for (int t = tc0; t < tc1; t += 8 * PERIOD) {
+#pragma unroll
+    for (int u = 0; u < PERIOD; ++u) {
+      const int t0 = t + 8 * u;
+      if (t0 < tc1) {                          // warp-uniform
+#pragma unroll
+        for (int tile = 0; tile < NTILE; ++tile) {
+          double v1, v2;
+          load2(tile, t0 + 4 * (NCH - 2), v1, v2);      // the two newest chunks of this tile step
+          wb[tile][(NCH - 2 + 2 * u) % NSLOT] = v1;
+          wb[tile][(NCH - 1 + 2 * u) % NSLOT] = v2;
+          // two independent accumulator chains (even / odd chunks): DMMA latency is long
+          double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
+#pragma unroll
+          for (int cc = 0; cc < NCH; ++cc) {
+            if (cc & 1) dmma884_t(d0, d1, a[cc], wb[tile][(cc + 2 * u) % NSLOT]);
+            else dmma884_t(c0, c1, a[cc], wb[tile][(cc + 2 * u) % NSLOT]);
+          }
+          // C fragment: time t0 + n, row row0 + 4*tile + k, columns q0 and q0 + 1
+          const int tt = t0 + n;
+          if (tt < tc1) {
+            double* q = wbase + (long)tt * 3 * panel.comp_stride + row0 + 4 * tile + k;
+            q[0] = c0 + d0;
+            q[16] = c1 + d1;
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int NT>
+static void launch_time_mma(const DfGeom& g, const PanelGeom& panel, const Taps& bx, const double* X, double* T1,
+                            int nsteps, bool gen, uint64_t seed, long s_base, cudaStream_t st) {
+  constexpr int NCH = (NT + 7 + 3) / 4, PERIOD = ((NCH + 1) & ~1) / 2;
+  constexpr int NPART = (NT <= 65) ? 2 : 4;                  // warps per column pair (must match the kernel)
+  const long nwarp = (long)NPART * panel.PB * (panel.Qpad / 2);
+  int nchunk = 1;
+  const long ctas_per_chunk = 3L * ceil_div(nwarp, 8);
+  while (nchunk < 64 && ctas_per_chunk * nchunk < 148L * 2 * 8 && nsteps / (nchunk * 2) >= 4 * NT) nchunk *= 2;
+  int tchunk = ceil_div(nsteps, nchunk);
+  tchunk = ceil_div(tchunk, 8 * PERIOD) * (8 * PERIOD);
+  nchunk = ceil_div(nsteps, tchunk);
+  dim3 grid(ceil_div(nwarp, 8), 3, nchunk);
+  const PhiloxKeys keys = philox_keys(seed);
+  if (gen)
+    df_time_mma_kernel<NT, true><<<grid, 256, 0, st>>>(X, T1, bx, g, panel, nwarp, nsteps, tchunk, keys, s_base);
+  else
+    df_time_mma_kernel<NT, false><<<grid, 256, 0, st>>>(X, T1, bx, g, panel, nwarp, nsteps, tchunk, keys, s_base);
+  count_launch();
+}
+
+// 0 = auto (DFMA sliding window up to 25 taps, tensor path from 33 taps), 1 = DFMA kernels only,
+// 2 = tensor-path (DMMA) kernel wherever the layout allows
+static int g_time_variant = 0;
+void df_set_time_variant(int v) { g_time_variant = v; }
+
 int launch_df_time(const DfGeom& g, const PanelGeom& panel, const Taps& bx, const double* X, double* T1, int nsteps,
                    bool gen, uint64_t seed, long s_base, bool tuned, cudaStream_t st) {
   if (nsteps <= 0) return 0;
   const int nt = 2 * g.nfx + 1;
   if (tuned) {
+    if (panel.PB > 0 && g_time_variant != 1) {
+#define F(N) case N: launch_time_mma<N>(g, panel, bx, X, T1, nsteps, gen, seed, s_base, st); PODSDF_CUDA(cudaGetLastError()); return 0;
+      if (g_time_variant == 2) {
+        switch (nt) {
+          PODSDF_TIME_TAPS(F)
+          default: break;
+        }
+      }
+      switch (nt) {          // from 33 taps on the tensor path wins; beyond, the DFMA register window no longer fits
+        F(33) F(49) F(65) F(97) F(129)
+        default: break;
+      }
+#undef F
+    }
     switch (nt) {
 #define F(N) case N: launch_time_tuned<N>(g, panel, bx, X, T1, nsteps, gen, seed, s_base, st); break;
       PODSDF_TIME_TAPS(F)

@@ -27,6 +27,10 @@ struct PanelGeom {
 };
 PanelGeom make_panel_geom(const DfGeom& g);
 
+// K-time variant for the panel layout: 0 = auto (DFMA sliding window up to 33 taps, DMMA Toeplitz for wider
+// filters), 1 = DFMA only, 2 = DMMA wherever possible
+void df_set_time_variant(int v);
+
 // true when a tuned (compile-time tap count) kernel exists for this size
 bool df_time_has_tuned(int ntx);
 bool df_plane_has_tuned(int nty, int ntz, bool diagonal);

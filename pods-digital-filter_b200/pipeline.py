@@ -21,11 +21,15 @@ except ImportError:
     import _capi
 
 
-def shard_range(n, rank, world):
-    """Contiguous block partition of range(n): the first n % world ranks get one extra item."""
-    base, extra = divmod(n, world)
+def shard_range(n, rank, world, align=1):
+    """Contiguous block partition of range(n): the first ranks get one extra block of `align` items.  DF time
+    shards use align=8: the tensor-path time filter sums in 8-step tiles, so shards that start on a multiple
+    of 8 reproduce the single-GPU run bit for bit."""
+    nb = (n + align - 1) // align
+    base, extra = divmod(nb, world)
     lo = rank * base + min(rank, extra)
-    return lo, lo + base + (1 if rank < extra else 0)
+    hi = lo + base + (1 if rank < extra else 0)
+    return min(lo * align, n), min(hi * align, n)
 
 
 # ------------------------------------------------------------------------------------- DF

@@ -48,6 +48,10 @@ def test_shard_range_partitions():
             assert all(cuts[i][1] == cuts[i + 1][0] for i in range(world - 1))
             sizes = [b - a for a, b in cuts]
             assert max(sizes) - min(sizes) <= 1
+            cuts8 = [pl.shard_range(n, r, world, 8) for r in range(world)]
+            assert cuts8[0][0] == 0 and cuts8[-1][1] == n
+            assert all(cuts8[i][1] == cuts8[i + 1][0] for i in range(world - 1))
+            assert all(a % 8 == 0 for a, _ in cuts8)
 
 
 def _df_halo(rank, world):

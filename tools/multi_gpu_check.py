@@ -38,7 +38,7 @@ def main():
     U, uu, vv, ww, uw = df.build_profile("hyperbolic-tangent", "top-hat", 1.0, 0.05, K)
     plan.set_coefficients(*pkg._lund.pack(*pkg._lund.lund_1d(U, uu, vv, ww, uw, J, K), J, K, None))
     seed = 77
-    t0, t1 = pl.shard_range(ns, rank, world)
+    t0, t1 = pl.shard_range(ns, rank, world, 8)
     own_hi = t1 if rank < world - 1 else ns + 2 * nf
     mine = torch.empty((own_hi - t0, 3, J + 2 * nf, K + 2 * nf), dtype=torch.float64, device=dev)
     plan.random_slabs_dev(seed, t0, own_hi - t0, mine.data_ptr(), torch.cuda.current_stream().cuda_stream)
@@ -47,7 +47,7 @@ def main():
     part_inj = shard.generate_injected(win).clone()
     part_gen = shard.generate_seeded(seed, t0).clone()
     torch.cuda.synchronize()
-    gathered = [torch.empty((pl.shard_range(ns, r, world)[1] - pl.shard_range(ns, r, world)[0], 3, J, K),
+    gathered = [torch.empty((pl.shard_range(ns, r, world, 8)[1] - pl.shard_range(ns, r, world, 8)[0], 3, J, K),
                             dtype=torch.float64, device=dev) for r in range(world)]
     dist.all_gather(gathered, part_inj)
     whole_inj = torch.cat(gathered, 0)
