@@ -254,7 +254,7 @@ def main():
     taps = df._taps(nf, ln)
     plan = capi.DfPlan(J, K, nf, nf, nf, taps, taps, taps, device=local_rank)
     plan.set_impl(args.impl_kernels)
-    coef, mask = pkg._lund.pack(*cfg3_lund(pkg), J, K, df.prof_rotation_matrix(1.0, 0.0, 0.0))
+    coef, mask = pkg._lund.pack(*cfg3_lund(pkg), J, K)      # default normal (1,0,0): the rotation is the identity
     plan.set_coefficients(coef, mask)
     shard = pkg.pipeline.DfShard(plan, n_planes, dev)
     seed, t0_rank = 20261018, rank * n_planes

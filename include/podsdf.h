@@ -80,6 +80,9 @@ PODSDF_API int podsdf_df_plan_set_chunk(podsdf_df_plan* plan, int chunk_planes);
  * coef[12][J*K] = M00,M01,M02,M10,...,M22,m0,m1,m2 planes.  mask bit i set = plane i present
  * (absent planes are exact zeros and are neither stored nor read).  coef == NULL: identity. */
 PODSDF_API int podsdf_df_set_coefficients(podsdf_df_plan* plan, const double* coef_host, unsigned mask);
+/* ref: rotate_velocity DF:1119-1131 / prof_rotation_matrix DF:1064-1116.  Constant 3x3 (row-major) applied to
+ * every velocity vector after the Lund transform; NULL switches it off. */
+PODSDF_API int podsdf_df_set_rotation(podsdf_df_plan* plan, const double* R9);
 
 /* ref: filter3DSciPy1D(x,y,...) DF:100-140.  x_host (2nfx+1, Jp, Kp) -> y_host (J, K), no Lund. */
 PODSDF_API int podsdf_df_filter_block_host(podsdf_df_plan* plan, const double* x_host, double* y_host);

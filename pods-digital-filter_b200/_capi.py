@@ -39,6 +39,7 @@ SIGNATURES = {
     "podsdf_df_plan_set_impl": [_vp, _i],
     "podsdf_df_plan_set_chunk": [_vp, _i],
     "podsdf_df_set_coefficients": [_vp, _vp, ctypes.c_uint],
+    "podsdf_df_set_rotation": [_vp, _vp],
     "podsdf_df_filter_block_host": [_vp, _vp, _vp],
     "podsdf_df_lund_apply_host": [_vp, _vp, _vp, _vp],
     "podsdf_df_generate_injected_host": [_vp, _vp, _l, _vp],
@@ -183,6 +184,14 @@ class DfPlan(object):
             return
         coef = f64(coef, (12, self.J * self.K), "coef")
         check(lib().podsdf_df_set_coefficients(self._h, ptr(coef), int(mask)))
+
+    def set_rotation(self, R):
+        """Constant 3x3 rotation applied after the Lund transform (None switches it off)."""
+        if R is None:
+            check(lib().podsdf_df_set_rotation(self._h, None))
+            return
+        R = f64(np.asarray(R, dtype=np.float64), (3, 3), "R")
+        check(lib().podsdf_df_set_rotation(self._h, ptr(R)))
 
     def filter_block(self, x, y):
         x = f64(x, (2 * self.nfx + 1, self.Jp, self.Kp), "x")

@@ -58,6 +58,7 @@ struct podsdf_df_plan {
   double* d_coef = nullptr;  // [12][P]
   unsigned mask = 0;
   bool have_coef = false;
+  Rot rot;                   // constant post-rotation (off by default)
   double* d_T1 = nullptr;  // [chunk][3][Np]
   double* d_T2 = nullptr;  // generic path: [chunk][3][Jp][K]
   double* d_X = nullptr;   // host-injected / generic-generated staging: [chunk+2nfx][3][Np]
@@ -82,7 +83,7 @@ bool use_tuned_time(const podsdf_df_plan* p) {
 bool use_tuned_plane(const podsdf_df_plan* p) {
   if (p->impl == PODSDF_IMPL_GENERIC) return false;
   return use_tuned_time(p) && (p->g.Kp % 2 == 0) &&
-         df_plane_has_tuned(2 * p->g.nfy + 1, 2 * p->g.nfz + 1, df_transform_is_diagonal(p->have_coef, p->mask));
+         df_plane_has_tuned(2 * p->g.nfy + 1, 2 * p->g.nfz + 1, df_transform_is_diagonal(p->have_coef, p->mask, p->rot));
 }
 PanelGeom panel_of(const podsdf_df_plan* p) { return use_tuned_plane(p) ? make_panel_geom(p->g) : PanelGeom(); }
 // sized for either layout: which one is used can change when the coefficients (coupled / diagonal) change
@@ -149,7 +150,7 @@ int run_chunk(podsdf_df_plan* p, const double* X_dev, bool gen, uint64_t seed, l
   PODSDF_TRY(launch_df_time(p->g, pg, p->bx, X, p->d_T1, nsteps, gen, seed, s_base, tt, st));
   PODSDF_CUDA(cudaEventRecord(e1, st));
   PODSDF_TRY(launch_df_plane(p->g, pg, p->by, p->bz, p->d_T1, out_dev, nsteps, 3, p->d_coef, p->mask, p->have_coef,
-                             p->d_T2, tp, st));
+                             p->rot, p->d_T2, tp, st));
   PODSDF_CUDA(cudaEventRecord(e2, st));
   return 0;
 }
@@ -280,6 +281,16 @@ int podsdf_df_set_coefficients(podsdf_df_plan* p, const double* coef_host, unsig
   return 0;
 }
 
+int podsdf_df_set_rotation(podsdf_df_plan* p, const double* R9) {
+  if (!p) return fail(PODSDF_ERR_INVALID, "plan is null");
+  p->rot = Rot();
+  if (R9) {
+    for (int i = 0; i < 9; ++i) p->rot.r[i] = R9[i];
+    p->rot.on = 1;
+  }
+  return 0;
+}
+
 int podsdf_df_filter_block_host(podsdf_df_plan* p, const double* x_host, double* y_host) {
   if (!p || !x_host || !y_host) return fail(PODSDF_ERR_INVALID, "null argument");
   DeviceGuard guard(p->device);
@@ -309,7 +320,7 @@ int podsdf_df_filter_block_host(podsdf_df_plan* p, const double* x_host, double*
   const bool tt = use_tuned_time(p), tp = use_tuned_plane(p);
   const PanelGeom pg = panel_of(p);
   rc = launch_df_time(g, pg, p->bx, dX, dT1, 1, false, 0, 0, tt, st);
-  if (!rc) rc = launch_df_plane(g, pg, p->by, p->bz, dT1, dY, 1, 3, nullptr, 0, false, dT2, tp, st);
+  if (!rc) rc = launch_df_plane(g, pg, p->by, p->bz, dT1, dY, 1, 3, nullptr, 0, false, Rot(), dT2, tp, st);
   if (!rc) {
     e = cudaMemcpyAsync(y_host, dY, sizeof(double) * g.P, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
@@ -321,7 +332,7 @@ int podsdf_df_filter_block_host(podsdf_df_plan* p, const double* x_host, double*
 
 int podsdf_df_lund_apply_host(podsdf_df_plan* p, double* yu, double* yv, double* yw) {
   if (!p || !yu || !yv || !yw) return fail(PODSDF_ERR_INVALID, "null argument");
-  if (!p->have_coef) return 0;  // identity
+  if (!p->have_coef && !p->rot.on) return 0;  // identity
   DeviceGuard guard(p->device);
   const long P = p->g.P;
   double* d = nullptr;
@@ -332,7 +343,7 @@ int podsdf_df_lund_apply_host(podsdf_df_plan* p, double* yu, double* yv, double*
   for (int c = 0; c < 3 && e == cudaSuccess; ++c)
     e = cudaMemcpyAsync(d + c * P, h[c], sizeof(double) * P, cudaMemcpyHostToDevice, st);
   int rc = 0;
-  if (e == cudaSuccess) rc = launch_df_lund(p->g, d, p->d_coef, p->mask, st);
+  if (e == cudaSuccess) rc = launch_df_lund(p->g, d, p->d_coef, p->mask, p->have_coef, p->rot, st);
   for (int c = 0; c < 3 && e == cudaSuccess && !rc; ++c)
     e = cudaMemcpyAsync(h[c], d + c * P, sizeof(double) * P, cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);

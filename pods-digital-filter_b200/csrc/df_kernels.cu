@@ -70,6 +70,7 @@ df_time_tuned_kernel(const double* __restrict__ X, double* __restrict__ T1, cons
   const long Np = g.Np;
   long ridx, widx, wstride;    // canonical point index (reads / Philox), write offset, write plane stride
   bool valid, has2, vec;
+  const bool paneled = panel.PB > 0;
   if (panel.PB > 0) {          // panel layout: L = (pb * QP + qp) * 16 + r, two columns q, q+1 of plane row p
     const int r = (int)(L & 15);
     const long colp = L >> 4;
@@ -89,7 +90,6 @@ df_time_tuned_kernel(const double* __restrict__ X, double* __restrict__ T1, cons
     ridx = widx = 2 * L;
     wstride = Np;
   }
-  const bool paneled = panel.PB > 0;
   const int last_slab = nsteps + NT - 2;
 
   double w0[NT], w1[NT];
@@ -98,7 +98,11 @@ df_time_tuned_kernel(const double* __restrict__ X, double* __restrict__ T1, cons
       philox_pair(keys, (uint64_t)(ridx >> 1), (uint64_t)(s_base + s), c, a, b);
     } else {
       const double* p = X + ((long)s * 3 + c) * Np + ridx;
-      if (vec) {
+      if (paneled) {           // lanes <-> rows: the rest of each 128-byte line is read by the next warps -> keep in L1
+        const double2 v = __ldg(reinterpret_cast<const double2*>(p));
+        a = v.x;
+        b = v.y;
+      } else if (vec) {
         const double2 v = __ldcs(reinterpret_cast<const double2*>(p));  // read once: streaming
         a = v.x;
         b = v.y;
@@ -506,19 +510,30 @@ __device__ __forceinline__ void lund_point(const double* __restrict__ coef, cons
   }
 }
 
+// y <- R y, written like numpy's R.dot(V): products summed left to right (NaN / inf propagate as 0*NaN = NaN)
+__device__ __forceinline__ void rotate_point(const Rot& rot, double& y0, double& y1, double& y2) {
+  const double a = y0, b = y1, c = y2;
+  y0 = fma(rot.r[2], c, fma(rot.r[1], b, rot.r[0] * a));
+  y1 = fma(rot.r[5], c, fma(rot.r[4], b, rot.r[3] * a));
+  y2 = fma(rot.r[8], c, fma(rot.r[7], b, rot.r[6] * a));
+}
+
 __global__ void __launch_bounds__(256)
-df_lund_kernel(double* __restrict__ planes, const double* __restrict__ coef, const unsigned mask, const long P) {
+df_lund_kernel(double* __restrict__ planes, const double* __restrict__ coef, const unsigned mask, const long P,
+               const int lund, const Rot rot) {
   const long pt = blockIdx.x * 256L + threadIdx.x;
   if (pt >= P) return;
-  double y[3];
-  lund_point(coef, mask, P, pt, planes[pt], planes[P + pt], planes[2 * P + pt], y);
+  double y[3] = {planes[pt], planes[P + pt], planes[2 * P + pt]};
+  if (lund) lund_point(coef, mask, P, pt, planes[pt], planes[P + pt], planes[2 * P + pt], y);
+  if (rot.on) rotate_point(rot, y[0], y[1], y[2]);
   planes[pt] = y[0];
   planes[P + pt] = y[1];
   planes[2 * P + pt] = y[2];
 }
 
-int launch_df_lund(const DfGeom& g, double* planes, const double* coef, unsigned mask, cudaStream_t st) {
-  df_lund_kernel<<<ceil_div(g.P, 256), 256, 0, st>>>(planes, coef, mask, g.P);
+int launch_df_lund(const DfGeom& g, double* planes, const double* coef, unsigned mask, bool lund, const Rot& rot,
+                   cudaStream_t st) {
+  df_lund_kernel<<<ceil_div(g.P, 256), 256, 0, st>>>(planes, coef, mask, g.P, lund ? 1 : 0, rot);
   count_launch();
   PODSDF_CUDA(cudaGetLastError());
   return 0;
@@ -618,7 +633,8 @@ constexpr unsigned kOffDiagMask = (1u << 1) | (1u << 2) | (1u << 3) | (1u << 5) 
 template <int NTY, int NTZ, int PAT>
 __global__ void __launch_bounds__(160, 2)
 df_plane_panel_kernel(const double* __restrict__ T1, double* __restrict__ out, const Taps by, const Taps bz,
-                      const DfGeom g, const PanelGeom panel, const double* __restrict__ coef, const unsigned mask) {
+                      const DfGeom g, const PanelGeom panel, const double* __restrict__ coef, const unsigned mask,
+                      const Rot rot) {
   using C = PanelCfg<NTY, NTZ>;
   static_assert(C::kCoupledFits, "two CTAs per SM");
   constexpr int TK = C::TK, SJ = C::SJ, R = C::R, TKIN = C::TKIN, RJ = C::RJ, PK = C::PK, NB = C::NB;
@@ -735,6 +751,7 @@ df_plane_panel_kernel(const double* __restrict__ T1, double* __restrict__ out, c
             y1 = cf[1][o] * f[1][o];
             y2 = fma(cf[3][o], f[2][o], cf[2][o] * f[0][o]);
           }
+          if (rot.on) rotate_point(rot, y0, y1, y2);
           double* op = dstp + pt0 + (long)o * g.K;
           __stcs(op, y0);
           __stcs(op + g.P, y1);
@@ -748,6 +765,7 @@ df_plane_panel_kernel(const double* __restrict__ T1, double* __restrict__ out, c
             const int pt = pt0 + o * g.K;
             double y[3] = {f[0][o], f[1][o], f[2][o]};
             if (PAT != 0) lund_point(coef, mask, g.P, pt, f[0][o], f[1][o], f[2][o], y);
+            if (rot.on) rotate_point(rot, y[0], y[1], y[2]);
 #pragma unroll
             for (int c = 0; c < 3; ++c) __stcs(dstp + (long)c * g.P + pt, y[c]);
           }
@@ -953,7 +971,7 @@ df_zpass_generic_kernel(const double* __restrict__ T1, double* __restrict__ T2, 
 __global__ void __launch_bounds__(256)
 df_ypass_generic_kernel(const double* __restrict__ T2, double* __restrict__ out, const Taps by, const int nty,
                         const DfGeom g, const int ncomp, const double* __restrict__ coef, const unsigned mask,
-                        const int lund) {
+                        const int lund, const Rot rot) {
   const long pt = blockIdx.x * 256L + threadIdx.x;
   if (pt >= g.P) return;
   const long plane = blockIdx.y;
@@ -965,9 +983,10 @@ df_ypass_generic_kernel(const double* __restrict__ T2, double* __restrict__ out,
     for (int m = 0; m < nty; ++m) acc = fma(by.b[nty - 1 - m], s[(long)m * g.K], acc);
     f[c] = acc;
   }
-  if (lund) {
-    double y[3];
-    lund_point(coef, mask, g.P, pt, f[0], f[1], f[2], y);
+  if (lund || rot.on) {
+    double y[3] = {f[0], f[1], f[2]};
+    if (lund) lund_point(coef, mask, g.P, pt, f[0], f[1], f[2], y);
+    if (rot.on) rotate_point(rot, y[0], y[1], y[2]);
     for (int c = 0; c < 3; ++c) out[(plane * 3 + c) * g.P + pt] = y[c];
   } else {
     for (int c = 0; c < ncomp; ++c) out[(plane * ncomp + c) * g.P + pt] = f[c];
@@ -987,7 +1006,9 @@ bool df_plane_has_tuned(int nty, int ntz, bool diagonal) {
 #undef F
   return false;
 }
-bool df_transform_is_diagonal(bool lund, unsigned mask) { return !lund || (mask & kOffDiagMask) == 0; }
+bool df_transform_is_diagonal(bool lund, unsigned mask, const Rot& rot) {
+  return !rot.on && (!lund || (mask & kOffDiagMask) == 0);
+}
 
 PanelGeom make_panel_geom(const DfGeom& g) {
   PanelGeom p;
@@ -999,7 +1020,8 @@ PanelGeom make_panel_geom(const DfGeom& g) {
 
 template <int NTY, int NTZ, int PAT>
 static int launch_plane_panel(const DfGeom& g, const PanelGeom& panel, const Taps& by, const Taps& bz, const double* T1,
-                              double* out, int nplanes, const double* coef, unsigned mask, cudaStream_t st) {
+                              double* out, int nplanes, const double* coef, unsigned mask, const Rot& rot,
+                              cudaStream_t st) {
   using C = PanelCfg<NTY, NTZ>;
   auto kern = df_plane_panel_kernel<NTY, NTZ, PAT>;
   static bool configured[64] = {};
@@ -1013,7 +1035,7 @@ static int launch_plane_panel(const DfGeom& g, const PanelGeom& panel, const Tap
     const int cnt = (nplanes - done < 65535) ? nplanes - done : 65535;
     dim3 grid(ceil_div(g.K, C::TK), cnt);
     kern<<<grid, C::NTHR, C::SMEM, st>>>(T1 + (long)done * 3 * panel.comp_stride, out + (long)done * 3 * g.P, by, bz, g,
-                                         panel, coef, mask);
+                                         panel, coef, mask, rot);
     count_launch();
   }
   PODSDF_CUDA(cudaGetLastError());
@@ -1021,16 +1043,16 @@ static int launch_plane_panel(const DfGeom& g, const PanelGeom& panel, const Tap
 }
 
 int launch_df_plane(const DfGeom& g, const PanelGeom& panel, const Taps& by, const Taps& bz, const double* T1,
-                    double* out, int nplanes, int ncomp, const double* coef, unsigned mask, bool lund, double* T2,
-                    bool tuned, cudaStream_t st) {
+                    double* out, int nplanes, int ncomp, const double* coef, unsigned mask, bool lund, const Rot& rot,
+                    double* T2, bool tuned, cudaStream_t st) {
   if (nplanes <= 0) return 0;
-  if (lund && ncomp != 3) return fail(PODSDF_ERR_INVALID, "Lund transform needs 3 components");
+  if ((lund || rot.on) && ncomp != 3) return fail(PODSDF_ERR_INVALID, "Lund transform / rotation need 3 components");
   const int nty = 2 * g.nfy + 1, ntz = 2 * g.nfz + 1;
   if (tuned) {
     if (ncomp != 3 || panel.PB == 0) return fail(PODSDF_ERR_UNSUPPORTED, "tuned plane kernel: 3 components, panel layout");
     const int pat = !lund ? 0 : ((mask & ~kPat1Mask) == 0 ? 1 : 2);
     // off-diagonal planes of M absent: the components are independent -> one CTA per component
-    const bool diagonal = df_transform_is_diagonal(lund, mask);
+    const bool diagonal = df_transform_is_diagonal(lund, mask, rot);
 #define F(A, B) \
   if (diagonal && nty == A && ntz == B) return launch_plane_panel1<A, B>(g, panel, by, bz, T1, out, nplanes, coef, mask, lund, st);
     PODSDF_PLANE_TAPS(F)
@@ -1038,9 +1060,9 @@ int launch_df_plane(const DfGeom& g, const PanelGeom& panel, const Taps& by, con
 #undef F
 #define F(A, B)                                                                                            \
   if (nty == A && ntz == B) {                                                                              \
-    if (pat == 0) return launch_plane_panel<A, B, 0>(g, panel, by, bz, T1, out, nplanes, coef, mask, st);  \
-    if (pat == 1) return launch_plane_panel<A, B, 1>(g, panel, by, bz, T1, out, nplanes, coef, mask, st);  \
-    return launch_plane_panel<A, B, 2>(g, panel, by, bz, T1, out, nplanes, coef, mask, st);                \
+    if (pat == 0) return launch_plane_panel<A, B, 0>(g, panel, by, bz, T1, out, nplanes, coef, mask, rot, st);  \
+    if (pat == 1) return launch_plane_panel<A, B, 1>(g, panel, by, bz, T1, out, nplanes, coef, mask, rot, st);  \
+    return launch_plane_panel<A, B, 2>(g, panel, by, bz, T1, out, nplanes, coef, mask, rot, st);                \
   }
     PODSDF_PLANE_TAPS(F)
 #undef F
@@ -1055,7 +1077,7 @@ int launch_df_plane(const DfGeom& g, const PanelGeom& panel, const Taps& by, con
     dim3 grid(ceil_div(g.P, 256), cnt);
     df_ypass_generic_kernel<<<grid, 256, 0, st>>>(T2 + (long)done * ncomp * g.Jp * g.K,
                                                   out + (long)done * ncomp * g.P, by, nty, g, ncomp, coef, mask,
-                                                  lund ? 1 : 0);
+                                                  lund ? 1 : 0, rot);
     count_launch();
   }
   PODSDF_CUDA(cudaGetLastError());

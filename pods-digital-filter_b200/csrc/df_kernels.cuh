@@ -27,6 +27,13 @@ struct PanelGeom {
 };
 PanelGeom make_panel_geom(const DfGeom& g);
 
+// Constant rotation applied after the Lund transform (digitalfilters.py:1119-1131): y <- R y.  Kept as nine
+// scalars in the kernel parameters instead of being folded into twelve dense coefficient planes.
+struct Rot {
+  double r[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  int on = 0;
+};
+
 // K-time variant for the panel layout: 0 = auto (DFMA sliding window up to 33 taps, DMMA Toeplitz for wider
 // filters), 1 = DFMA only, 2 = DMMA wherever possible
 void df_set_time_variant(int v);
@@ -35,7 +42,7 @@ void df_set_time_variant(int v);
 bool df_time_has_tuned(int ntx);
 bool df_plane_has_tuned(int nty, int ntz, bool diagonal);
 // true when the transform never mixes components (no Lund, or no off-diagonal plane of M present)
-bool df_transform_is_diagonal(bool lund, unsigned mask);
+bool df_transform_is_diagonal(bool lund, unsigned mask, const Rot& rot);
 
 // T1[t] = sum_m bx[m] X[t + (NTX-1-m)] for t in [0, nsteps);  X has nsteps + NTX - 1 slabs.
 // gen != 0: X is ignored and slab s is Philox(seed, s_base + s) (generated mode, tuned kernels only).
@@ -46,11 +53,12 @@ int launch_df_time(const DfGeom& g, const PanelGeom& panel, const Taps& bx, cons
 // ncomp_in = 3 normally; lund = false writes the filtered field unchanged (coef ignored).
 // T2 is the generic path's workspace [nplanes][3][Jp][K] (may be null for the tuned path).
 int launch_df_plane(const DfGeom& g, const PanelGeom& panel, const Taps& by, const Taps& bz, const double* T1,
-                    double* out, int nplanes, int ncomp, const double* coef, unsigned mask, bool lund, double* T2,
-                    bool tuned, cudaStream_t st);
+                    double* out, int nplanes, int ncomp, const double* coef, unsigned mask, bool lund, const Rot& rot,
+                    double* T2, bool tuned, cudaStream_t st);
 
 // in-place y = M x + m on three planes (backs adapt*): planes[3][P]
-int launch_df_lund(const DfGeom& g, double* planes, const double* coef, unsigned mask, cudaStream_t st);
+int launch_df_lund(const DfGeom& g, double* planes, const double* coef, unsigned mask, bool lund, const Rot& rot,
+                   cudaStream_t st);
 
 // materialise Philox slabs [s0, s0+n) -> X[n][3][Np]
 int launch_df_random_slabs(const DfGeom& g, uint64_t seed, long s0, long n, double* X, cudaStream_t st);

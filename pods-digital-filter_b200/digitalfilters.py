@@ -100,11 +100,15 @@ def filter3D(x, y, a, jma, kma, nfx, nfy, nfz):
 
 # ------------------------------------------------------------------------------------ Lund
 def _apply(yu, yv, yw, fac_mean, jma, kma, rotation=None):
-    coef, mask = _lund.pack(fac_mean[0], fac_mean[1], jma, kma, rotation)
     one = np.array([1.0])
     p = _plan(jma, kma, 0, 0, 0, one, one, one)
-    p.set_coefficients(coef, mask)
+    if fac_mean is None:
+        p.set_coefficients(None, 0)
+    else:
+        p.set_coefficients(*_lund.pack(fac_mean[0], fac_mean[1], jma, kma))
+    p.set_rotation(rotation)
     p.lund_apply(yu, yv, yw)
+    p.set_rotation(None)
 
 
 def adapt1d(yu, yv, yw, uin, uuin, vvin, wwin, uwin, jma, kma):
@@ -198,8 +202,7 @@ def rotate_velocity(A, nx, ny, nz):
     pts = len(A) // 3
     R = prof_rotation_matrix(nx, ny, nz)
     u, v, w = (np.array(A[c * pts:(c + 1) * pts], dtype=np.float64).reshape(1, pts) for c in range(3))
-    ident = (1.0, 0.0, 1.0, 0.0, 0.0, 1.0)
-    _apply(u, v, w, (ident, (0.0, 0.0, 0.0)), 1, pts, rotation=R)
+    _apply(u, v, w, None, 1, pts, rotation=R)
     return np.concatenate([u.ravel(), v.ravel(), w.ravel()])
 
 
@@ -232,7 +235,9 @@ def generate(nsteps, jma, kma, lnx, lny, lnz, nfx, nfy, nfz, fac_mean=None, rota
     if fac_mean is None:
         p.set_coefficients(None, 0)
     else:
-        p.set_coefficients(*_lund.pack(fac_mean[0], fac_mean[1], jma, kma, rotation))
+        p.set_coefficients(*_lund.pack(fac_mean[0], fac_mean[1], jma, kma))
+    # the identity is skipped (it is exact, and keeps the three components independent on the device)
+    p.set_rotation(None if rotation is None or np.array_equal(rotation, np.eye(3)) else rotation)
     if slabs is not None:
         return p.generate_injected(slabs[:nsteps + 2 * nfx], out)
     return p.generate_seeded(seed, t0, nsteps, out)
