@@ -458,7 +458,7 @@ int launch_df_time(const DfGeom& g, const PanelGeom& panel, const Taps& bx, cons
   if (tuned) {
     if (panel.PB > 0 && g_time_variant != 1) {
 #define F(N) case N: launch_time_mma<N>(g, panel, bx, X, T1, nsteps, gen, seed, s_base, st); PODSDF_CUDA(cudaGetLastError()); return 0;
-      if (g_time_variant == 2) {
+      if (g_time_variant == 2 || !gen) {   // injected slabs: the tensor-path kernel's 8-byte loads pattern is faster
         switch (nt) {
           PODSDF_TIME_TAPS(F)
           default: break;
