@@ -180,3 +180,91 @@ def df_to_podfs(plan, nsteps, nm, dt, et, seed=None, slabs=None, device_index=0)
     res = pod_resident(shard.out.view(nsteps, M), M, nsteps, _capi.LAYOUT_TIME_BY_ROWS, nm, dt, et, device_index)
     res["planes"] = shard.out
     return res
+
+
+def reshard_time_to_rows(planes, group=None):
+    """DF -> PODFS hand-off across GPUs.  `planes` (n_local, M) holds this rank's time
+    shard of the snapshot matrix in the generator's layout a[t][row]; PODFS wants every rank to own a block of
+    rows for ALL snapshots.  One all-to-all (NCCL over NVLink; gloo on CPU) moves block (t in shard s, rows of
+    rank r) from rank s to rank r; the result (N_total, M_local) is again the time-by-rows layout, so no
+    transpose pass is needed.  Returns (a_local, (m0, m1))."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    n_local, M = planes.shape
+    if world == 1:
+        return planes, (0, M)
+    counts = [torch.zeros(1, dtype=torch.int64, device=planes.device) for _ in range(world)]
+    dist.all_gather(counts, torch.tensor([n_local], dtype=torch.int64, device=planes.device), group=group)
+    n_of = [int(c.item()) for c in counts]
+    cuts = [shard_range(M, r, world) for r in range(world)]
+    m0, m1 = cuts[rank]
+    send = [planes[:, a:b].contiguous() for a, b in cuts]                       # my steps, rows of rank r
+    recv = [torch.empty((n_of[s], m1 - m0), dtype=planes.dtype, device=planes.device) for s in range(world)]
+    if dist.get_backend(group) == "nccl":
+        dist.all_to_all(recv, send, group=group)
+    else:                                   # gloo (CPU tests) has no all-to-all: same exchange as point-to-point pairs
+        recv[rank].copy_(send[rank])
+        ops = [dist.P2POp(dist.isend, send[r], r, group) for r in range(world) if r != rank]
+        ops += [dist.P2POp(dist.irecv, recv[s], s, group) for s in range(world) if s != rank]
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    return torch.cat(recv, dim=0), (m0, m1)
+
+
+def df_to_podfs_sharded(plan, nsteps_total, nm, dt, et, seed, device_index=0, group=None):
+    """Config-3/4 style run on all ranks: every rank generates its time shard (generated stream, 8-aligned
+    shard starts), the planes are re-sharded by rows with one all-to-all, PODFS runs on the row shard with one
+    all-reduce of the Gram matrix.  Returns pod_resident's dict for this rank's rows plus `rows` = (m0, m1)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    dev = torch.device("cuda", device_index)
+    t0, t1 = shard_range(nsteps_total, rank, world, 8)
+    shard = DfShard(plan, max(t1 - t0, 1), dev)
+    shard.generate_seeded(seed, t0)
+    M = 3 * plan.J * plan.K
+    torch.cuda.synchronize(dev)
+    a_local, rows = reshard_time_to_rows(shard.out.view(-1, M)[:t1 - t0], group)
+    del shard
+    res = pod_resident(a_local, rows[1] - rows[0], nsteps_total, _capi.LAYOUT_TIME_BY_ROWS, nm, dt, et, device_index, group)
+    res["rows"] = rows
+    res["planes_rows"] = a_local
+    return res
+
+
+# -------------------------------------------------------------------- PODFS reconstruction
+def temporal_reconstruction(c64, c_ind, c_count, period, times):
+    """a_i(t) = Re sum_n c[c_ind[i,n], i] exp(2 pi i k_n t / period), k_n = c_ind[i,n] - N//2: the series the
+    CFD solver evaluates (docs/usage/CFDCodeIntegration.rst:85-91) and the reference's plot-only y2
+    (POD:1602-1612).  Host side: it is (modes x kept coefficients x times), tiny.  Returns (len(times), nm)."""
+    N, nm = c64.shape
+    times = np.asarray(times, dtype=np.float64)
+    y2 = np.zeros((times.shape[0], nm))
+    for i in range(nm):
+        sel = c_ind[i, :c_count[i]]
+        k = sel.astype(np.int64) - N // 2
+        ph = np.exp(1j * 2 * np.pi * np.outer(times, k) / period)
+        y2[:, i] = (ph @ c64[sel, i].astype(np.complex128)).real
+    return y2
+
+
+def reconstruct_field(Phi, mean, y2, device_index=0):
+    """U(x, t_j) = mean(x) + sum_i Phi_i(x) a_i(t_j): the PODFS inlet a solver rebuilds, for a-posteriori
+    error and statistics checks.  Phi (M, nm) CUDA tensor, mean (M,) CUDA tensor, y2 (Nt, nm) numpy.
+    Returns a CUDA tensor (M, Nt).  The product runs in the FP64 tensor-core projection kernel."""
+    import torch
+    L = _capi.lib()
+    M, nm = Phi.shape
+    Nt = y2.shape[0]
+    dev = Phi.device
+    T = torch.from_numpy(np.ascontiguousarray(y2.T)).to(dev)          # (nm, Nt): "temporal modes" of the product
+    ones = torch.ones(Nt, dtype=torch.float64, device=dev)
+    U = torch.empty((M, Nt), dtype=torch.float64, device=dev)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    _capi.check(L.podsdf_project_dev(device_index, Phi.contiguous().data_ptr(), M, nm, 0, T.data_ptr(), Nt, ones.data_ptr(),
+                                     Nt, 1.0, U.data_ptr(), st))
+    U += mean[:, None]
+    return U

@@ -105,3 +105,18 @@ def _gram_allreduce(rank, world):
 
 def test_pod_row_shards_allreduce():
     assert all(_run(_gram_allreduce, 2))
+
+
+def _reshard(rank, world):
+    """Time-sharded planes -> row-sharded snapshot matrix with one all-to-all."""
+    pl = pkg().pipeline
+    N, M = 21, 3 * 17
+    full = torch.arange(N * M, dtype=torch.float64).reshape(N, M)
+    t0, t1 = pl.shard_range(N, rank, world, 8)
+    a_local, (m0, m1) = pl.reshard_time_to_rows(full[t0:t1].clone())
+    return bool(torch.equal(a_local, full[:, m0:m1]))
+
+
+def test_df_to_pod_reshard_all_to_all():
+    assert all(_run(_reshard, 2))
+    assert all(_run(_reshard, 3))

@@ -179,7 +179,8 @@ def test_philox_stream_and_time_shards(P):
         p.set_chunk(11)
         whole = p.generate_seeded(seed, 0, ns)
         inj = p.generate_injected(p.random_slabs(seed, 0, ns + 2 * nf))
-        assert np.array_equal(whole, inj)
+        # same numbers; the two modes may run different time-filter kernels (DFMA window / DMMA Toeplitz)
+        assert rel_err(whole, inj) < 1e-14
         shard = p.generate_seeded(seed, 16, ns - 16)          # shard offsets that are multiples of 8: bitwise
         assert np.array_equal(shard, whole[16:])
         shard = p.generate_seeded(seed, 17, ns - 17)          # any other offset: same numbers to rounding
@@ -246,7 +247,7 @@ def test_device_pointer_entries_and_kernel_timers(P):
     out2 = torch.empty_like(out)
     p.generate_injected_dev(slabs.data_ptr(), ns + 2 * nf, out2.data_ptr(), 0)
     torch.cuda.synchronize()
-    assert torch.equal(out, out2)
+    assert float((out - out2).abs().max()) < 1e-14     # same stream; the modes may use different time kernels
     assert P._capi.launch_count() > 0
 
 
@@ -300,4 +301,4 @@ def test_wide_filters_config5(P, nf):
     p = df._plan(J, K, nf, nf, nf, df._taps(nf, ln), df._taps(nf, ln), df._taps(nf, ln))
     p.set_impl(2)
     p.set_chunk(64)
-    assert np.array_equal(p.generate_seeded(9, 5, ns), p.generate_injected(p.random_slabs(9, 5, ns + 2 * nf)))
+    assert rel_err(p.generate_seeded(9, 5, ns), p.generate_injected(p.random_slabs(9, 5, ns + 2 * nf))) < 1e-14

@@ -233,3 +233,30 @@ def test_config1_df_to_podfs_on_device(P):
     assert np.abs(phi.T @ phi - np.eye(nm)).max() < 1e-9
     assert (np.abs(res["c128"] * sign - f["c128"]).max(axis=0) / np.abs(f["c128"]).max(axis=0) < bound * 10).all()
     assert np.array_equal(res["c_count"], f["c_count"])
+
+
+def test_podfs_reconstruction_evaluator(P):
+    """U(x,t) = mean + sum_i Phi_i a_i(t) with a_i(t) from the kept Fourier coefficients, against
+    the oracle's y2 (POD:1602-1612) and a numpy product; with all coefficients kept (et = 1) and all valid modes
+    the reconstruction returns the snapshots."""
+    torch = pytest.importorskip("torch")
+    M, N, nm = 3 * 400, 64, 12
+    A = podo.synthetic_snapshots(M, N, seed=2, rank_r=10, noise=0.0)
+    mean = A.mean(1)
+    A0 = A - mean[:, None]
+    dev = torch.device("cuda", 0)
+    res = P.pipeline.pod_resident(torch.from_numpy(A.copy()).to(dev), M, N, 0, nm, 0.05, 0.9)
+    c64 = res["c128"].astype(np.complex64)
+    period = N * 0.05
+    times = np.linspace(0, (N - 1) * 0.05, N)
+    y2 = P.pipeline.temporal_reconstruction(c64, res["c_ind"], res["c_count"], period, times)
+    f = podo.fourier_coefficients(res["T"], N, res["nm"], 0.05, 0.9, reconstruct=True)
+    assert np.abs(y2 - f["y2"]).max() < 1e-6 * np.abs(f["y2"]).max()          # complex64 storage on both sides
+    U = P.pipeline.reconstruct_field(res["Phi"], res["mean"], y2).cpu().numpy()
+    ref = mean[:, None] + res["Phi"].cpu().numpy() @ y2.T
+    assert rel_err(U, ref) < 1e-12
+    # full series (et = 1 keeps every harmonic): the rank-10 data is reproduced to complex64 accuracy
+    c64b, indb, cntb = P.PODFS.select_fourier(res["c128"], 1.0)
+    y2b = P.pipeline.temporal_reconstruction(c64b, indb, cntb, period, times)
+    Ub = P.pipeline.reconstruct_field(res["Phi"][:, :10].contiguous(), res["mean"], y2b[:, :10]).cpu().numpy()
+    assert np.abs(Ub - A).max() < 5e-6 * np.abs(A0).max()

@@ -8,6 +8,7 @@
 2. DF, generated mode: time shards regenerate their halo from the Philox stream (no collective).
 3. PODFS: rows of a snapshot matrix are sharded, partial Grams are all-reduced (NCCL), the replicated
    eigen-solve / projection / Fourier fit must match the single-GPU result.
+4. DF -> PODFS: time-sharded planes are re-sharded by rows with one all-to-all and fed to the row-sharded PODFS.
 Rank 0 prints one JSON line."""
 import json
 import os
@@ -54,8 +55,12 @@ def main():
     dist.all_gather(gathered, part_gen)
     whole_gen = torch.cat(gathered, 0)
     single = pl.DfShard(plan, ns, dev).generate_seeded(seed, 0)
+    all_slabs = torch.empty((ns + 2 * nf, 3, J + 2 * nf, K + 2 * nf), dtype=torch.float64, device=dev)
+    plan.random_slabs_dev(seed, 0, ns + 2 * nf, all_slabs.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    single_inj = pl.DfShard(plan, ns, dev).generate_injected(all_slabs)
     torch.cuda.synchronize()
-    out["df_injected_halo_bitexact"] = bool(torch.equal(whole_inj, single))
+    out["df_injected_halo_bitexact"] = bool(torch.equal(whole_inj, single_inj))
+    out["df_injected_vs_generated_max_abs"] = float((whole_inj - single).abs().max())
     out["df_generated_shards_bitexact"] = bool(torch.equal(whole_gen, single))
 
     # ---- 3: PODFS row shards (the DF planes above are the snapshots: layout [t][row])
@@ -70,7 +75,16 @@ def main():
     phi_ref = ref["Phi"][m0:m1].cpu().numpy()
     out["pod_spatial_modes_rel_err"] = float(np.abs(res["Phi"].cpu().numpy() * sign - phi_ref).max() / np.abs(phi_ref).max())
     out["pod_fourier_counts_equal"] = bool(np.array_equal(res["c_count"], ref["c_count"]))
-    ok = (out["df_injected_halo_bitexact"] and out["df_generated_shards_bitexact"] and out["pod_energy_rel_err"] < 1e-12
+    # ---- 4: DF -> PODFS across ranks: time shards, one all-to-all re-shard by rows, row-sharded PODFS
+    sh = pl.df_to_podfs_sharded(plan, ns, nm, 0.01, 0.9, seed, local)
+    r0, r1 = sh["rows"]
+    out["reshard_max_abs_err"] = float((sh["planes_rows"] + sh["mean"][None, :] - single.view(N, M)[:, r0:r1]).abs().max())
+    sign2 = np.sign(np.sum(sh["T"] * ref["T"], axis=0))
+    out["pipeline_temporal_modes_rel_err"] = float(np.abs(sh["T"] * sign2 - ref["T"]).max() / np.abs(ref["T"]).max())
+    phi_ref2 = ref["Phi"][r0:r1].cpu().numpy()
+    out["pipeline_spatial_modes_rel_err"] = float(np.abs(sh["Phi"].cpu().numpy() * sign2 - phi_ref2).max() / np.abs(phi_ref2).max())
+    ok = (out["df_injected_halo_bitexact"] and out["reshard_max_abs_err"] < 1e-12 and out["pipeline_temporal_modes_rel_err"] < 1e-8
+          and out["pipeline_spatial_modes_rel_err"] < 1e-8 and out["df_generated_shards_bitexact"] and out["pod_energy_rel_err"] < 1e-12
           and out["pod_temporal_modes_rel_err"] < 1e-8 and out["pod_spatial_modes_rel_err"] < 1e-8
           and out["pod_fourier_counts_equal"])
     flags = torch.tensor([1.0 if ok else 0.0], device=dev)
