@@ -15,7 +15,7 @@ LIB = os.path.join(HERE, "libpodsdf.so")
 SOURCES = ["df_kernels.cu", "df_api.cu", "pod_kernels.cu", "pod_api.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-         "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
+         "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"] + os.environ.get("PODSDF_EXTRA_NVCC_FLAGS", "").split()
 
 
 def _deps(src):
