@@ -36,6 +36,25 @@ FP64_DMMA_PEAK_TFLOPS = 37.0   # measured on this pool's B200 with tools/probe_f
 FP64_DFMA_PEAK_TFLOPS = 34.0
 
 
+# stdout carries exactly ONE JSON line: everything else any library prints there (the NCCL version banner, the
+# reference-style progress prints) is diverted to stderr for the whole run.
+_REAL_STDOUT = None
+
+
+def _divert_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+        sys.stdout = sys.stderr
+
+
+def _emit(line):
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -190,7 +209,7 @@ def run_reference(args, rank):
         "e2e": {"value": value, "unit": "planes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "pod": pod,
     }
-    print(json.dumps(line))
+    _emit(line)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -216,6 +235,7 @@ def main():
     ap.add_argument("--impl-kernels", type=int, default=0, help="0 auto, 1 generic, 2 tuned")
     args = ap.parse_args()
 
+    _divert_stdout()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -366,7 +386,7 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_timed,
             "gpu_launches_total": launches_all, "clocks": clocks, "pod": pod,
         }
-        print(json.dumps(line))
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
