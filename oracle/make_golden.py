@@ -173,6 +173,30 @@ def golden_main(DF, POD, tag, argv, seed):
     return cap
 
 
+# half-channel profile: wall at y=0, centre at y=1 (read_profile mirrors it)
+PROFILE_TXT = """y U uu vv ww uv
+0.00 0.000 0.0000 0.0000 0.0000 0.00000
+0.05 0.420 0.0061 0.0009 0.0021 -0.00110
+0.12 0.650 0.0083 0.0019 0.0030 -0.00160
+0.25 0.800 0.0064 0.0022 0.0029 -0.00140
+0.45 0.910 0.0041 0.0019 0.0023 -0.00095
+0.70 0.975 0.0024 0.0014 0.0016 -0.00048
+1.00 1.000 0.0016 0.0011 0.0012 0.00000
+"""
+
+
+def golden_read_profile(DF):
+    """read_profile (DF:487-522) on a small 1-D profile file (text stored in the fixture)."""
+    tmp = os.path.join(os.path.dirname(HERE), "build", "golden_profile.txt")
+    os.makedirs(os.path.dirname(tmp), exist_ok=True)
+    with open(tmp, "w") as f:
+        f.write(PROFILE_TXT)
+    out = {"in_text": np.array(PROFILE_TXT)}
+    for kma in (11, 32):
+        out["out_kma%d" % kma] = np.stack(_quiet(DF.read_profile, tmp, kma))
+    np.savez(os.path.join(GOLD, "read_profile.npz"), **out)
+
+
 def golden_pod(POD):
     """calculate_correlation_matrix both branches, sort_eigenvalues with a NaN and a tie."""
     rs = np.random.RandomState(3)
@@ -216,6 +240,7 @@ def main():
     golden_filter(DF)
     golden_lund(DF)
     golden_pod(POD)
+    golden_read_profile(DF)
     for tag, (argv, seed) in MAIN_CASES.items():
         cap = golden_main(DF, POD, tag, argv, seed)
         print("main_%s: A %s nm %d N_FC %s" % (tag, cap["A"].shape, cap["nm"], cap["N_FC"]))

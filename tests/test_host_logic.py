@@ -118,3 +118,14 @@ def test_reference_stream_draw_order():
     np.random.seed(3)
     X = df.reference_stream(5, 4, 6, 2, 1, 3)
     assert np.array_equal(np.moveaxis(X, 1, 0), dfo.reference_stream(3, 5, 4, 6, 2, 1, 3))
+
+
+def test_read_profile_matches_reference(tmp_path):
+    """read_profile (DF:487-522): mirror the half profile, spline onto kma points, zero the walls."""
+    df = pkg().digitalfilters
+    g = golden("read_profile.npz")
+    f = tmp_path / "profile.txt"
+    f.write_text(str(g["in_text"]))
+    for kma in (11, 32):
+        got = np.stack(df.read_profile(str(f), kma))
+        assert np.array_equal(got, g["out_kma%d" % kma])
