@@ -296,6 +296,25 @@ def build_profile(mean_profile, turb_profile, bulk_velocity, turbulence_intensit
     return U, uu, vv, ww, uw
 
 
+def read_profile(profilefile, K):
+    """DF:487-522.  1-D profile file with columns y,U,uu,vv,ww,uv: the half profile is mirrored about its
+    last point (uv changes sign), y is normalised to [0,1], cubic splines are evaluated at K points and the
+    wall values are forced to zero."""
+    d = np.genfromtxt(profilefile, names=True, autostrip=True, comments="#")
+    n = d.shape[0]
+    for row in reversed(d[0:n - 2]):
+        d = np.append(d, row)
+    d["y"][n:] = (-(d["y"][n:] - 1.0) + 1)
+    d["uv"][n:] = -d["uv"][n:]
+    z = d["y"]
+    z = (z - np.min(z)) / (np.max(z) - np.min(z))
+    zi = np.linspace(np.min(z), np.max(z), K)
+    out = [_itp.splev(zi, _itp.splrep(z, d[name], s=0), der=0) for name in ("U", "uu", "vv", "ww", "uv")]
+    for v in out:
+        v[0] = v[-1] = 0.0
+    return tuple(out)
+
+
 def channel_profile(K):
     """synthetic realizable channel profile on z in [0,1]
     (not in the reference; shared definition for CPU and GPU sides of the test)."""

@@ -152,6 +152,10 @@ def golden_main(DF, POD, tag, argv, seed):
     os.chdir(tmp)
     old_argv = sys.argv
     try:
+        if "PROFILE" in argv:
+            with open("profile_in.txt", "w") as f:
+                f.write(PROFILE_TXT)
+            argv = [os.path.abspath("profile_in.txt") if a == "PROFILE" else a for a in argv]
         sys.argv = ["digitalfilters.py"] + argv
         np.random.seed(seed)
         import warnings
@@ -165,7 +169,7 @@ def golden_main(DF, POD, tag, argv, seed):
         DF.pod.POD = real_POD
         DF.pod.fourier_coefficients = real_fc
     np.savez(os.path.join(GOLD, "main_%s.npz" % tag),
-             in_argv=np.array(argv), in_seed=seed,
+             in_argv=np.array(MAIN_CASES[tag][0]), in_seed=seed, in_profile_text=np.array(PROFILE_TXT),
              out_A=cap["A"], out_mean_field=cap["mean_field"],
              out_temporal_modes=cap["temporal_modes"], out_spatial_modes=cap["spatial_modes"],
              out_nm=cap["nm"], out_N_FC=cap["N_FC"], out_FC=cap["FC"], out_period=cap["period"],
@@ -229,6 +233,8 @@ MAIN_CASES = {
               "-p", "ring-hyperbolic-tangent", "--ring", "0.4", "--u_dash", "0.1"], 4),
     "dt": (["-n", "16", "-l", "1.5", "-f", "2", "-k", "7", "-j", "6", "-m", "6", "-t", "0.08",
             "-e", "0.8"], 5),
+    # 1-D profile file (read_profile, shear stress, no rotation); "PROFILE" is replaced by a file holding PROFILE_TXT
+    "profile": (["-n", "12", "-l", "1.5", "-f", "2", "-k", "9", "-j", "6", "-m", "4", "-i", "PROFILE"], 6),
 }
 
 

@@ -23,13 +23,18 @@ def parse(argv):
     return o
 
 
-def setup(argv):
-    """Returns dict with everything the DF loop needs for a golden main case."""
+def setup(argv, profile_path=None):
+    """Returns dict with everything the DF loop needs for a golden main case.  profile_path: file to use where
+    the golden argv says "-i PROFILE" (the reference ran with a temporary copy of the same text)."""
     o = parse(argv)
     J, K, ns = o["j"], o["k"], o["n"]
     nrm = np.sqrt(o["nx"] ** 2 + o["ny"] ** 2 + o["nz"] ** 2)          # DF:1291-1293
     normal = (o["nx"] / nrm, o["ny"] / nrm, o["nz"] / nrm)
-    U, uu, vv, ww, uw = dfo.build_profile(o["p"], "top-hat", o["U0"], o["u_dash"], K)
+    from_file = o.get("i") == "PROFILE"
+    if from_file:
+        U, uu, vv, ww, uw = dfo.read_profile(profile_path, K)             # DF:1306-1307
+    else:
+        U, uu, vv, ww, uw = dfo.build_profile(o["p"], "top-hat", o["U0"], o["u_dash"], K)
     lnx, lny, lnz, nfx, nfy, nfz, dt = dfo.derive_filter_sizes(o["l"], o["f"], o["r"], U, o["t"])
     for a in (uu, vv, ww):                                                # DF:1347-1354
         a[a < 0.0] = 0.0
@@ -37,6 +42,8 @@ def setup(argv):
         lund = ("2d", U, uu, vv, ww, uw, o["p"], o["ring"])
     else:
         lund = ("1d", U, uu, vv, ww, uw)
+    if from_file:
+        normal = None                                                     # DF:1476: rotation only without a profile file
     return dict(J=J, K=K, ns=ns, nm=o["m"], et=o["e"], dt=dt, normal=normal, lund=lund,
                 lnx=lnx, lny=lny, lnz=lnz, nfx=nfx, nfy=nfy, nfz=nfz, profile=(U, uu, vv, ww, uw),
                 mean_profile=o["p"], ring=o["ring"])

@@ -64,11 +64,13 @@ def test_adapt_variants_match_reference(P):
 
 
 @pytest.mark.parametrize("impl", IMPLS)
-@pytest.mark.parametrize("tag", ["default", "rotated", "roundjet", "square", "ring", "dt"])
-def test_time_loop_matches_reference_main(P, tag, impl):
+@pytest.mark.parametrize("tag", ["default", "rotated", "roundjet", "square", "ring", "dt", "profile"])
+def test_time_loop_matches_reference_main(P, tag, impl, tmp_path):
     """The fused device loop on the reference's own random draws == the A the reference's main() built."""
     g = golden("main_%s.npz" % tag)
-    s = replay.setup(g["in_argv"])
+    prof = tmp_path / "profile_in.txt"
+    prof.write_text(str(g["in_profile_text"]))
+    s = replay.setup(g["in_argv"], str(prof))
     J, K, ns = s["J"], s["K"], s["ns"]
     X = dfo.reference_stream(int(g["in_seed"]), ns, J, K, s["nfx"], s["nfy"], s["nfz"])
     slabs = np.ascontiguousarray(np.moveaxis(X, 0, 1))
@@ -77,7 +79,7 @@ def test_time_loop_matches_reference_main(P, tag, impl):
         fm = lund.lund_2d(*s["profile"], J, K, s["mean_profile"], s["ring"])
     else:
         fm = lund.lund_1d(*s["profile"], J, K)
-    R = P.digitalfilters.prof_rotation_matrix(*s["normal"])
+    R = P.digitalfilters.prof_rotation_matrix(*s["normal"]) if s["normal"] is not None else None
     planes = P.digitalfilters.generate(ns, J, K, s["lnx"], s["lny"], s["lnz"], s["nfx"], s["nfy"], s["nfz"],
                                        fm, R, slabs=slabs, impl=impl, chunk=5)
     A = planes.reshape(ns, -1).T
@@ -251,14 +253,16 @@ def test_device_pointer_entries_and_kernel_timers(P):
     assert P._capi.launch_count() > 0
 
 
-@pytest.mark.parametrize("tag", ["default", "rotated", "roundjet", "dt"])
+@pytest.mark.parametrize("tag", ["default", "rotated", "roundjet", "dt", "profile"])
 def test_cli_main_is_a_drop_in(P, tag, tmp_path, monkeypatch):
     """`digitalfilters.main()` with the reference's own flags and a seeded global np.random reproduces what the
     reference's main() produced (golden): snapshot matrix, mean field, POD modes up to sign, PODFS.dat."""
     g = golden("main_%s.npz" % tag)
     monkeypatch.chdir(tmp_path)
+    (tmp_path / "profile_in.txt").write_text(str(g["in_profile_text"]))
+    argv = [str(tmp_path / "profile_in.txt") if str(a) == "PROFILE" else str(a) for a in g["in_argv"]]
     np.random.seed(int(g["in_seed"]))
-    i_d = P.digitalfilters.main([str(a) for a in g["in_argv"]])
+    i_d = P.digitalfilters.main(argv)
     assert rel_err(i_d.mean_field, g["out_mean_field"]) < 1e-13
     nm = int(g["out_nm"])
     assert i_d.nm == nm

@@ -122,12 +122,13 @@ def _check_pod(P, A, ns, npts, nm, dt, et, ref, ref_fc, weights=None, tol=1e-9):
     return i_d, dat
 
 
-@pytest.mark.parametrize("tag", ["default", "rotated", "roundjet", "square", "ring", "dt"])
+@pytest.mark.parametrize("tag", ["default", "rotated", "roundjet", "square", "ring", "dt", "profile"])
 def test_pod_and_fourier_match_reference_main(P, tag):
     """POD + Fourier fit of the reference's own snapshot matrix == what the reference's main() produced."""
     g = golden("main_%s.npz" % tag)
-    s = replay.setup(g["in_argv"])
-    ns, npts = s["ns"], s["J"] * s["K"]
+    o = replay.parse(g["in_argv"])
+    ns, npts = o["n"], o["j"] * o["k"]
+    s = dict(nm=o["m"], et=o["e"], dt=float(g["out_dt"]))
     A = g["out_A"]
     ref = dict(nm=int(g["out_nm"]), temporal_modes=g["out_temporal_modes"], spatial_modes=g["out_spatial_modes"],
                energy=np.mean(g["out_temporal_modes"].real ** 2, axis=0))

@@ -81,6 +81,14 @@ def test_rotation_matches_reference():
         assert np.allclose(dfo.rotate_velocity(g["in_col"], *n), rot, rtol=0, atol=1e-15)
 
 
+def test_read_profile_matches_reference(tmp_path):
+    g = load("read_profile.npz")
+    f = tmp_path / "p.txt"
+    f.write_text(str(g["in_text"]))
+    for kma in (11, 32):
+        assert np.array_equal(np.stack(dfo.read_profile(str(f), kma)), g["out_kma%d" % kma])
+
+
 def test_pod_parts_match_reference():
     g = load("pod_parts.npz")
     A, w = g["in_A"], g["in_w"]
@@ -96,15 +104,17 @@ def test_pod_parts_match_reference():
     assert np.array_equal(tm, g["out_tm_sorted"])
 
 
-MAIN = ["default", "rotated", "roundjet", "square", "ring", "dt"]
+MAIN = ["default", "rotated", "roundjet", "square", "ring", "dt", "profile"]
 
 
 @pytest.mark.parametrize("tag", MAIN)
-def test_main_replay_matches_reference(tag):
+def test_main_replay_matches_reference(tag, tmp_path):
     """The whole DF loop + mean removal + POD + Fourier fit, replayed by the oracle on the
     reference's own random draws, equals what the reference's main() produced."""
     g = load("main_%s.npz" % tag)
-    s = replay.setup(g["in_argv"])
+    prof = tmp_path / "profile_in.txt"
+    prof.write_text(str(g["in_profile_text"]))
+    s = replay.setup(g["in_argv"], str(prof))
     J, K, ns = s["J"], s["K"], s["ns"]
     X = dfo.reference_stream(int(g["in_seed"]), ns, J, K, s["nfx"], s["nfy"], s["nfz"])
     A = dfo.generate(X, ns, J, K, s["lnx"], s["lny"], s["lnz"], s["nfx"], s["nfy"], s["nfz"],
