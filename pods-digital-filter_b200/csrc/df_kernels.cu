@@ -831,8 +831,9 @@ df_plane_panel1_kernel(const double* __restrict__ T1, double* __restrict__ out, 
   const bool has_b = lund && (mask & (1u << (9 + comp)));       // mean plane present
   const double m_default = lund ? 0.0 : 1.0;                    // absent M_cc plane is an exact zero
   // per-thread walking pointers: point (j0, k) of this step, advanced by SJ rows per step
-  const long rowK = g.K, stepK = (long)SJ * g.K;
-  long pt = (long)(sg * R - (NTY - 1)) * rowK + k;
+  // 32-bit point indices (J*K < 2^29 is checked at plan creation): one IMAD.WIDE per address
+  const int rowK = g.K, stepK = SJ * g.K;
+  int pt = (sg * R - (NTY - 1)) * rowK + k;
   const double* cm = coef + (long)(4 * comp) * g.P;
   const double* cb = coef + (long)(9 + comp) * g.P;
   double* dstp = out + pc * g.P;
@@ -882,8 +883,8 @@ df_plane_panel1_kernel(const double* __restrict__ T1, double* __restrict__ out, 
 #pragma unroll
         for (int o = 0; o < R; ++o) {
           const bool ok = (j0 + o >= 0) && (j0 + o < g.J);
-          cfm[o] = (ok && has_m) ? __ldg(cm + pt + o * rowK) : m_default;
-          cfb[o] = (ok && has_b) ? __ldg(cb + pt + o * rowK) : 0.0;
+          cfm[o] = (ok && has_m) ? __ldg(cm + pt + (long)o * rowK) : m_default;
+          cfb[o] = (ok && has_b) ? __ldg(cb + pt + (long)o * rowK) : 0.0;
         }
       }
       double f[R];
