@@ -306,3 +306,29 @@ def test_wide_filters_config5(P, nf):
     p.set_impl(2)
     p.set_chunk(64)
     assert rel_err(p.generate_seeded(9, 5, ns), p.generate_injected(p.random_slabs(9, 5, ns + 2 * nf))) < 1e-14
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_time_loop_with_full_stress_tensor(P, impl):
+    """adapt2prf inside the fused loop (DF:1445-1446): full symmetric R(j,k) with every clamp branch, 2-D means
+    -> the general 3x3 + means pattern of the coupled plane kernel, plus a rotation on top."""
+    g = golden("lund.npz")
+    prf = g["in_prf"]                     # U,V,W,uu,vv,ww,uv,uw,vw on a 9 x 11 plane, clamps fire at many points
+    J, K, nf, ln, ns = 9, 11, 4, 2.0, 19
+    X = dfo.reference_stream(3, ns, J, K, nf, nf, nf)
+    ref = dfo.generate(X, ns, J, K, ln, ln, ln, nf, nf, nf, ("prf",) + tuple(prf), rotate=(0.6, -0.48, 0.64))
+    fm = P._lund.lund_prf(*prf)
+    R = P.digitalfilters.prof_rotation_matrix(0.6, -0.48, 0.64)
+    planes = P.digitalfilters.generate(ns, J, K, ln, ln, ln, nf, nf, nf, fm, R,
+                                       slabs=np.ascontiguousarray(np.moveaxis(X, 0, 1)), impl=impl)
+    assert rel_err(planes.reshape(ns, -1).T, ref) < 1e-13
+    # a larger plane so that interior (unguarded) strips of the tuned kernel are exercised too
+    J, K, ns = 70, 150, 12
+    rs = np.random.RandomState(8)
+    f = rs.standard_normal((6, J, K)) * 0.05
+    fields = [rs.standard_normal((J, K)) for _ in range(3)] + [f[0] ** 2 + 0.01, f[1] ** 2 + 0.01, f[2] ** 2 + 0.01, f[3], f[4], f[5]]
+    X = dfo.reference_stream(4, ns, J, K, nf, nf, nf)
+    ref = dfo.generate(X, ns, J, K, ln, ln, ln, nf, nf, nf, ("prf",) + tuple(fields))
+    planes = P.digitalfilters.generate(ns, J, K, ln, ln, ln, nf, nf, nf, P._lund.lund_prf(*fields), None,
+                                       slabs=np.ascontiguousarray(np.moveaxis(X, 0, 1)), impl=impl)
+    assert rel_err(planes.reshape(ns, -1).T, ref) < 1e-13
