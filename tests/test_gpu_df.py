@@ -332,3 +332,29 @@ def test_time_loop_with_full_stress_tensor(P, impl):
     planes = P.digitalfilters.generate(ns, J, K, ln, ln, ln, nf, nf, nf, P._lund.lund_prf(*fields), None,
                                        slabs=np.ascontiguousarray(np.moveaxis(X, 0, 1)), impl=impl)
     assert rel_err(planes.reshape(ns, -1).T, ref) < 1e-13
+
+
+def test_cli_quickstart_and_verbose_outputs(P, tmp_path, monkeypatch):
+    """docs/usage/quickstart.rst:72 (`-n 5`) and the verbose flag: the artefact list of the reference
+    (PODFS_mean.prf, PODFS_mode_????.prf, PODFS.dat; with -v the per-step planes and temporal modes)."""
+    monkeypatch.chdir(tmp_path)
+    np.random.seed(1)
+    i_d = P.digitalfilters.main(["-n", "5", "-v", "--rng", "philox", "--seed", "3"])
+    names = sorted(p.name for p in (tmp_path / "PODFS").iterdir())
+    assert "PODFS.dat" in names and "PODFS_mean.prf" in names and "POD.eigenvalues.dat" in names
+    assert sum(n.startswith("PODFS_mode_") for n in names) == i_d.nm
+    assert sum(n.endswith("E-01.prf") or n.endswith("E+00.prf") for n in names) == 5          # one plane file per step
+    assert sum(n.startswith("POD.temporal_mode_") for n in names) >= i_d.nm
+    first = (tmp_path / "PODFS" / "PODFS_mean.prf").read_text().split("\n")
+    assert first[0] == "# PODFS_mean # name of the profile" and first[10] == "data,x,y,z,u,v,w"
+    assert first[11].startswith("0.000000000000,-0.500000000000,0.550000011921,")          # CFDCodeIntegration.rst:53
+    assert len(first) == 11 + 110 + 1
+    tree = P.HDF5.hdf5_tree(_with_hdf5_fields(P, i_d))
+    assert tree["main"]["mean"]["data"].shape == (110 * 6,) and tree["main"]["attrs"]["N_POD"] == i_d.nm
+
+
+def _with_hdf5_fields(P, i_d):
+    i_d.hdf5 = True
+    P.PODFS.fourier_coefficients(i_d)
+    P.PODFS.pod2prf(i_d)
+    return i_d
