@@ -315,6 +315,133 @@ def read_profile(profilefile, K):
     return tuple(out)
 
 
+def _axis_rotation(theta, nx, ny, nz):
+    """Rodrigues rotation about the (unit) axis n by theta, the 3x3 form written out at DF:648-650, 664-666."""
+    C, S = np.cos(theta), np.sin(theta)
+    t = 1 - C
+    return np.array([[t * nx ** 2 + C, t * nx * ny - S * nz, t * nx * nz + S * ny],
+                     [t * nx * ny + S * nz, t * ny ** 2 + C, t * ny * nz - S * nx],
+                     [t * nx * nz - S * ny, t * ny * nz + S * nx, t * nz ** 2 + C]])
+
+
+def read_prf(profilefile, res, mdot, den, bulk_velocity, non_dim, TestGrad):
+    """DF:524-1035.  2-D `.prf` ingestion: columns named on the `data,` header line (x,y,z,u,v,w and k with e or
+    sdr); plane normal from (last-first) x (second-first); the plane is rotated into y-z, resampled on a
+    (kma, jma) raster of spacing `res` with linear `griddata`; optional mass-flow / bulk-velocity rescaling
+    at constant turbulence intensity and length scale (python-2 `3/2 == 1`, DF:758-788); velocity gradients
+    (2x2 box-smoothed) and the eddy-viscosity Reynolds stresses (DF:1000-1010).  Returns the reference's tuple
+    U,V,W,uu,vv,ww,uv,uw,vw (each (jma,kma)), lnx, kma, jma, normal(3), centre(3).  `non_dim` only affects the
+    reference's plots."""
+    skip = 0
+    with open(profilefile) as f:
+        while True:
+            line = f.readline()
+            skip += 1
+            if line.startswith("data"):
+                names = [c.strip() for c in line.strip().split(",")]
+                break
+    col = {n: i - 1 for i, n in enumerate(names) if i > 0}
+    try:
+        d = np.loadtxt(profilefile, skiprows=skip)
+    except Exception:
+        d = np.loadtxt(profilefile, skiprows=skip, delimiter=",")
+    xA, yA, zA = d[:, col["x"]], d[:, col["y"]], d[:, col["z"]]
+    v2 = (xA[1] - xA[0], yA[1] - yA[0], zA[1] - zA[0])
+    v1 = (xA[-1] - xA[0], yA[-1] - yA[0], zA[-1] - zA[0])
+    xn = v1[1] * v2[2] - v1[2] * v2[1]
+    yn = v1[2] * v2[0] - v1[0] * v2[2]
+    zn = v1[0] * v2[1] - v1[1] * v2[0]
+    nnorm = np.sqrt(xn ** 2 + yn ** 2 + zn ** 2)
+    xn, yn, zn = xn / nnorm, yn / nnorm, zn / nnorm
+    xc = (np.amax(xA) + np.amin(xA)) / 2
+    yc = (np.amax(yA) + np.amin(yA)) / 2
+    zc = (np.amax(zA) + np.amin(zA)) / 2
+    pts = np.array([xA - xc, yA - yc, zA - zc])
+    pts = np.dot(_axis_rotation(-np.arccos(xn), 0, -zn, yn), pts)            # normal -> (1,0,0), DF:636-658
+    pts = np.dot(_axis_rotation(-np.arctan2(zn, yn), xn, yn, zn), pts)        # twist correction, DF:638, 660-672
+    yspan = np.amax(pts[1]) - np.amin(pts[1])
+    zspan = np.amax(pts[2]) - np.amin(pts[2])
+    kma = int(math.ceil(zspan / res))
+    jma = int(math.ceil(yspan / res))
+    yi = np.linspace(np.min(pts[1]), np.min(pts[1]) + res * jma, jma)
+    zi = np.linspace(np.min(pts[2]), np.min(pts[2]) + res * kma, kma)
+    y, z = np.meshgrid(yi, zi)
+    yz = pts[1:, :].T
+
+    def grid(name, clip):
+        g = _itp.griddata(yz, d[:, col[name]], (y, z), fill_value=0.0, method="linear")
+        if clip:
+            g[g < 0] = 0
+        return g
+
+    U, V, W = grid("u", False), grid("v", False), grid("w", False)
+    k = grid("k", True)
+    if "e" in col:
+        eps = grid("e", True)
+    if "sdr" in col:
+        eps = 0.09 * k * grid("sdr", True)
+        eps[np.where(eps > 100000000)] = 0
+    if mdot != 0.0 or bulk_velocity != 1.0:
+        udotn = np.mean(U) * xn + np.mean(V) * yn + np.mean(W) * zn
+        if mdot != 0.0:
+            scale = mdot / (udotn * (res ** 2 * (kma - 1) * (jma - 1)) * den)
+        else:
+            scale = bulk_velocity / udotn
+        flag = eps > 0
+        TI = np.sqrt(2. / 3. * k[flag]) / np.sqrt(U[flag] ** 2 + V[flag] ** 2 + W[flag] ** 2)
+        L = k[flag] ** 1 / eps[flag]
+        U, V, W = U * scale, V * scale, W * scale
+        k[flag] = TI ** 2 * (U[flag] ** 2 + W[flag] ** 2 + V[flag] ** 2)
+        eps[flag] = k[flag] ** 1 / L
+    if TestGrad:
+        eps = np.ones(np.shape(U))
+        k = np.ones(np.shape(U))
+        k[0] = eps[0] = 0.0
+    flag = np.where(eps == 0.0)
+    flag1 = np.where(U == 0.0)
+    U[flag] = 0
+    V[flag] = 0
+    W[flag] = 0
+    k[flag] = 0
+    eps[flag1] = 0
+    if TestGrad:
+        U[:] = 1 * y + 2 * z
+        V[:] = 3 * y + 4 * z
+        W[:] = 5 * y + 6 * z
+    grads = []
+    for F in (U, V, W):
+        dz, dy = np.gradient(F, res)
+        dy[flag] = 0
+        dz[flag] = 0
+        grads += [dy, dz]
+    if not TestGrad:
+        for g in grads:                                                      # DF:828-842: backward 2x2 box mean
+            g1 = g.copy()
+            for i in range(1, kma - 1):
+                for j in range(1, jma - 1):
+                    g[i, j] = np.mean(g1[i - 1:i + 1, j - 1:j + 1])
+    dUdy, dUdz, dVdy, dVdz, dWdy, dWdz = grads
+    dUdx = -dVdy - dWdz
+    dVdx = np.zeros((kma, jma))
+    dWdx = np.zeros((kma, jma))
+    B = 2 * np.amax(pts[1])
+    Cc = 2 * np.amax(pts[2])
+    lnx = math.ceil(0.07 * 2 * B * Cc / (B + Cc) / res)
+    nu_t = np.zeros((kma, jma))
+    pos = np.where(eps > 0)
+    nu_t[pos] = 0.09 * k[pos] ** 2 / eps[pos]
+    uu = -2. * nu_t * dUdx + 2. / 3. * k
+    vv = -2. * nu_t * dVdy + 2. / 3. * k
+    ww = -2. * nu_t * dWdz + 2. / 3. * k
+    uv = -nu_t * (dUdy + dVdx)
+    uw = -nu_t * (dUdz + dWdx)
+    vw = -nu_t * (dVdz + dWdy)
+    for a in (uu, vv, ww):
+        a[np.where(a < 0.0)] = 0.0
+    fields = [np.flip(a, 0).T for a in (U, V, W, uu, vv, ww, uv, uw, vw)]
+    return tuple(fields) + (lnx, kma, jma, xn, yn, zn, xc, yc, zc)
+
+
 def channel_profile(K):
     """synthetic realizable channel profile on z in [0,1]
     (not in the reference; shared definition for CPU and GPU sides of the test)."""
@@ -440,13 +567,16 @@ def remove_mean(A):
     return mean_field, A
 
 
-def derive_filter_sizes(lengthscale, fwidth, res, U, dt):
-    """DF:1277-1285, 1311-1322.  Returns (lnx,lny,lnz,nfx,nfy,nfz,dt)."""
+def derive_filter_sizes(lengthscale, fwidth, res, U, dt, V=0, W=0, ln_file=None):
+    """DF:1277-1285, 1299-1322.  Returns (lnx,lny,lnz,nfx,nfy,nfz,dt).  ln_file: the length scale a `.prf`
+    file yields (DF:1301-1304 overwrite lnx=lny=lnz with it; the filter half-widths stay on the flags)."""
     lnx = lny = lnz = lengthscale
     nf = int(math.ceil(fwidth * lengthscale))
     nfx = nfy = nfz = nf
+    if ln_file is not None:
+        lnx = lny = lnz = ln_file
     U = np.asarray(U, dtype=np.float64)
-    flag = np.where(U ** 2 != 0)
+    flag = np.where(U ** 2 + V ** 2 + W ** 2 != 0)
     if dt == 0.0:
         dt = res / np.mean(U[flag])
     else:

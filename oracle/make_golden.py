@@ -156,6 +156,11 @@ def golden_main(DF, POD, tag, argv, seed):
             with open("profile_in.txt", "w") as f:
                 f.write(PROFILE_TXT)
             argv = [os.path.abspath("profile_in.txt") if a == "PROFILE" else a for a in argv]
+        if "PRF" in argv:
+            DF.plt = _NoPlot()
+            with open("inlet.prf", "w") as f:
+                f.write(MAIN_PRF_TXT)
+            argv = [os.path.abspath("inlet.prf") if a == "PRF" else a for a in argv]
         sys.argv = ["digitalfilters.py"] + argv
         np.random.seed(seed)
         import warnings
@@ -170,6 +175,7 @@ def golden_main(DF, POD, tag, argv, seed):
         DF.pod.fourier_coefficients = real_fc
     np.savez(os.path.join(GOLD, "main_%s.npz" % tag),
              in_argv=np.array(MAIN_CASES[tag][0]), in_seed=seed, in_profile_text=np.array(PROFILE_TXT),
+             in_prf_text=np.array(MAIN_PRF_TXT),
              out_A=cap["A"], out_mean_field=cap["mean_field"],
              out_temporal_modes=cap["temporal_modes"], out_spatial_modes=cap["spatial_modes"],
              out_nm=cap["nm"], out_N_FC=cap["N_FC"], out_FC=cap["FC"], out_period=cap["period"],
@@ -201,6 +207,74 @@ def golden_read_profile(DF):
     np.savez(os.path.join(GOLD, "read_profile.npz"), **out)
 
 
+def prf_text(J, K, res, normal=(1, 0, 0), centre=(0, 0, 0), jitter=0.0, seed=0, cols="k,e"):
+    """A synthetic 2-D inlet profile in the `.prf` layout the reference reads (DF:524-575) and writes
+    (POD:854-887): header lines, a `data,<names>` line, comma-separated rows.  J x K points on a plane with the
+    given normal/centre, optionally jittered like an unstructured CFD face list; a jet-like velocity along the
+    normal plus small in-plane components, k and epsilon (or omega) fields."""
+    rs = np.random.RandomState(seed)
+    n = np.array(normal, float)
+    n /= np.linalg.norm(n)
+    a = np.cross(n, [0, 0, 1.0])
+    a /= np.linalg.norm(a)
+    b = np.cross(n, a)
+    Y, Z = np.meshgrid((np.arange(J) - (J - 1) / 2) * res, (np.arange(K) - (K - 1) / 2) * res, indexing="ij")
+    Y = Y + jitter * res * rs.uniform(-1, 1, Y.shape)
+    Z = Z + jitter * res * rs.uniform(-1, 1, Z.shape)
+    Y, Z = Y.reshape(-1), Z.reshape(-1)
+    pts = np.array(centre)[None, :] + Y[:, None] * a[None, :] + Z[:, None] * b[None, :]
+    r = np.sqrt((Y / (J * res / 2)) ** 2 + (Z / (K * res / 2)) ** 2)
+    vel = (2.0 * (1 - 0.8 * r ** 2))[:, None] * n[None, :] + (0.1 * np.sin(3 * Y))[:, None] * a[None, :] \
+        - (0.05 * np.cos(2 * Z))[:, None] * b[None, :]
+    k = 0.02 * (1 + r) ** 2
+    second = 0.5 * (0.3 + r) if cols.endswith("e") else 40.0 * (0.3 + r)
+    lines = ["# synthetic inlet profile", "units: SI", "data,x,y,z,u,v,w,%s" % cols]
+    for i in range(len(r)):
+        lines.append(",".join("%.12f" % x for x in (*pts[i], *vel[i], k[i], second[i])))
+    return "\n".join(lines) + "\n"
+
+
+class _NoPlot:
+    """read_prf draws 16 contour plots through nplotlib (DF:846-867, 1012-1023); not part of its result."""
+
+    def contourf(self, *a, **k):
+        pass
+
+    def close(self, *a, **k):
+        pass
+
+
+PRF_CASES = {
+    # tag: (prf_text kwargs, (res, mdot, den, bulk_velocity, non_dim, TestGrad))
+    "aligned": (dict(J=9, K=12, res=0.1), (0.1, 0.0, 0.0, 1.0, False, False)),
+    "massflow": (dict(J=10, K=8, res=0.05, normal=(1, 0.5, 0.3), centre=(1, 2, 3), jitter=0.2, seed=1),
+                 (0.05, 0.3, 1.2, 1.0, False, False)),
+    "bulk_sdr": (dict(J=8, K=11, res=0.05, normal=(0.2, 1, -0.4), centre=(0, -1, 0.5), jitter=0.15, seed=2,
+                      cols="k,sdr"), (0.04, 0.0, 0.0, 2.5, True, False)),
+    "testgrad": (dict(J=9, K=12, res=0.1), (0.1, 0.0, 0.0, 1.0, False, True)),
+}
+PRF_NAMES = ["U", "V", "W", "uu", "vv", "ww", "uv", "uw", "vw", "lnx", "kma", "jma", "xn", "yn", "zn", "xc", "yc", "zc"]
+
+
+def golden_read_prf(DF):
+    """read_prf (DF:524-1035) on synthetic .prf files (texts stored in the fixture)."""
+    DF.plt = _NoPlot()
+    tmp = os.path.join(os.path.dirname(HERE), "build", "golden_prf")
+    os.makedirs(tmp, exist_ok=True)
+    out = {}
+    for tag, (kw, args) in PRF_CASES.items():
+        text = prf_text(**kw)
+        path = os.path.join(tmp, tag + ".prf")
+        with open(path, "w") as f:
+            f.write(text)
+        res = _quiet(DF.read_prf, path, *args)
+        out["in_text_" + tag] = np.array(text)
+        out["in_args_" + tag] = np.array(args, dtype=np.float64)
+        for name, v in zip(PRF_NAMES, res):
+            out["out_%s_%s" % (name, tag)] = np.asarray(v)
+    np.savez(os.path.join(GOLD, "read_prf.npz"), **out)
+
+
 def golden_pod(POD):
     """calculate_correlation_matrix both branches, sort_eigenvalues with a NaN and a tie."""
     rs = np.random.RandomState(3)
@@ -220,6 +294,8 @@ def golden_pod(POD):
     np.savez(os.path.join(GOLD, "pod_parts.npz"), **out)
 
 
+MAIN_PRF_TXT = prf_text(J=9, K=8, res=0.1, normal=(1, 0.3, -0.2), centre=(0.5, 0, 1), jitter=0.1, seed=5)
+
 MAIN_CASES = {
     # tag: (argv, seed)
     "default": (["-n", "14", "-l", "1.5", "-f", "2", "-k", "7", "-j", "6", "-m", "5"], 0),
@@ -235,6 +311,8 @@ MAIN_CASES = {
             "-e", "0.8"], 5),
     # 1-D profile file (read_profile, shear stress, no rotation); "PROFILE" is replaced by a file holding PROFILE_TXT
     "profile": (["-n", "12", "-l", "1.5", "-f", "2", "-k", "9", "-j", "6", "-m", "4", "-i", "PROFILE"], 6),
+    # 2-D .prf file (read_prf + adapt2prf; plane size, normal and origin come from the file); "PRF" -> MAIN_PRF_TXT
+    "prf": (["-n", "10", "-l", "1.0", "-f", "2", "-m", "3", "-r", "0.1", "--U0", "1.5", "-i", "PRF"], 7),
 }
 
 
@@ -247,6 +325,7 @@ def main():
     golden_lund(DF)
     golden_pod(POD)
     golden_read_profile(DF)
+    golden_read_prf(DF)
     for tag, (argv, seed) in MAIN_CASES.items():
         cap = golden_main(DF, POD, tag, argv, seed)
         print("main_%s: A %s nm %d N_FC %s" % (tag, cap["A"].shape, cap["nm"], cap["N_FC"]))

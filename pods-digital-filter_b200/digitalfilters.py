@@ -144,11 +144,108 @@ def read_profile(profilefile, kma):
     return tuple(out)
 
 
-def read_prf(*args, **kwargs):
-    """DF:524-1035 (2-D .prf ingestion with Delaunay interpolation and 16 plots) is outside the hot
-    path this package rebuilds; adapt2prf itself is available."""
-    raise NotImplementedError("read_prf (.prf ingestion) is not part of the B200 hot path; "
-                              "call adapt2prf / DfPlan with your own 2-D fields")
+def _rodrigues(theta, ax, ay, az):
+    c, s_ = np.cos(theta), np.sin(theta)
+    t = 1 - c
+    return np.array([[t * ax ** 2 + c, t * ax * ay - s_ * az, t * ax * az + s_ * ay],
+                     [t * ax * ay + s_ * az, t * ay ** 2 + c, t * ay * az - s_ * ax],
+                     [t * ax * az - s_ * ay, t * ay * az + s_ * ax, t * az ** 2 + c]])
+
+
+def _box4(g):
+    """Backward 2x2 box mean on the interior, the smoothing of DF:828-842."""
+    out = g.copy()
+    out[1:-1, 1:-1] = (g[:-2, :-2] + g[:-2, 1:-1] + g[1:-1, :-2] + g[1:-1, 1:-1]) / 4.0
+    return out
+
+
+def read_prf(profilefile, res, mdot, den, bulk_velocity, non_dim, TestGrad):
+    """DF:524-1035: 2-D `.prf` profile -> mean velocity and Reynolds-stress planes for adapt2prf.
+
+    Host-side set-up, run once per job.  The columns are named on the `data,...` header line (x,y,z,u,v,w,k and
+    e or sdr).  The face list is turned into the y-z plane (normal from the first, second and last point, as
+    the reference does), resampled on a (kma, jma) raster of spacing `res` with linear griddata, optionally
+    rescaled to a mass flow or bulk velocity at constant turbulence intensity and length scale, and closed
+    with an eddy-viscosity model on box-smoothed gradients.  Returns U,V,W,uu,vv,ww,uv,uw,vw (jma,kma), lnx,
+    kma, jma, xn,yn,zn, xc,yc,zc.  `non_dim` only rescaled the reference's plot axes."""
+    from scipy import interpolate
+    with open(profilefile) as f:
+        skip = 0
+        for line in f:
+            skip += 1
+            if line.startswith("data"):
+                break
+        else:
+            raise Exception("no 'data' header line in " + profilefile)
+    names = [c.strip() for c in line.strip().split(",")][1:]
+    col = {n: i for i, n in enumerate(names)}
+    try:
+        table = np.loadtxt(profilefile, skiprows=skip)
+    except Exception:
+        table = np.loadtxt(profilefile, skiprows=skip, delimiter=",")
+    xyz = np.array([table[:, col[c]] for c in "xyz"])
+    e1, e2 = xyz[:, -1] - xyz[:, 0], xyz[:, 1] - xyz[:, 0]
+    nrm = np.array([e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]])
+    xn, yn, zn = nrm / np.sqrt(nrm[0] ** 2 + nrm[1] ** 2 + nrm[2] ** 2)
+    xc, yc, zc = ((np.amax(a) + np.amin(a)) / 2 for a in xyz)
+    pts = np.array([xyz[0] - xc, xyz[1] - yc, xyz[2] - zc])
+    pts = np.dot(_rodrigues(-np.arccos(xn), 0, -zn, yn), pts)
+    pts = np.dot(_rodrigues(-np.arctan2(zn, yn), xn, yn, zn), pts)
+    ymin, zmin = np.min(pts[1]), np.min(pts[2])
+    jma = int(math.ceil((np.amax(pts[1]) - ymin) / res))
+    kma = int(math.ceil((np.amax(pts[2]) - zmin) / res))
+    y, z = np.meshgrid(np.linspace(ymin, ymin + res * jma, jma), np.linspace(zmin, zmin + res * kma, kma))
+
+    def raster(name, nonneg=True):
+        g = interpolate.griddata(pts[1:].T, table[:, col[name]], (y, z), fill_value=0.0, method="linear")
+        return np.maximum(g, 0.0) if nonneg else g
+
+    U, V, W = (raster(c, False) for c in "uvw")
+    k = raster("k")
+    if "e" in col:
+        eps = raster("e")
+    if "sdr" in col:
+        eps = 0.09 * k * raster("sdr")
+        eps[eps > 100000000] = 0
+    if mdot != 0.0 or bulk_velocity != 1.0:
+        udotn = np.mean(U) * xn + np.mean(V) * yn + np.mean(W) * zn
+        area = res ** 2 * (kma - 1) * (jma - 1)
+        scale = mdot / (udotn * area * den) if mdot != 0.0 else bulk_velocity / udotn
+        live = eps > 0
+        TI = np.sqrt(2. / 3. * k[live]) / np.sqrt(U[live] ** 2 + V[live] ** 2 + W[live] ** 2)
+        L = k[live] / eps[live]              # the reference's k**(3/2) under python 2 is k**1
+        U, V, W = U * scale, V * scale, W * scale
+        k[live] = TI ** 2 * (U[live] ** 2 + W[live] ** 2 + V[live] ** 2)
+        eps[live] = k[live] / L
+    if TestGrad:
+        eps = np.ones_like(U)
+        k = np.ones_like(U)
+        k[0] = eps[0] = 0.0
+    dead, still = eps == 0.0, U == 0.0
+    for a in (U, V, W, k):
+        a[dead] = 0
+    eps[still] = 0
+    if TestGrad:
+        U, V, W = 1 * y + 2 * z, 3 * y + 4 * z, 5 * y + 6 * z
+    grads = {}
+    for c, F in zip("UVW", (U, V, W)):
+        for axis, d in zip("zy", np.gradient(F, res)):
+            d[dead] = 0
+            grads[c + axis] = d if TestGrad else _box4(d)
+    B, C = 2 * np.amax(pts[1]), 2 * np.amax(pts[2])
+    lnx = math.ceil(0.07 * 2 * B * C / (B + C) / res)
+    nu_t = np.zeros((kma, jma))
+    live = eps > 0
+    nu_t[live] = 0.09 * k[live] ** 2 / eps[live]
+    dUdx = -grads["Vy"] - grads["Wz"]
+    uu = np.maximum(-2. * nu_t * dUdx + 2. / 3. * k, 0.0)
+    vv = np.maximum(-2. * nu_t * grads["Vy"] + 2. / 3. * k, 0.0)
+    ww = np.maximum(-2. * nu_t * grads["Wz"] + 2. / 3. * k, 0.0)
+    uv = -nu_t * (grads["Uy"] + 0.0)
+    uw = -nu_t * (grads["Uz"] + 0.0)
+    vw = -nu_t * (grads["Vz"] + grads["Wy"])
+    planes = tuple(np.ascontiguousarray(a[::-1].T) for a in (U, V, W, uu, vv, ww, uv, uw, vw))
+    return planes + (lnx, kma, jma, xn, yn, zn, xc, yc, zc)
 
 
 def build_profile(mean_profile, turb_profile, bulk_velocity, turbulence_intensity, kma):
@@ -314,14 +411,22 @@ def main(argv=None):
     nrm = np.sqrt(options.nx ** 2 + options.ny ** 2 + options.nz ** 2)
     nx, ny, nz = options.nx / nrm, options.ny / nrm, options.nz / nrm   # DF:1291-1293
 
+    ox, oy, oz = options.ox, options.oy, options.oz
+    V = W = 0
+    from_prf = False
     if options.profilefile and os.path.isfile(profilefile):
-        if profilefile.endswith(".prf"):
-            read_prf(profilefile)
-        U, uu, vv, ww, uw = read_profile(profilefile, kma)
+        if profilefile.endswith(".prf"):                                 # DF:1299-1304: precise 2-D profile file
+            from_prf = True
+            (U, V, W, uu, vv, ww, uv, uw, vw, lnx, kma, jma, nx, ny, nz, ox, oy, oz) = read_prf(
+                profilefile, res, options.mdot, options.den, options.bulk_velocity, options.non_dim,
+                options.TestGrad)
+            lny = lnz = lnx
+        else:
+            U, uu, vv, ww, uw = read_profile(profilefile, kma)
     else:
         U, uu, vv, ww, uw = build_profile(mean_profile, options.turb_profile, options.bulk_velocity,
                                           options.turbulence_intensity, kma)
-    flag = np.where(U ** 2 != 0)                                         # DF:1311-1322 (V = W = 0 here)
+    flag = np.where(U ** 2 + V ** 2 + W ** 2 != 0)                       # DF:1311-1322
     if dt == 0.:
         dt = res / np.mean(U[flag])
         print("timestep set to: ", dt, " seconds")
@@ -330,19 +435,22 @@ def main(argv=None):
         nfx = int(math.ceil(float(options.fwidth) * lnx))
         print("Lengthscale in x-direction set to: ", lnx, "grid points")
         print("Filter width in x-direction set to: ", nfx, "grid points")
-    for v in (uu, vv, ww):                                               # DF:1347-1354
-        v[v < 0.0] = 0.0
+    if not from_prf:                                                     # DF:1345-1352
+        for v in (uu, vv, ww):
+            v[v < 0.0] = 0.0
 
     i_d = obj()
     i_d.kma, i_d.jma, i_d.ns, i_d.dt, i_d.nm, i_d.et = kma, jma, nsteps, dt, options.nm, options.et
-    i_d.rot, i_d.t_o, i_d.res, i_d.n = options.rot, [options.ox, options.oy, options.oz], res, [nx, ny, nz]
+    i_d.rot, i_d.t_o, i_d.res, i_d.n = options.rot, [ox, oy, oz], res, [nx, ny, nz]
     num_points = jma * kma
     i_d.num_points = num_points
     i_d.is_POD_var_vec = False
     i_d.grid = pod.make_inflow_plane(i_d)
     i_d.hdf5 = options.hdf5
 
-    if mean_profile in ["double-hyperbolic-tangent", "ring-hyperbolic-tangent", "circular-hyperbolic-tangent"]:
+    if from_prf:
+        fac_mean = _lund.lund_prf(U, V, W, uu, vv, ww, uv, uw, vw)                     # DF:1445-1446
+    elif mean_profile in ["double-hyperbolic-tangent", "ring-hyperbolic-tangent", "circular-hyperbolic-tangent"]:
         fac_mean = _lund.lund_2d(U, uu, vv, ww, uw, jma, kma, mean_profile, inner_d)   # DF:1447-1449
     else:
         fac_mean = _lund.lund_1d(U, uu, vv, ww, uw, jma, kma)                          # DF:1450-1451

@@ -23,14 +23,23 @@ def parse(argv):
     return o
 
 
-def setup(argv, profile_path=None):
-    """Returns dict with everything the DF loop needs for a golden main case.  profile_path: file to use where
-    the golden argv says "-i PROFILE" (the reference ran with a temporary copy of the same text)."""
+def setup(argv, profile_path=None, prf_path=None):
+    """Returns dict with everything the DF loop needs for a golden main case.  profile_path / prf_path: files to
+    use where the golden argv says "-i PROFILE" / "-i PRF" (the reference ran with a temporary copy of the same
+    text)."""
     o = parse(argv)
     J, K, ns = o["j"], o["k"], o["n"]
     nrm = np.sqrt(o["nx"] ** 2 + o["ny"] ** 2 + o["nz"] ** 2)          # DF:1291-1293
     normal = (o["nx"] / nrm, o["ny"] / nrm, o["nz"] / nrm)
-    from_file = o.get("i") == "PROFILE"
+    from_file = o.get("i") in ("PROFILE", "PRF")
+    if o.get("i") == "PRF":                                               # DF:1299-1304
+        r = dfo.read_prf(prf_path, o["r"], 0.0, 0.0, o["U0"], False, False)
+        U, V, W, uu, vv, ww, uv, uw, vw, ln_file, K, J = r[:12]
+        lnx, lny, lnz, nfx, nfy, nfz, dt = dfo.derive_filter_sizes(o["l"], o["f"], o["r"], U, o["t"], V, W, ln_file)
+        return dict(J=J, K=K, ns=ns, nm=o["m"], et=o["e"], dt=dt, normal=None,
+                    lund=("prf", U, V, W, uu, vv, ww, uv, uw, vw), lnx=lnx, lny=lny, lnz=lnz,
+                    nfx=nfx, nfy=nfy, nfz=nfz, profile=(U, V, W, uu, vv, ww, uv, uw, vw),
+                    mean_profile=o["p"], ring=o["ring"], plane_normal=r[12:15], plane_centre=r[15:18])
     if from_file:
         U, uu, vv, ww, uw = dfo.read_profile(profile_path, K)             # DF:1306-1307
     else:

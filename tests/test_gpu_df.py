@@ -64,19 +64,23 @@ def test_adapt_variants_match_reference(P):
 
 
 @pytest.mark.parametrize("impl", IMPLS)
-@pytest.mark.parametrize("tag", ["default", "rotated", "roundjet", "square", "ring", "dt", "profile"])
+@pytest.mark.parametrize("tag", ["default", "rotated", "roundjet", "square", "ring", "dt", "profile", "prf"])
 def test_time_loop_matches_reference_main(P, tag, impl, tmp_path):
     """The fused device loop on the reference's own random draws == the A the reference's main() built."""
     g = golden("main_%s.npz" % tag)
     prof = tmp_path / "profile_in.txt"
     prof.write_text(str(g["in_profile_text"]))
-    s = replay.setup(g["in_argv"], str(prof))
+    prf = tmp_path / "inlet.prf"
+    prf.write_text(str(g["in_prf_text"]))
+    s = replay.setup(g["in_argv"], str(prof), str(prf))
     J, K, ns = s["J"], s["K"], s["ns"]
     X = dfo.reference_stream(int(g["in_seed"]), ns, J, K, s["nfx"], s["nfy"], s["nfz"])
     slabs = np.ascontiguousarray(np.moveaxis(X, 0, 1))
     lund = P._lund
     if s["lund"][0] == "2d":
         fm = lund.lund_2d(*s["profile"], J, K, s["mean_profile"], s["ring"])
+    elif s["lund"][0] == "prf":
+        fm = lund.lund_prf(*s["profile"])
     else:
         fm = lund.lund_1d(*s["profile"], J, K)
     R = P.digitalfilters.prof_rotation_matrix(*s["normal"]) if s["normal"] is not None else None
@@ -253,14 +257,16 @@ def test_device_pointer_entries_and_kernel_timers(P):
     assert P._capi.launch_count() > 0
 
 
-@pytest.mark.parametrize("tag", ["default", "rotated", "roundjet", "dt", "profile"])
+@pytest.mark.parametrize("tag", ["default", "rotated", "roundjet", "dt", "profile", "prf"])
 def test_cli_main_is_a_drop_in(P, tag, tmp_path, monkeypatch):
     """`digitalfilters.main()` with the reference's own flags and a seeded global np.random reproduces what the
     reference's main() produced (golden): snapshot matrix, mean field, POD modes up to sign, PODFS.dat."""
     g = golden("main_%s.npz" % tag)
     monkeypatch.chdir(tmp_path)
     (tmp_path / "profile_in.txt").write_text(str(g["in_profile_text"]))
+    (tmp_path / "inlet.prf").write_text(str(g["in_prf_text"]))
     argv = [str(tmp_path / "profile_in.txt") if str(a) == "PROFILE" else str(a) for a in g["in_argv"]]
+    argv = [str(tmp_path / "inlet.prf") if a == "PRF" else a for a in argv]
     np.random.seed(int(g["in_seed"]))
     i_d = P.digitalfilters.main(argv)
     assert rel_err(i_d.mean_field, g["out_mean_field"]) < 1e-13

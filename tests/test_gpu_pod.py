@@ -122,12 +122,12 @@ def _check_pod(P, A, ns, npts, nm, dt, et, ref, ref_fc, weights=None, tol=1e-9):
     return i_d, dat
 
 
-@pytest.mark.parametrize("tag", ["default", "rotated", "roundjet", "square", "ring", "dt", "profile"])
+@pytest.mark.parametrize("tag", ["default", "rotated", "roundjet", "square", "ring", "dt", "profile", "prf"])
 def test_pod_and_fourier_match_reference_main(P, tag):
     """POD + Fourier fit of the reference's own snapshot matrix == what the reference's main() produced."""
     g = golden("main_%s.npz" % tag)
     o = replay.parse(g["in_argv"])
-    ns, npts = o["n"], o["j"] * o["k"]
+    ns, npts = o["n"], g["out_A"].shape[0] // 3          # (a .prf file sets the plane size itself)
     s = dict(nm=o["m"], et=o["e"], dt=float(g["out_dt"]))
     A = g["out_A"]
     ref = dict(nm=int(g["out_nm"]), temporal_modes=g["out_temporal_modes"], spatial_modes=g["out_spatial_modes"],

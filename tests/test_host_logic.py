@@ -129,3 +129,24 @@ def test_read_profile_matches_reference(tmp_path):
     for kma in (11, 32):
         got = np.stack(df.read_profile(str(f), kma))
         assert np.array_equal(got, g["out_kma%d" % kma])
+
+
+@pytest.mark.parametrize("tag", ["aligned", "massflow", "bulk_sdr", "testgrad"])
+def test_read_prf_matches_reference(tag, tmp_path):
+    """read_prf (DF:524-1035), the vectorised product version, against what the reference returned for the same
+    file and flags: raster size, plane normal and centre, length scale exactly; fields to rounding (the 2x2
+    box mean is summed in a different order)."""
+    df = pkg().digitalfilters
+    g = golden("read_prf.npz")
+    f = tmp_path / (tag + ".prf")
+    f.write_text(str(g["in_text_" + tag]))
+    a = g["in_args_" + tag]
+    out = df.read_prf(str(f), a[0], a[1], a[2], a[3], bool(a[4]), bool(a[5]))
+    names = ["U", "V", "W", "uu", "vv", "ww", "uv", "uw", "vw", "lnx", "kma", "jma", "xn", "yn", "zn", "xc", "yc", "zc"]
+    for name, v in zip(names, out):
+        ref = g["out_%s_%s" % (name, tag)]
+        if name in ("U", "V", "W", "uu", "vv", "ww", "uv", "uw", "vw"):
+            assert v.shape == ref.shape == (int(g["out_jma_" + tag]), int(g["out_kma_" + tag]))
+            assert np.abs(v - ref).max() <= 1e-13 * max(1.0, np.abs(ref).max()), (tag, name)
+        else:
+            assert np.array_equal(np.asarray(v), ref), (tag, name)

@@ -104,7 +104,22 @@ def test_pod_parts_match_reference():
     assert np.array_equal(tm, g["out_tm_sorted"])
 
 
-MAIN = ["default", "rotated", "roundjet", "square", "ring", "dt", "profile"]
+@pytest.mark.parametrize("tag", ["aligned", "massflow", "bulk_sdr", "testgrad"])
+def test_read_prf_matches_reference(tag, tmp_path):
+    """2-D .prf ingestion (DF:524-1035) against the reference's own outputs: axis-aligned raster, tilted and
+    jittered face list with mass-flow rescaling, omega instead of epsilon with bulk-velocity rescaling, and
+    the --test_gradients switch."""
+    g = load("read_prf.npz")
+    path = tmp_path / (tag + ".prf")
+    path.write_text(str(g["in_text_" + tag]))
+    a = g["in_args_" + tag]
+    out = dfo.read_prf(str(path), a[0], a[1], a[2], a[3], bool(a[4]), bool(a[5]))
+    names = ["U", "V", "W", "uu", "vv", "ww", "uv", "uw", "vw", "lnx", "kma", "jma", "xn", "yn", "zn", "xc", "yc", "zc"]
+    for name, v in zip(names, out):
+        assert np.array_equal(np.asarray(v), g["out_%s_%s" % (name, tag)]), (tag, name)
+
+
+MAIN = ["default", "rotated", "roundjet", "square", "ring", "dt", "profile", "prf"]
 
 
 @pytest.mark.parametrize("tag", MAIN)
@@ -114,7 +129,9 @@ def test_main_replay_matches_reference(tag, tmp_path):
     g = load("main_%s.npz" % tag)
     prof = tmp_path / "profile_in.txt"
     prof.write_text(str(g["in_profile_text"]))
-    s = replay.setup(g["in_argv"], str(prof))
+    prf = tmp_path / "inlet.prf"
+    prf.write_text(str(g["in_prf_text"]))
+    s = replay.setup(g["in_argv"], str(prof), str(prf))
     J, K, ns = s["J"], s["K"], s["ns"]
     X = dfo.reference_stream(int(g["in_seed"]), ns, J, K, s["nfx"], s["nfy"], s["nfz"])
     A = dfo.generate(X, ns, J, K, s["lnx"], s["lny"], s["lnz"], s["nfx"], s["nfy"], s["nfz"],
