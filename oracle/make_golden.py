@@ -275,6 +275,22 @@ def golden_read_prf(DF):
     np.savez(os.path.join(GOLD, "read_prf.npz"), **out)
 
 
+def golden_welch(SIG):
+    """fct_welch (SIG:10-68): Welch PSD of a two-tone test signal, the three windows, even and odd block
+    sizes, one and several 50 %-overlap blocks."""
+    rs = np.random.RandomState(11)
+    t = np.arange(600) * 0.01
+    x = np.sin(2 * np.pi * 7.0 * t) + 0.4 * np.cos(2 * np.pi * 19.0 * t + 0.3) + 0.05 * rs.standard_normal(t.size)
+    out = {"in_x": x, "in_fs": 100.0}
+    for N in (600, 128, 75):
+        for iw in (1, 2, 3):
+            f, Sxx, M = _quiet(SIG.fct_welch, x, 100.0, N, iw)
+            out["out_f_%d_%d" % (N, iw)] = np.array(f)
+            out["out_Sxx_%d_%d" % (N, iw)] = np.array(Sxx)
+            out["out_M_%d_%d" % (N, iw)] = M
+    np.savez(os.path.join(GOLD, "welch.npz"), **out)
+
+
 def golden_pod(POD):
     """calculate_correlation_matrix both branches, sort_eigenvalues with a NaN and a tie."""
     rs = np.random.RandomState(3)
@@ -326,6 +342,7 @@ def main():
     golden_pod(POD)
     golden_read_profile(DF)
     golden_read_prf(DF)
+    golden_welch(ref_py3._loaded["SIG"])
     for tag, (argv, seed) in MAIN_CASES.items():
         cap = golden_main(DF, POD, tag, argv, seed)
         print("main_%s: A %s nm %d N_FC %s" % (tag, cap["A"].shape, cap["nm"], cap["N_FC"]))

@@ -200,3 +200,25 @@ def synthetic_snapshots(M, N, seed=0, rank_r=40, noise=1e-3, row0=0, rows=None):
     ii ^= ii >> np.uint64(33)
     A += noise * ((ii >> np.uint64(11)).astype(np.float64) / 9007199254740992.0 - 0.5)
     return A
+
+
+def fct_welch(x, fs, N, iwindow):
+    """nsigproclib_no_mpi.py:10-68 (reached from POD:1373 in verbose mode).  Welch PSD with 50 % overlap; block
+    spectra are stored in complex64 before squaring, the running sum is float64 (imaginary part dropped), the
+    result is returned as complex64.  `-N/2`, `N/2-1` are python-2 integer divisions."""
+    w = {1: np.ones(N), 2: np.hanning(N), 3: np.blackman(N)}[iwindow]
+    Cw = N / np.sum(w ** 2)
+    noverlap = int(np.floor(N / 2))
+    M, end = 1, N
+    while end + noverlap <= x.size:
+        end += noverlap
+        M += 1
+    f = np.linspace((-N) // 2, N // 2 - 1, N) / N * fs
+    Sxx = np.zeros(N, dtype=np.complex64)
+    acc = np.zeros(N)
+    for j in range(M):
+        Sxx[:] = np.fft.fft(x[j * noverlap:j * noverlap + N] * w)
+        Sxx[:] = np.fft.fftshift(Sxx)
+        acc[:] = (acc + Cw / N / fs * Sxx * np.conj(Sxx)).real
+    Sxx[:] = acc / M
+    return f, Sxx, M

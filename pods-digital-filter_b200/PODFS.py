@@ -120,6 +120,17 @@ def POD(A, num_snapshots, num_points, num_components, correct_for_cell_volumes, 
     write_eigenvalues(num_valid_modes, ns, energy, restart_dir + "POD.eigenvalues.dat")
     if getattr(i_d, "verbose", False):
         write_temporal_modes(num_valid_modes, ns, dt, temporal_modes, restart_dir)
+        # POD:1366-1388: Welch PSD of the written temporal modes.  The reference plots them (POD_PSD_mode_j.png,
+        # matplotlib); here the same numbers go to a two-column text file next to the temporal modes.
+        from . import nsigproclib_no_mpi as sp
+        nw = num_modes_to_write
+        if nw < 0 or nw > num_modes_trunc:
+            nw = num_modes_trunc
+        i_d.PSD = np.zeros((N, nw))
+        for j in range(nw):
+            fs, Sxx, _ = sp.fct_welch(temporal_modes[:, j], 1. / dt / stride, N, iwindow)
+            i_d.PSD[:, j] = Sxx.real
+            np.savetxt(restart_dir + "POD_PSD_mode_" + str(j) + ".dat", np.column_stack([fs, Sxx.real]))
     print("\nCode completed.")
     print("==============================================================\n")
     i_d.temporal_modes = temporal_modes

@@ -8,7 +8,8 @@ from . import _capi          # noqa: F401  (fails loudly if libpodsdf.so has not
 from . import _lund          # noqa: F401
 from . import PODFS          # noqa: F401
 from . import HDF5           # noqa: F401
+from . import nsigproclib_no_mpi  # noqa: F401
 from . import digitalfilters  # noqa: F401
 from . import pipeline       # noqa: F401  (torch is imported lazily, only by the device drivers)
 
-__all__ = ["_capi", "_lund", "PODFS", "HDF5", "digitalfilters", "pipeline"]
+__all__ = ["_capi", "_lund", "PODFS", "HDF5", "nsigproclib_no_mpi", "digitalfilters", "pipeline"]

@@ -351,6 +351,7 @@ def test_cli_quickstart_and_verbose_outputs(P, tmp_path, monkeypatch):
     assert sum(n.startswith("PODFS_mode_") for n in names) == i_d.nm
     assert sum(n.endswith("E-01.prf") or n.endswith("E+00.prf") for n in names) == 5          # one plane file per step
     assert sum(n.startswith("POD.temporal_mode_") for n in names) >= i_d.nm
+    assert sum(n.startswith("POD_PSD_mode_") for n in names) == i_d.nm and i_d.PSD.shape == (5, i_d.nm)
     first = (tmp_path / "PODFS" / "PODFS_mean.prf").read_text().split("\n")
     assert first[0] == "# PODFS_mean # name of the profile" and first[10] == "data,x,y,z,u,v,w"
     assert first[11].startswith("0.000000000000,-0.500000000000,0.550000011921,")          # CFDCodeIntegration.rst:53

@@ -261,3 +261,19 @@ def test_podfs_reconstruction_evaluator(P):
     y2b = P.pipeline.temporal_reconstruction(c64b, indb, cntb, period, times)
     Ub = P.pipeline.reconstruct_field(res["Phi"][:, :10].contiguous(), res["mean"], y2b[:, :10]).cpu().numpy()
     assert np.abs(Ub - A).max() < 5e-6 * np.abs(A0).max()
+
+
+def test_welch_psd_matches_reference(P):
+    """`nsigproclib_no_mpi.fct_welch` on the device DFT == the reference's own outputs (SIG:10-68).  The
+    reference squares complex64 block spectra, so agreement is to float32 rounding of the largest line."""
+    g = golden("welch.npz")
+    sp = P.nsigproclib_no_mpi
+    for N in (600, 128, 75):
+        for iw in (1, 2, 3):
+            f, Sxx, M = sp.fct_welch(g["in_x"], float(g["in_fs"]), N, iw)
+            ref = g["out_Sxx_%d_%d" % (N, iw)]
+            assert M == int(g["out_M_%d_%d" % (N, iw)])
+            assert np.array_equal(f, g["out_f_%d_%d" % (N, iw)])
+            assert Sxx.dtype == np.complex64 and np.abs(Sxx - ref).max() < 4e-7 * np.abs(ref).max()
+    with pytest.raises(SystemExit):
+        sp.fct_welch(g["in_x"][:10], 1.0, 11, 1)

@@ -119,6 +119,17 @@ def test_read_prf_matches_reference(tag, tmp_path):
         assert np.array_equal(np.asarray(v), g["out_%s_%s" % (name, tag)]), (tag, name)
 
 
+def test_welch_psd_matches_reference():
+    """fct_welch (SIG:10-68) against the reference's own outputs."""
+    g = load("welch.npz")
+    for N in (600, 128, 75):
+        for iw in (1, 2, 3):
+            f, Sxx, M = podo.fct_welch(g["in_x"], float(g["in_fs"]), N, iw)
+            assert M == int(g["out_M_%d_%d" % (N, iw)])
+            assert np.array_equal(f, g["out_f_%d_%d" % (N, iw)])
+            assert np.array_equal(Sxx, g["out_Sxx_%d_%d" % (N, iw)])
+
+
 MAIN = ["default", "rotated", "roundjet", "square", "ring", "dt", "profile", "prf"]
 
 
