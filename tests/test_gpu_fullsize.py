@@ -152,3 +152,81 @@ def test_config4_shard_podfs_identities(P):
     ref = torch.fft.fftshift(torch.fft.fft(T_d, dim=0), dim=0) / N
     got = torch.view_as_complex(c)
     assert float((got - ref).abs().max()) < 1e-12 * float(ref.abs().max())
+
+
+GUARD = 8192     # doubles either side of every output
+
+
+def _guarded(torch, n):
+    """A device buffer of n doubles between two sentinel-filled guard zones; returns (whole, interior view)."""
+    whole = torch.full((n + 2 * GUARD,), -7.25e77, dtype=torch.float64, device="cuda")
+    return whole, whole[GUARD:GUARD + n]
+
+
+def _guards_intact(whole):
+    return bool((whole[:GUARD] == -7.25e77).all()) and bool((whole[-GUARD:] == -7.25e77).all())
+
+
+@pytest.mark.parametrize("J,K,nfx,nfy,nfz", [(7, 5, 2, 2, 2), (33, 65, 4, 4, 4), (64, 64, 10, 10, 10), (17, 130, 16, 8, 4),
+                                             (100, 31, 3, 6, 1), (1, 40, 2, 0, 3), (129, 127, 32, 32, 32)])
+def test_device_outputs_stay_inside_their_buffers(P, J, K, nfx, nfy, nfz):
+    """compute-sanitizer is unavailable on this pool: every device-pointer entry writes into a buffer with
+    sentinel guard zones on both sides (ragged sizes, generic and tuned kernels, both modes), the guards must be
+    untouched and every interior element overwritten."""
+    torch = pytest.importorskip("torch")
+    df = P.digitalfilters
+    ns = 21
+    p = df._plan(J, K, nfx, nfy, nfz, df._taps(nfx, max(nfx / 2, 1.0)), df._taps(nfy, max(nfy / 2, 1.0)),
+                 df._taps(nfz, max(nfz / 2, 1.0)))
+    rs = np.random.RandomState(1)
+    coef = rs.uniform(-1, 1, (12, J * K))
+    for impl in (1, 0):
+        for mask in (0, 0xFFF):
+            p.set_impl(impl)
+            p.set_chunk(8)
+            p.set_coefficients(coef if mask else None, mask)
+            n_out = ns * 3 * J * K
+            whole, out = _guarded(torch, n_out)
+            p.generate_seeded_dev(11, 5, ns, out.data_ptr(), 0)
+            torch.cuda.synchronize()
+            assert _guards_intact(whole) and not bool((out == -7.25e77).any()), ("seeded", impl, mask)
+            n_sl = (ns + 2 * nfx) * 3 * (J + 2 * nfy) * (K + 2 * nfz)
+            wsl, slabs = _guarded(torch, n_sl)
+            p.random_slabs_dev(11, 5, ns + 2 * nfx, slabs.data_ptr(), 0)
+            torch.cuda.synchronize()
+            assert _guards_intact(wsl) and not bool((slabs == -7.25e77).any()), ("slabs", impl, mask)
+            whole2, out2 = _guarded(torch, n_out)
+            p.generate_injected_dev(slabs.data_ptr(), ns + 2 * nfx, out2.data_ptr(), 0)
+            torch.cuda.synchronize()
+            assert _guards_intact(whole2) and _guards_intact(wsl), ("injected", impl, mask)
+            assert float((out - out2).abs().max()) < 1e-13 * max(1.0, float(out.abs().max()))
+
+
+@pytest.mark.parametrize("M,N,nm", [(48, 5, 3), (300, 129, 7), (3 * 1111, 257, 33), (4998, 128, 128)])
+def test_pod_device_outputs_stay_inside_their_buffers(P, M, N, nm):
+    torch = pytest.importorskip("torch")
+    capi, L = P._capi, P._capi.lib()
+    for layout in (0, 1):
+        wa, a = _guarded(torch, M * N)
+        a.copy_(torch.randn(M * N, dtype=torch.float64, device="cuda"))
+        wm, mean = _guarded(torch, M)
+        capi.check(L.podsdf_mean_rows_dev(0, a.data_ptr(), M, N, layout, mean.data_ptr(), 1, 0))
+        wc, C = _guarded(torch, N * N)
+        capi.check(L.podsdf_gram_dev(0, a.data_ptr(), M, N, layout, None, 0, 1.0 / N, C.data_ptr(), 0))
+        wl, lam = _guarded(torch, N)
+        wv, V = _guarded(torch, N * N)
+        V.copy_(C)
+        capi.check(L.podsdf_eig_sym_dev(0, V.data_ptr(), N, lam.data_ptr(), 0))
+        wt, T = _guarded(torch, N * nm)
+        T.copy_(V.view(N, N)[N - nm:].T.contiguous().view(-1))
+        dinv = torch.ones(nm, dtype=torch.float64, device="cuda")
+        wp, Phi = _guarded(torch, M * nm)
+        capi.check(L.podsdf_project_dev(0, a.data_ptr(), M, N, layout, T.data_ptr(), nm, dinv.data_ptr(), nm, 1.0 / N,
+                                        Phi.data_ptr(), 0))
+        wf, c = _guarded(torch, N * nm * 2)
+        capi.check(L.podsdf_dft_modes_dev(0, T.data_ptr(), N, nm, nm, c.data_ptr(), 0))
+        torch.cuda.synchronize()
+        for name, w, inner in (("A", wa, a), ("mean", wm, mean), ("C", wc, C), ("lam", wl, lam), ("V", wv, V),
+                               ("T", wt, T), ("Phi", wp, Phi), ("c", wf, c)):
+            assert _guards_intact(w), (name, layout)
+            assert not bool((inner == -7.25e77).any()), (name, layout)
