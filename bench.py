@@ -29,6 +29,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+DF_CHUNK = 1256      # planes per pass of the time loop (2500-plane shard = 2 passes; see profiles/r01_chunk_sweep.json)
 CFG3 = dict(J=512, K=512, nf=10, ln=5.0, profile="circular-hyperbolic-tangent", U0=1.0, u_dash=0.02, ring=0.5,
             planes_per_gpu=2500, total_steps_at_8_gpus=20000)
 CFG4 = dict(rows_per_gpu=393216, snapshots=10000, modes=100, et=0.9, dt=1.0e-3)
@@ -274,6 +275,9 @@ def main():
     taps = df._taps(nf, ln)
     plan = capi.DfPlan(J, K, nf, nf, nf, taps, taps, taps, device=local_rank)
     plan.set_impl(args.impl_kernels)
+    plan.set_chunk(DF_CHUNK)
+    n_passes = -(-n_planes // DF_CHUNK)                      # K-time + K-plane launches per step
+    planes_per_launch = n_planes / float(n_passes)
     coef, mask = pkg._lund.pack(*cfg3_lund(pkg), J, K)      # default normal (1,0,0): the rotation is the identity
     plan.set_coefficients(coef, mask)
     shard = pkg.pipeline.DfShard(plan, n_planes, dev)
@@ -312,7 +316,7 @@ def main():
     ms_per_step = ms_total / args.steps
     value = world * n_planes * args.steps / (ms_total * 1e-3)
 
-    # ---- roofline of the dominant kernel (K-plane: yz filter + Lund, one launch per 512-plane chunk)
+    # ---- roofline of the dominant kernel (K-plane: yz filter + Lund, one launch per pass of <= DF_CHUNK planes)
     b_plane, b_time, fl_total, fl_plane = df_algorithmic(J, K, nf, nf, nf)
     if args.rng == "injected":
         b_time = 24.0 * (J + 2 * nf) * (K + 2 * nf) * 2
@@ -321,9 +325,10 @@ def main():
     roofline = {
         "kernel": "df_plane_panel_kernel (z-pass + y-pass + Lund/rotation + mean, fused)" if plan_is_tuned(pkg, nf) else "df generic plane kernels",
         "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-        "peak_source": hbm_src, "traffic": kplane_traffic(nf, min(n_planes, 512)),
-        "algorithmic_bytes_per_plane": b_plane, "planes_per_launch": min(n_planes, 512),
-        "algorithmic_bytes_per_launch": b_plane * min(n_planes, 512),
+        "peak_source": hbm_src, "traffic": kplane_traffic(nf, planes_per_launch),
+        "algorithmic_bytes_per_plane": b_plane, "planes_per_launch": planes_per_launch,
+        "algorithmic_bytes_per_launch": b_plane * planes_per_launch,
+        "launches_per_step": n_passes, "avg_launch_ms": t_plane_ms / n_passes,
         "kernel_ms_per_step": t_plane_ms,
         "fp64": {"achieved_tflops": fl_plane * n_planes / (t_plane_ms * 1e-3) / 1e12, "peak_tflops": FP64_DFMA_PEAK_TFLOPS,
                  "frac": fl_plane * n_planes / (t_plane_ms * 1e-3) / 1e12 / FP64_DFMA_PEAK_TFLOPS,

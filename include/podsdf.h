@@ -70,8 +70,9 @@ PODSDF_API int podsdf_df_plan_create(int device, int J, int K, int nfx, int nfy,
                           const double* by, const double* bz, podsdf_df_plan** plan);
 PODSDF_API int podsdf_df_plan_destroy(podsdf_df_plan* plan);
 PODSDF_API int podsdf_df_plan_set_impl(podsdf_df_plan* plan, int impl);
-/* planes generated per internal pass (workspace = chunk*3*Jp*Kp doubles); rounded down to a multiple of 8
- * (minimum 8); default 512.  Results do not depend on it bitwise. */
+/* planes generated per internal pass (workspace = min(chunk, steps of the call)*3*Jp*Kp doubles, grown on
+ * demand); rounded down to a multiple of 8 (minimum 8); default: what fits a 12 GiB workspace, at most 1280.
+ * Results do not depend on it bitwise. */
 PODSDF_API int podsdf_df_plan_set_chunk(podsdf_df_plan* plan, int chunk_planes);
 
 /* ref: adapt1d DF:143-178, adapt2prf DF:180-231, adapt2d DF:233-485, rotate_velocity DF:1119-1131.

@@ -166,7 +166,10 @@ class DfPlan(object):
 
     def close(self):
         if getattr(self, "_h", None):
-            lib().podsdf_df_plan_destroy(self._h)
+            try:
+                lib().podsdf_df_plan_destroy(self._h)
+            except TypeError:          # interpreter shutdown: module globals are already gone
+                pass
             self._h = None
 
     __del__ = close

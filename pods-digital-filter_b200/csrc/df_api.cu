@@ -53,7 +53,7 @@ struct podsdf_df_plan {
   DfGeom g{};
   Taps bx{}, by{}, bz{};
   int impl = PODSDF_IMPL_AUTO;
-  int chunk = 512;
+  int chunk = 512;         // replaced at plan creation by default_chunk()
   // device state
   double* d_coef = nullptr;  // [12][P]
   unsigned mask = 0;
@@ -63,7 +63,7 @@ struct podsdf_df_plan {
   double* d_T2 = nullptr;  // generic path: [chunk][3][Jp][K]
   double* d_X = nullptr;   // host-injected / generic-generated staging: [chunk+2nfx][3][Np]
   double* d_out[2] = {nullptr, nullptr};  // host paths: [chunk][3][P]
-  int ws_chunk = 0;        // chunk the workspaces were sized for
+  int cap_core = 0, cap_t2 = 0, cap_x = 0, cap_out[2] = {0, 0};   // planes each workspace currently holds
   cudaStream_t s_compute = nullptr, s_copy = nullptr;
   cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
   std::vector<cudaEvent_t> ev_pool;  // timing events of the last call: (t0,t1,t2) per chunk
@@ -97,28 +97,41 @@ int free_workspace(podsdf_df_plan* p) {
     if (*q) cudaFree(*q);
     *q = nullptr;
   }
-  p->ws_chunk = 0;
+  p->cap_core = p->cap_t2 = p->cap_x = p->cap_out[0] = p->cap_out[1] = 0;
   return 0;
 }
 
-// T1 (+T2 for the generic plane path) sized for `chunk` planes
-int ensure_core_ws(podsdf_df_plan* p) {
-  if (p->ws_chunk != p->chunk) free_workspace(p);
-  const DfGeom& g = p->g;
-  if (!p->d_T1) PODSDF_CUDA(cudaMalloc(&p->d_T1, sizeof(double) * t1_doubles_per_plane(p) * (size_t)p->chunk));
-  if (!use_tuned_plane(p) && !p->d_T2)   // generic plane path only (allocated lazily: it is as large as T1)
-    PODSDF_CUDA(cudaMalloc(&p->d_T2, sizeof(double) * 3 * (size_t)g.Jp * g.K * (size_t)p->chunk));
-  p->ws_chunk = p->chunk;
+// Default planes per pass: as many as fit a 12 GiB T1 workspace, at most 1280.  Longer passes amortise the 2*nfx
+// warm-up slabs of the time filter (config 3: 14.6 ms per 2500 planes at 512, 14.0 ms from 840 up).
+int default_chunk(const podsdf_df_plan* p) {
+  const size_t per_plane = sizeof(double) * t1_doubles_per_plane(p);
+  const size_t fit = ((size_t)12 << 30) / per_plane;
+  const int c = (int)std::min<size_t>(fit, 1280) & ~7;
+  return c < 8 ? 8 : c;
+}
+
+// workspaces grow on demand to `need` planes (= min(chunk, steps of the call)); cudaFree synchronises the device,
+// so a buffer still read by an earlier asynchronous pass is never pulled away
+static int grow(double** buf, int* cap, int need, size_t doubles_per_plane, size_t extra_planes = 0) {
+  if (*buf && *cap >= need) return 0;
+  if (*buf) cudaFree(*buf);
+  *buf = nullptr;
+  *cap = 0;
+  PODSDF_CUDA(cudaMalloc(buf, sizeof(double) * doubles_per_plane * ((size_t)need + extra_planes)));
+  *cap = need;
   return 0;
 }
-int ensure_x_ws(podsdf_df_plan* p) {
-  if (!p->d_X)
-    PODSDF_CUDA(cudaMalloc(&p->d_X, sizeof(double) * 3 * p->g.Np * (size_t)(p->chunk + 2 * p->g.nfx)));
+// T1 (+T2 for the generic plane path, allocated lazily: it is as large as T1)
+int ensure_core_ws(podsdf_df_plan* p, int need) {
+  PODSDF_TRY(grow(&p->d_T1, &p->cap_core, need, t1_doubles_per_plane(p)));
+  if (!use_tuned_plane(p)) PODSDF_TRY(grow(&p->d_T2, &p->cap_t2, need, 3 * (size_t)p->g.Jp * p->g.K));
   return 0;
 }
-int ensure_out_ws(podsdf_df_plan* p) {
-  for (int i = 0; i < 2; ++i)
-    if (!p->d_out[i]) PODSDF_CUDA(cudaMalloc(&p->d_out[i], sizeof(double) * 3 * p->g.P * (size_t)p->chunk));
+int ensure_x_ws(podsdf_df_plan* p, int need) {
+  return grow(&p->d_X, &p->cap_x, need, 3 * (size_t)p->g.Np, 2 * (size_t)p->g.nfx);
+}
+int ensure_out_ws(podsdf_df_plan* p, int need) {
+  for (int i = 0; i < 2; ++i) PODSDF_TRY(grow(&p->d_out[i], &p->cap_out[i], need, 3 * (size_t)p->g.P));
   return 0;
 }
 
@@ -139,7 +152,7 @@ int run_chunk(podsdf_df_plan* p, const double* X_dev, bool gen, uint64_t seed, l
     return fail(PODSDF_ERR_UNSUPPORTED, "PODSDF_IMPL_TUNED requested but no tuned kernel for these filter widths");
   const double* X = X_dev;
   if (gen && !tt) {  // generic time filter needs materialised slabs
-    PODSDF_TRY(ensure_x_ws(p));
+    PODSDF_TRY(ensure_x_ws(p, nsteps));
     PODSDF_TRY(launch_df_random_slabs(p->g, seed, s_base, nsteps + 2 * p->g.nfx, p->d_X, st));
     X = p->d_X;
     gen = false;
@@ -223,6 +236,7 @@ int podsdf_df_plan_create(int device, int J, int K, int nfx, int nfy, int nfz, c
     podsdf_df_plan_destroy(p);
     return cuda_fail(e, "plan stream/event creation", __FILE__, __LINE__);
   }
+  p->chunk = default_chunk(p);
   *plan = p;
   return 0;
 }
@@ -358,7 +372,7 @@ int podsdf_df_generate_injected_dev(podsdf_df_plan* p, const double* slabs_dev, 
   const long nsteps = n_slabs - 2L * p->g.nfx;
   if (nsteps < 1) return fail(PODSDF_ERR_INVALID, "need at least 2*nfx+1 slabs");
   DeviceGuard guard(p->device);
-  PODSDF_TRY(ensure_core_ws(p));
+  PODSDF_TRY(ensure_core_ws(p, (int)std::min<long>(p->chunk, nsteps)));
   cudaStream_t st = (cudaStream_t)stream;
   p->ev_used = 0;
   p->ev_stream = st;
@@ -374,7 +388,7 @@ int podsdf_df_generate_seeded_dev(podsdf_df_plan* p, uint64_t seed, long t0, lon
   if (!p || !out_dev) return fail(PODSDF_ERR_INVALID, "null argument");
   if (nsteps < 1 || t0 < 0) return fail(PODSDF_ERR_INVALID, "bad step range");
   DeviceGuard guard(p->device);
-  PODSDF_TRY(ensure_core_ws(p));
+  PODSDF_TRY(ensure_core_ws(p, (int)std::min<long>(p->chunk, nsteps)));
   cudaStream_t st = (cudaStream_t)stream;
   p->ev_used = 0;
   p->ev_stream = st;
@@ -390,15 +404,19 @@ int podsdf_df_generate_seeded_dev(podsdf_df_plan* p, uint64_t seed, long t0, lon
 static int generate_host(podsdf_df_plan* p, const double* slabs_host, bool gen, uint64_t seed, long t0, long nsteps,
                          double* out_host) {
   DeviceGuard guard(p->device);
-  PODSDF_TRY(ensure_core_ws(p));
-  PODSDF_TRY(ensure_out_ws(p));
-  if (!gen) PODSDF_TRY(ensure_x_ws(p));
+  // the host link is ~100x slower than the kernels: short passes (<= 256 planes) start the first copy early and
+  // keep both staging buffers small; the extra warm-up slabs of the time filter hide behind the copies
+  const int hchunk = std::min(p->chunk, 256);
+  const int need = (int)std::min<long>(hchunk, nsteps);
+  PODSDF_TRY(ensure_core_ws(p, need));
+  PODSDF_TRY(ensure_out_ws(p, need));
+  if (!gen) PODSDF_TRY(ensure_x_ws(p, need));
   const DfGeom& g = p->g;
   p->ev_used = 0;
   p->ev_stream = p->s_compute;
   int i = 0;
-  for (long t = 0; t < nsteps; t += p->chunk, ++i) {
-    const int n = (int)std::min<long>(p->chunk, nsteps - t);
+  for (long t = 0; t < nsteps; t += hchunk, ++i) {
+    const int n = (int)std::min<long>(hchunk, nsteps - t);
     const int b = i & 1;
     if (i >= 2) PODSDF_CUDA(cudaStreamWaitEvent(p->s_compute, p->ev_copied[b], 0));
     if (!gen)
