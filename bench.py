@@ -276,7 +276,7 @@ def main():
     plan = capi.DfPlan(J, K, nf, nf, nf, taps, taps, taps, device=local_rank)
     plan.set_impl(args.impl_kernels)
     plan.set_chunk(DF_CHUNK)
-    n_passes = -(-n_planes // DF_CHUNK)                      # K-time + K-plane launches per step
+    n_passes = -(-n_planes // plan.info()["chunk"])          # K-time + K-plane launches per step
     planes_per_launch = n_planes / float(n_passes)
     coef, mask = pkg._lund.pack(*cfg3_lund(pkg), J, K)      # default normal (1,0,0): the rotation is the identity
     plan.set_coefficients(coef, mask)
@@ -316,6 +316,8 @@ def main():
     ms_per_step = ms_total / args.steps
     value = world * n_planes * args.steps / (ms_total * 1e-3)
 
+    info = plan.info()
+    assert info["passes"] == n_passes, (info, n_passes)
     # ---- roofline of the dominant kernel (K-plane: yz filter + Lund, one launch per pass of <= DF_CHUNK planes)
     b_plane, b_time, fl_total, fl_plane = df_algorithmic(J, K, nf, nf, nf)
     if args.rng == "injected":
@@ -323,7 +325,10 @@ def main():
     hbm_peak, hbm_src = measured_peaks()
     achieved = b_plane * n_planes / (t_plane_ms * 1e-3) / 1e9
     roofline = {
-        "kernel": "df_plane_panel_kernel (z-pass + y-pass + Lund/rotation + mean, fused)" if plan_is_tuned(pkg, nf) else "df generic plane kernels",
+        "kernel": ("df_plane_panel1_kernel<%d,%d> (z-pass + y-pass + Lund + mean fused, one CTA per strip/plane/component)"
+                   % (2 * nf + 1, 2 * nf + 1) if info["diagonal"] else
+                   "df_plane_panel_kernel<%d,%d> (z-pass + y-pass + coupled Lund/rotation + mean fused)" % (2 * nf + 1, 2 * nf + 1))
+        if info["tuned_plane"] else "df generic plane kernels",
         "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
         "peak_source": hbm_src, "traffic": kplane_traffic(nf, planes_per_launch),
         "algorithmic_bytes_per_plane": b_plane, "planes_per_launch": planes_per_launch,
@@ -387,17 +392,14 @@ def main():
                                    "(config 3's 20000 steps at 8 GPUs)" % (nf, ln, n_planes),
                        "rng": args.rng, "planes_per_step_per_gpu": n_planes, "parallelism": "time-sharded x%d" % world,
                        "l2": "every step writes %.1f GB per GPU (>> 126 MB L2); no flush needed" % (n_planes * 3 * J * K * 8 / 1e9),
-                       "kernels": "tuned" if plan_is_tuned(pkg, nf) else "generic"},
+                       "kernels": "tuned" if (info["tuned_time"] and info["tuned_plane"]) else "generic",
+                       "planes_per_pass": info["chunk"]},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_timed,
             "gpu_launches_total": launches_all, "clocks": clocks, "pod": pod,
         }
         _emit(line)
     if world > 1:
         dist.destroy_process_group()
-
-
-def plan_is_tuned(pkg, nf):
-    return (2 * nf + 1) in (9, 13, 17, 21, 25, 33, 49, 65, 97, 129)
 
 
 def run_pod(args, pkg, torch, dist, dev, local_rank, rank, world, barrier, max_over_ranks):

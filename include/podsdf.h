@@ -110,6 +110,11 @@ PODSDF_API int podsdf_df_random_slabs_dev(podsdf_df_plan* plan, uint64_t seed, l
 /* device time (ms) of the kernels of the last generate_* call on this plan: [0] time filter,
  * [1] plane filter + Lund, measured with CUDA events on the launching stream */
 PODSDF_API int podsdf_df_last_kernel_ms(podsdf_df_plan* plan, double* ms2);
+/* what the plan will run with its current impl / coefficients / rotation: info[0] planes per pass (chunk),
+ * info[1] 1 if a tuned time filter exists for 2*nfx+1 taps, info[2] 1 if a tuned plane filter exists for
+ * (2*nfy+1, 2*nfz+1) and the current transform, info[3] 1 if the transform is diagonal (per-component plane
+ * kernel) and 0 if it couples components, info[4] passes of the last generate_* call */
+PODSDF_API int podsdf_df_plan_info(podsdf_df_plan* plan, int* info5);
 
 /* ------------------------------------------------------------------------------ PODFS */
 /* ref: mean removal DF:1492-1495.  mean[M] = mean over time; A -= mean (in place) if subtract. */

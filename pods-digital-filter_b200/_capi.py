@@ -38,6 +38,7 @@ SIGNATURES = {
     "podsdf_df_plan_destroy": [_vp],
     "podsdf_df_plan_set_impl": [_vp, _i],
     "podsdf_df_plan_set_chunk": [_vp, _i],
+    "podsdf_df_plan_info": [_vp, ctypes.POINTER(_i)],
     "podsdf_df_set_coefficients": [_vp, _vp, ctypes.c_uint],
     "podsdf_df_set_rotation": [_vp, _vp],
     "podsdf_df_filter_block_host": [_vp, _vp, _vp],
@@ -237,6 +238,12 @@ class DfPlan(object):
 
     def random_slabs_dev(self, seed, s0, n, out_ptr, stream=0):
         check(lib().podsdf_df_random_slabs_dev(self._h, int(seed), int(s0), int(n), _vp(out_ptr), _vp(stream)))
+
+    def info(self):
+        """dict(chunk, tuned_time, tuned_plane, diagonal, passes) -- what the plan runs with its current settings."""
+        a = (_i * 5)()
+        check(lib().podsdf_df_plan_info(self._h, a))
+        return dict(chunk=a[0], tuned_time=bool(a[1]), tuned_plane=bool(a[2]), diagonal=bool(a[3]), passes=a[4])
 
     def last_kernel_ms(self):
         ms = np.zeros(2)

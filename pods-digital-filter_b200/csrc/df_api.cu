@@ -492,4 +492,14 @@ int podsdf_df_last_kernel_ms(podsdf_df_plan* p, double* ms2) {
   return 0;
 }
 
+int podsdf_df_plan_info(podsdf_df_plan* p, int* info5) {
+  if (!p || !info5) return fail(PODSDF_ERR_INVALID, "null argument");
+  info5[0] = p->chunk;
+  info5[1] = use_tuned_time(p) ? 1 : 0;
+  info5[2] = use_tuned_plane(p) ? 1 : 0;
+  info5[3] = df_transform_is_diagonal(p->have_coef, p->mask, p->rot) ? 1 : 0;
+  info5[4] = (int)(p->ev_used / 3);
+  return 0;
+}
+
 }  // extern "C"

@@ -248,6 +248,10 @@ def test_device_pointer_entries_and_kernel_timers(P):
     assert np.array_equal(out.cpu().numpy(), host)
     t_time, t_plane = p.last_kernel_ms()
     assert t_time > 0 and t_plane > 0
+    assert p.info() == dict(chunk=16, tuned_time=True, tuned_plane=True, diagonal=True, passes=3)
+    p.set_rotation(P.digitalfilters.prof_rotation_matrix(1.0, 1.0, 0.5))
+    assert p.info()["diagonal"] is False
+    p.set_rotation(None)
     slabs = torch.empty((ns + 2 * nf, 3, J + 2 * nf, K + 2 * nf), dtype=torch.float64, device="cuda:0")
     p.random_slabs_dev(5, 3, ns + 2 * nf, slabs.data_ptr(), 0)
     out2 = torch.empty_like(out)
