@@ -150,3 +150,24 @@ def test_read_prf_matches_reference(tag, tmp_path):
             assert np.abs(v - ref).max() <= 1e-13 * max(1.0, np.abs(ref).max()), (tag, name)
         else:
             assert np.array_equal(np.asarray(v), ref), (tag, name)
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs first): exactly one JSON line on stdout with the
+    contract's keys; it must not need a GPU."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "1", "--no-pod"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.split("\n") if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "df_planes_per_s" and d["unit"] == "planes/s"
+    assert d["higher_is_better"] is True and d["steps"] == 1 and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "planes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"]
