@@ -91,9 +91,26 @@ def df_algorithmic(J, K, nfx, nfy, nfz):
 class ClockSampler(object):
     """nvidia-smi clocks line of B200_PROFILING.md, sampled during the timed region."""
 
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
+
     def __init__(self, index):
-        self.rows = []
+        self.rows = []          # (time, sm_mhz, reasons bitmask, power_w)
+        self.smax = None
+        self.stop_flag = False
+        self.mode = None
         self.proc = None
+        try:                    # NVML in-process: a sample every few ms (the timed region is ~0.1-0.3 s)
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.mode = "nvml"
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.mode = None
         q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -101,36 +118,64 @@ class ClockSampler(object):
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + q,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.mode = "nvidia-smi"
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        nv, h = self.nv, self.h
+        while not self.stop_flag:
+            try:
+                mhz = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                except Exception:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                try:
+                    watts = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                except Exception:
+                    watts = None
+                self.rows.append((time.time(), mhz, mask, watts))
+            except Exception:
+                pass
+            time.sleep(0.003)
+
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append((time.time(), line.strip()))
-
-    def stop(self, t0, t1):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, smax, reasons = [], None, set()
-        for ts, line in self.rows:
-            f = [x.strip() for x in line.split(",")]
+            f = [x.strip() for x in line.strip().split(",")]
             if len(f) < 9:
                 continue
             try:
-                smax = float(f[2])
-                if t0 - 0.05 <= ts <= t1 + 0.15:
-                    sm.append(float(f[1]))
-                    for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                        if v.lower().startswith("active"):
-                            reasons.add(name)
+                self.smax = float(f[2])
+                mask = 0
+                for (name, bit), v in zip(self.REASONS, f[5:9]):
+                    if v.lower().startswith("active"):
+                        mask |= bit
+                self.rows.append((time.time(), float(f[1]), mask, float(f[3])))
             except ValueError:
                 continue
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
-                "samples": len(sm)}
+
+    def stop(self, t0, t1):
+        if self.mode is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"]}
+        if self.mode == "nvidia-smi":
+            time.sleep(0.15)
+            self.proc.terminate()
+        self.stop_flag = True
+        pad = 0.0 if self.mode == "nvml" else 0.15
+        rows = [r for r in self.rows if t0 - 0.02 <= r[0] <= t1 + pad]
+        reasons = set()
+        for _, _, mask, _ in rows:
+            for name, bit in self.REASONS:
+                if mask & bit:
+                    reasons.add(name)
+        sm = [r[1] for r in rows]
+        watts = [r[3] for r in rows if r[3] is not None]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_min_mhz": float(min(sm)) if sm else None,
+                "sm_max_mhz": self.smax, "reasons": sorted(reasons), "samples": len(sm), "source": self.mode,
+                "power_w_median": float(np.median(watts)) if watts else None}
 
 
 def cfg3_lund(pkg):
@@ -217,7 +262,9 @@ def run_reference(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=8,
+                    help="timed steps; the default 8 shards of 2500 planes are config 3's whole 20000-step job")
+    ap.add_argument("--sustained-steps", type=int, default=40, help="extra back-to-back steps for the sustained figure (0 = off)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--df-planes", type=int, default=CFG3["planes_per_gpu"])
@@ -298,7 +345,8 @@ def main():
         df_step()
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    time.sleep(0.3 if rank == 0 else 0.0)
+    if sampler is not None and sampler.mode == "nvidia-smi":
+        time.sleep(0.3)                                  # the CLI sampler needs time to start; NVML does not
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     w0 = time.time()
@@ -315,6 +363,27 @@ def main():
     clocks = sampler.stop(w0, w1) if sampler else None
     ms_per_step = ms_total / args.steps
     value = world * n_planes * args.steps / (ms_total * 1e-3)
+
+    # ---- sustained leg: the same step back to back for ~0.6 s, long enough for the board's power controller to
+    # settle (FP64-heavy kernels run into sw_power_cap on this pool); reported next to `value`, never instead of it
+    sustained = None
+    if args.sustained_steps > 0:
+        barrier()
+        sampler2 = ClockSampler(local_rank) if rank == 0 else None
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        v0 = time.time()
+        s0.record(stream)
+        for _ in range(args.sustained_steps):
+            df_step()
+        s1.record(stream)
+        barrier()
+        v1 = time.time()
+        ms_sus = max_over_ranks(s0.elapsed_time(s1))
+        tt_s, tp_s = plan.last_kernel_ms()
+        sustained = {"value": world * n_planes * args.sustained_steps / (ms_sus * 1e-3), "unit": "planes/s",
+                     "steps": args.sustained_steps, "ms_per_step": ms_sus / args.sustained_steps,
+                     "time_filter_ms": tt_s, "plane_filter_ms": tp_s,
+                     "clocks": sampler2.stop(v0, v1) if sampler2 else None}
 
     info = plan.info()
     assert info["passes"] == n_passes, (info, n_passes)
@@ -395,7 +464,7 @@ def main():
                        "kernels": "tuned" if (info["tuned_time"] and info["tuned_plane"]) else "generic",
                        "planes_per_pass": info["chunk"]},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_timed,
-            "gpu_launches_total": launches_all, "clocks": clocks, "pod": pod,
+            "gpu_launches_total": launches_all, "clocks": clocks, "sustained": sustained, "pod": pod,
         }
         _emit(line)
     if world > 1:
