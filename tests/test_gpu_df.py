@@ -369,3 +369,32 @@ def _with_hdf5_fields(P, i_d):
     P.PODFS.fourier_coefficients(i_d)
     P.PODFS.pod2prf(i_d)
     return i_d
+
+
+def test_host_path_short_passes_match_device_path(P):
+    """The host entries cut the run into passes of <= 256 planes (double-buffered D2H), the device entries into
+    passes of the plan's chunk: same bits, pinned or pageable output, generated and injected stream."""
+    torch = pytest.importorskip("torch")
+    J, K, nf, ns = 48, 80, 6, 700
+    df = P.digitalfilters
+    p = df._plan(J, K, nf, nf, nf, df._taps(nf, 3.0), df._taps(nf, 3.0), df._taps(nf, 3.0))
+    rs = np.random.RandomState(2)
+    coef = rs.uniform(0.5, 1.5, (12, J * K))
+    p.set_coefficients(coef, 0b111100010001)
+    assert p.info()["chunk"] == 1280
+    dev = torch.empty((ns, 3, J, K), dtype=torch.float64, device="cuda")
+    p.generate_seeded_dev(77, 40, ns, dev.data_ptr(), 0)
+    torch.cuda.synchronize()
+    assert p.info()["passes"] == 1
+    host = p.generate_seeded(77, 40, ns)                       # pageable numpy output
+    assert p.info()["passes"] == 3                             # 256 + 256 + 188
+    assert np.array_equal(host, dev.cpu().numpy())
+    pinned, owner = P._capi.pinned_empty((ns, 3, J, K))
+    p.generate_seeded(77, 40, ns, out=pinned)
+    assert np.array_equal(pinned, host)
+    owner.free()
+    slabs = p.random_slabs(77, 40, ns + 2 * nf)
+    inj = p.generate_injected(slabs)
+    assert rel_err(inj, host) < 1e-14                          # injected mode runs the tensor-path time filter
+    p.set_chunk(96)
+    assert np.array_equal(p.generate_injected(slabs), inj)     # and is itself independent of the pass length
