@@ -138,6 +138,17 @@ PODSDF_API int podsdf_gram_last_ms(double* ms);
  * `_dev`: in place -- on exit ROW j of C_dev_inout_V is eigenvector j (no transpose pass).
  * The sort / NaN guard / validity count / scaling of POD:1310-1327, 1430-1447 stay in the Python shim. */
 PODSDF_API int podsdf_eig_sym_host(int device, const double* C_host, long N, double* lambda_host, double* V_host);
+
+/* "All eigenvalues + the nm leading eigenvectors" (what PODFS.py:1329-1333 consumes of linalg.eig's result):
+ * lambda[N] ascending as above; on exit rows 0..nm-1 of C (dev) / V[nm][N] (host) are the unit eigenvectors of the
+ * nm LARGEST eigenvalues in DESCENDING order; the remaining rows of C are scratch.  *path (may be NULL) = 1 when the
+ * tridiagonal route ran (Dsytrd, bisection, inverse iteration, Dormtr, re-orthonormalisation: the divide-and-conquer
+ * and the N x N back-transformation are skipped), 0 when the leading eigenvalues were not well separated (relative
+ * gap below 1e-7), a residual check failed or the size is unusual, and the full solver of podsdf_eig_sym_* ran. */
+PODSDF_API int podsdf_eig_sym_top_dev(int device, double* C_dev_inout_V, long N, int nm, double* lambda_dev, int* path,
+                           void* stream);
+PODSDF_API int podsdf_eig_sym_top_host(int device, const double* C_host, long N, int nm, double* lambda_host,
+                            double* V_host, int* path);
 PODSDF_API int podsdf_eig_sym_dev(int device, double* C_dev_inout_V, long N, double* lambda_dev, void* stream);
 
 /* ref: projection POD:1329-1333.  Phi[M][nm] = A (M x N) . T (N x nm) . diag(dinv) * scale,

@@ -55,6 +55,8 @@ SIGNATURES = {
     "podsdf_gram_dev": [_i, _vp, _l, _l, _i, _vp, _l, _d, _vp, _vp],
     "podsdf_gram_last_ms": [_vp],
     "podsdf_eig_sym_host": [_i, _vp, _l, _vp, _vp],
+    "podsdf_eig_sym_top_dev": [_i, _vp, _l, _i, _vp, ctypes.POINTER(_i), _vp],
+    "podsdf_eig_sym_top_host": [_i, _vp, _l, _i, _vp, _vp, ctypes.POINTER(_i)],
     "podsdf_eig_sym_dev": [_i, _vp, _l, _vp, _vp],
     "podsdf_project_host": [_i, _vp, _l, _l, _i, _vp, _l, _vp, _i, _d, _vp],
     "podsdf_project_dev": [_i, _vp, _l, _l, _i, _vp, _l, _vp, _i, _d, _vp, _vp],
@@ -278,6 +280,18 @@ def eig_sym(C, device=0):
     V = np.empty((N, N))
     check(lib().podsdf_eig_sym_host(device, ptr(C), N, ptr(lam), ptr(V)))
     return lam, V
+
+
+def eig_sym_top(C, nm, device=0):
+    """All eigenvalues (ascending) and the unit eigenvectors of the nm largest as ROWS, descending; also returns
+    which route ran (1 = tridiagonal route, 0 = full solver)."""
+    C = f64(C, name="C")
+    N = C.shape[0]
+    lam = np.empty(N)
+    V = np.empty((int(nm), N))
+    path = _i(0)
+    check(lib().podsdf_eig_sym_top_host(device, ptr(C), N, int(nm), ptr(lam), ptr(V), ctypes.byref(path)))
+    return lam, V, path.value
 
 
 def project(A, T, dinv, nm, scale, layout=LAYOUT_ROWS_BY_TIME, device=0):

@@ -2,10 +2,12 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <cmath>
 #include <mutex>
 #include <vector>
 
 #include "../../include/podsdf.h"
+#include "eig_kernels.cuh"
 #include "pod_kernels.cuh"
 
 using namespace podsdf;
@@ -20,7 +22,7 @@ struct Scratch {
   double* p = nullptr;
   size_t bytes = 0;
 };
-Scratch g_scratch[64][2];
+Scratch g_scratch[64][3];
 std::mutex g_scratch_mu;
 int scratch_get(int device, int slot, size_t bytes, double** out) {
   std::lock_guard<std::mutex> lk(g_scratch_mu);
@@ -57,6 +59,14 @@ struct Cusolver {
   cusolverStatus_t (*set_stream)(cusolverDnHandle_t, cudaStream_t) = nullptr;
   cusolverStatus_t (*bufsize)(cusolverDnHandle_t, int, int, int, const double*, int, const double*, int*) = nullptr;
   cusolverStatus_t (*syevd)(cusolverDnHandle_t, int, int, int, double*, int, double*, double*, int, int*) = nullptr;
+  // tridiagonal reduction and its back-transformation (the "eigenvalues + leading vectors" route)
+  cusolverStatus_t (*sytrd_bufsize)(cusolverDnHandle_t, int, int, const double*, int, const double*, const double*,
+                                    const double*, int*) = nullptr;
+  cusolverStatus_t (*sytrd)(cusolverDnHandle_t, int, int, double*, int, double*, double*, double*, double*, int, int*) = nullptr;
+  cusolverStatus_t (*ormtr_bufsize)(cusolverDnHandle_t, int, int, int, int, int, const double*, int, const double*,
+                                    const double*, int, int*) = nullptr;
+  cusolverStatus_t (*ormtr)(cusolverDnHandle_t, int, int, int, int, int, double*, int, double*, double*, int, double*, int,
+                            int*) = nullptr;
   std::string err;
 };
 
@@ -80,19 +90,24 @@ Cusolver& cusolver() {
     cs.bufsize = (decltype(cs.bufsize))dlsym(cs.lib, "cusolverDnDsyevd_bufferSize");
     cs.syevd = (decltype(cs.syevd))dlsym(cs.lib, "cusolverDnDsyevd");
     if (!cs.create || !cs.destroy || !cs.set_stream || !cs.bufsize || !cs.syevd) cs.err = "libcusolver lacks Dsyevd";
+    cs.sytrd_bufsize = (decltype(cs.sytrd_bufsize))dlsym(cs.lib, "cusolverDnDsytrd_bufferSize");
+    cs.sytrd = (decltype(cs.sytrd))dlsym(cs.lib, "cusolverDnDsytrd");
+    cs.ormtr_bufsize = (decltype(cs.ormtr_bufsize))dlsym(cs.lib, "cusolverDnDormtr_bufferSize");
+    cs.ormtr = (decltype(cs.ormtr))dlsym(cs.lib, "cusolverDnDormtr");
   });
   return cs;
 }
+
+cusolverDnHandle_t g_handles[64] = {};
+std::recursive_mutex g_solver_mu;            // one solve at a time per process: the handles are shared
 
 // eigen-decomposition in place: on exit row j of C is eigenvector j (ascending eigenvalues)
 int eig_inplace(int device, double* C_dev, long N, double* lambda_dev, cudaStream_t st) {
   if (N > 46340) return fail(PODSDF_ERR_UNSUPPORTED, "N too large for the 32-bit cuSOLVER interface");
   Cusolver& cs = cusolver();
   if (!cs.err.empty()) return fail(PODSDF_ERR_CUDA, cs.err);
-  static cusolverDnHandle_t handles[64] = {};
-  static std::mutex mu;
-  std::lock_guard<std::mutex> lk(mu);      // one solve at a time per process: the handle is shared
-  cusolverDnHandle_t& h = handles[device & 63];
+  std::lock_guard<std::recursive_mutex> lk(g_solver_mu);
+  cusolverDnHandle_t& h = g_handles[device & 63];
   if (!h && cs.create(&h) != 0) return fail(PODSDF_ERR_CUDA, "cusolverDnCreate failed");
   int rc = 0, lwork = 0;
   double* work = nullptr;
@@ -114,6 +129,94 @@ int eig_inplace(int device, double* C_dev, long N, double* lambda_dev, cudaStrea
     else if (hinfo != 0) rc = fail(PODSDF_ERR_NUMERIC, "Dsyevd did not converge, info = " + std::to_string(hinfo));
   }
   return rc;
+}
+
+// All eigenvalues (ascending, lambda_dev) and the eigenvectors of the nm largest: on exit rows 0..nm-1 of C are
+// those eigenvectors in DESCENDING order of the eigenvalue (the other rows are scratch).
+// Route 1: Dsytrd -> bisection for all eigenvalues -> inverse iteration for nm vectors of T -> Dormtr -> Cholesky-QR
+// (the divide-and-conquer and the N x N back-transformation of Dsyevd are skipped).  Route 0 (taken when the
+// leading eigenvalues are not well separated, when a check of route 1 fails, or for small / unusual sizes): the
+// full Dsyevd on a saved copy of C, then the leading rows are gathered.  *path reports which one ran.
+int eig_top_inplace(int device, double* C_dev, long N, int nm, double* lambda_dev, cudaStream_t st, int* path) {
+  if (N > 46340) return fail(PODSDF_ERR_UNSUPPORTED, "N too large for the 32-bit cuSOLVER interface");
+  if (nm < 1 || nm > N) return fail(PODSDF_ERR_INVALID, "nm must be in 1..N");
+  Cusolver& cs = cusolver();
+  if (!cs.err.empty()) return fail(PODSDF_ERR_CUDA, cs.err);
+  std::lock_guard<std::recursive_mutex> lk(g_solver_mu);
+  const int n = (int)N;
+  const bool eligible = cs.sytrd && cs.sytrd_bufsize && cs.ormtr && cs.ormtr_bufsize && N >= 256 && nm <= 512 && 4L * nm <= N;
+  // scratch: [C copy | Z nm*N | d | e | tau | e2 | lam host-mirror unused | bounds 4 | resid nm | S nm*nm | flag | invit]
+  const size_t nn = (size_t)N * N, zn = (size_t)nm * N;
+  const size_t invit = eligible ? tridiag_invit_workspace_doubles(N, nm) : 0;
+  const size_t total = nn + zn + 4 * (size_t)N + 8 + (size_t)nm + (size_t)nm * nm + 2 + invit;
+  double* ws = nullptr;
+  PODSDF_TRY(scratch_get(device, 2, sizeof(double) * total, &ws));
+  double* Ccopy = ws;
+  double* Z = Ccopy + nn;
+  double* d = Z + zn;
+  double* e = d + N;
+  double* tau = e + N;
+  double* e2 = tau + N;
+  double* bounds = e2 + N;
+  double* resid = bounds + 8;
+  double* S = resid + nm;
+  int* flag = reinterpret_cast<int*>(S + (size_t)nm * nm);
+  double* winv = S + (size_t)nm * nm + 2;
+  *path = 0;
+  int rc = 0;
+  bool fast_ok = false;
+  if (eligible) {
+    PODSDF_CUDA(cudaMemcpyAsync(Ccopy, C_dev, sizeof(double) * nn, cudaMemcpyDeviceToDevice, st));
+    cusolverDnHandle_t& h = g_handles[device & 63];
+    if (!h && cs.create(&h) != 0) return fail(PODSDF_ERR_CUDA, "cusolverDnCreate failed");
+    if (cs.set_stream(h, st) != 0) return fail(PODSDF_ERR_CUDA, "cusolverDnSetStream failed");
+    int lw1 = 0, lw2 = 0;
+    // CUBLAS_FILL_MODE_LOWER = 0, CUBLAS_SIDE_LEFT = 0, CUBLAS_OP_N = 0
+    if (cs.sytrd_bufsize(h, 0, n, C_dev, n, d, e, tau, &lw1) != 0) return fail(PODSDF_ERR_CUDA, "Dsytrd_bufferSize failed");
+    if (cs.ormtr_bufsize(h, 0, 0, 0, n, nm, C_dev, n, tau, Z, n, &lw2) != 0)
+      return fail(PODSDF_ERR_CUDA, "Dormtr_bufferSize failed");
+    const int lwork = std::max(lw1, lw2);
+    double* work = nullptr;
+    PODSDF_TRY(scratch_get(device, 1, sizeof(double) * (size_t)std::max(lwork, 1), &work));
+    DevBuf info;
+    if (info.alloc(8) != cudaSuccess) return fail(PODSDF_ERR_CUDA, "eigen-solver workspace allocation failed");
+    if (cs.sytrd(h, 0, n, C_dev, n, d, e, tau, work, lwork, (int*)info.p) != 0) return fail(PODSDF_ERR_CUDA, "Dsytrd failed");
+    PODSDF_TRY(launch_tridiag_eigenvalues(d, e, N, e2, bounds, lambda_dev, st));
+    // the leading nm+1 eigenvalues decide whether independent inverse iterations are safe
+    std::vector<double> top((size_t)nm + 1);
+    const long first = N - 1 - nm;      // ascending index of the (nm+1)-th largest (>= 0 because 4 nm <= N)
+    PODSDF_CUDA(cudaMemcpyAsync(top.data(), lambda_dev + first, sizeof(double) * (nm + 1), cudaMemcpyDeviceToHost, st));
+    PODSDF_CUDA(cudaStreamSynchronize(st));
+    const double lmax = std::fabs(top[nm]);
+    bool separated = lmax > 0.0;
+    for (int j = 0; j < nm && separated; ++j)
+      if (!(top[j + 1] - top[j] > 1.0e-7 * lmax)) separated = false;
+    if (separated) {
+      PODSDF_TRY(launch_tridiag_invit(d, e, bounds, lambda_dev, N, nm, winv, Z, resid, st));
+      if (cs.ormtr(h, 0, 0, 0, n, nm, C_dev, n, tau, Z, n, work, lwork, (int*)info.p) != 0)
+        return fail(PODSDF_ERR_CUDA, "Dormtr failed");
+      PODSDF_TRY(launch_orthonormalize_rows(Z, N, nm, S, flag, st));
+      std::vector<double> hres((size_t)nm);
+      int hflag = 1;
+      PODSDF_CUDA(cudaMemcpyAsync(hres.data(), resid, sizeof(double) * nm, cudaMemcpyDeviceToHost, st));
+      PODSDF_CUDA(cudaMemcpyAsync(&hflag, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+      PODSDF_CUDA(cudaStreamSynchronize(st));
+      fast_ok = hflag == 0;
+      for (int j = 0; j < nm && fast_ok; ++j)
+        if (!(hres[j] < 1.0e-12)) fast_ok = false;
+    }
+    if (!fast_ok) PODSDF_CUDA(cudaMemcpyAsync(C_dev, Ccopy, sizeof(double) * nn, cudaMemcpyDeviceToDevice, st));
+  }
+  if (fast_ok) {
+    *path = 1;
+  } else {
+    rc = eig_inplace(device, C_dev, N, lambda_dev, st);
+    if (rc) return rc;
+    PODSDF_TRY(launch_rows_gather_descending(C_dev, N, nm, Z, st));
+  }
+  PODSDF_CUDA(cudaMemcpyAsync(C_dev, Z, sizeof(double) * zn, cudaMemcpyDeviceToDevice, st));
+  PODSDF_CUDA(cudaStreamSynchronize(st));
+  return 0;
 }
 
 }  // namespace
@@ -183,6 +286,35 @@ int podsdf_eig_sym_dev(int device, double* C_dev_inout_V, long N, double* lambda
   PODSDF_TRY(check_device(device));
   DeviceGuard guard(device);
   return eig_inplace(device, C_dev_inout_V, N, lambda_dev, (cudaStream_t)stream);
+}
+
+int podsdf_eig_sym_top_dev(int device, double* C_dev_inout_V, long N, int nm, double* lambda_dev, int* path,
+                           void* stream) {
+  if (!C_dev_inout_V || !lambda_dev || N < 1) return fail(PODSDF_ERR_INVALID, "bad argument");
+  PODSDF_TRY(check_device(device));
+  DeviceGuard guard(device);
+  int route = 0;
+  const int rc = eig_top_inplace(device, C_dev_inout_V, N, nm, lambda_dev, (cudaStream_t)stream, &route);
+  if (path) *path = route;
+  return rc;
+}
+
+int podsdf_eig_sym_top_host(int device, const double* C_host, long N, int nm, double* lambda_host, double* V_host,
+                            int* path) {
+  if (!C_host || !lambda_host || !V_host || N < 1 || nm < 1 || nm > N) return fail(PODSDF_ERR_INVALID, "bad argument");
+  PODSDF_TRY(check_device(device));
+  DeviceGuard guard(device);
+  DevBuf C, lam;
+  const size_t nn = sizeof(double) * (size_t)N * N;
+  PODSDF_CUDA(C.alloc(nn));
+  PODSDF_CUDA(lam.alloc(sizeof(double) * N));
+  PODSDF_CUDA(cudaMemcpy(C.p, C_host, nn, cudaMemcpyHostToDevice));
+  int route = 0;
+  PODSDF_TRY(eig_top_inplace(device, C.p, N, nm, lam.p, 0, &route));
+  if (path) *path = route;
+  PODSDF_CUDA(cudaMemcpy(lambda_host, lam.p, sizeof(double) * N, cudaMemcpyDeviceToHost));
+  PODSDF_CUDA(cudaMemcpy(V_host, C.p, sizeof(double) * (size_t)nm * N, cudaMemcpyDeviceToHost));
+  return 0;
 }
 
 int podsdf_eig_sym_host(int device, const double* C_host, long N, double* lambda_host, double* V_host) {

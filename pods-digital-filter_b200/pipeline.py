@@ -136,10 +136,20 @@ def pod_resident(A, M, N, layout, nm, dt, et, device_index=0, group=None, timers
     allreduce_gram(C, group)
     marks[2].record()
     lam = torch.empty(N, dtype=torch.float64, device=dev)
-    _capi.check(L.podsdf_eig_sym_dev(device_index, C.data_ptr(), N, lam.data_ptr(), st))   # rows of C = vectors
+    # all eigenvalues + the leading vectors only (rows 0.. of C, descending): PODFS never reads the other N - nm
+    # eigenvectors (POD:1329-1333); nm < 0 ("keep every valid mode") needs them all
+    n_vec = N if nm < 0 else min(int(nm), N)
+    if n_vec < N:
+        import ctypes
+        route = ctypes.c_int(0)
+        _capi.check(L.podsdf_eig_sym_top_dev(device_index, C.data_ptr(), N, n_vec, lam.data_ptr(), ctypes.byref(route), st))
+        vec = lambda j: C[N - 1 - j].cpu().numpy()       # ascending index j -> row of the descending list
+    else:
+        _capi.check(L.podsdf_eig_sym_dev(device_index, C.data_ptr(), N, lam.data_ptr(), st))   # rows of C = vectors
+        vec = lambda j: C[j].cpu().numpy()
     marks[3].record()
     lam_h = lam.cpu().numpy()
-    energy, nm, T = select_modes(lam_h, lambda j: C[j].cpu().numpy(), N, nm)
+    energy, nm, T = select_modes(lam_h, vec, N, nm)
     T_d = torch.from_numpy(np.ascontiguousarray(T)).to(dev)
     dinv = torch.from_numpy(1.0 / energy[:nm]).to(dev)
     Phi = torch.empty((M, nm), dtype=torch.float64, device=dev)

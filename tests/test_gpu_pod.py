@@ -277,3 +277,40 @@ def test_welch_psd_matches_reference(P):
             assert Sxx.dtype == np.complex64 and np.abs(Sxx - ref).max() < 4e-7 * np.abs(ref).max()
     with pytest.raises(SystemExit):
         sp.fct_welch(g["in_x"][:10], 1.0, 11, 1)
+
+
+@pytest.mark.parametrize("N,nm,kind", [(600, 20, "separated"), (1000, 100, "separated"), (777, 33, "noise_floor"),
+                                       (512, 16, "clustered"), (300, 300, "separated"), (100, 5, "separated")])
+def test_leading_eigenpairs(P, N, nm, kind):
+    """`podsdf_eig_sym_top_*`: all eigenvalues + the nm leading eigenvectors.  Separated spectra take
+    the tridiagonal route (bisection + inverse iteration), clustered leading eigenvalues and small/odd sizes the full
+    solver; either way eigenvalues, residuals and orthonormality are at rounding level."""
+    rs = np.random.RandomState(N + nm)
+    Q, _ = np.linalg.qr(rs.standard_normal((N, N)))
+    if kind == "separated":
+        lam = np.arange(1, N + 1, dtype=np.float64) ** -1.6
+    elif kind == "noise_floor":                      # a few strong modes above a flat, dense floor (rank-deficient data)
+        lam = np.r_[np.arange(1, 61, dtype=np.float64) ** -1.2, 1e-9 * (1 + 1e-3 * rs.uniform(size=N - 60))]
+        lam[700:] = 0.0
+    else:                                            # two equal leading eigenvalues
+        lam = np.arange(1, N + 1, dtype=np.float64) ** -1.0
+        lam[3] = lam[2]
+    C = (Q * lam[None, :]) @ Q.T
+    C = 0.5 * (C + C.T)
+    w, V, path = P._capi.eig_sym_top(C, nm)
+    expect_fast = kind in ("separated", "noise_floor") and N >= 256 and 4 * nm <= N
+    assert path == (1 if expect_fast else 0), (path, kind)
+    ref = np.linalg.eigvalsh(C)
+    assert np.abs(w - ref).max() < 2e-14 * ref[-1] * 10
+    assert (np.diff(w) >= 0).all()
+    top = w[::-1][:nm]
+    assert np.abs(V @ C - top[:, None] * V).max() < 1e-13 * ref[-1]
+    assert np.abs(V @ V.T - np.eye(nm)).max() < 1e-13
+    # same invariant subspaces as the full solver (vectors up to sign where the eigenvalue is simple)
+    w2, V2 = P._capi.eig_sym(C)
+    full = V2[:, ::-1][:, :nm].T
+    if kind != "clustered":
+        gap = np.minimum(np.abs(np.diff(np.r_[top, w[::-1][nm] if nm < N else -np.inf])),
+                         np.abs(np.diff(np.r_[np.inf, top]))) / ref[-1]
+        dots = np.abs(np.sum(V * full, axis=1))
+        assert (1.0 - dots < 1e-12 / np.maximum(gap, 1e-12) ** 2 + 1e-13).all()
