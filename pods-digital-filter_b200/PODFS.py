@@ -189,9 +189,20 @@ def select_fourier(c128, energy_target):
     c = c128.astype(np.complex64)                                          # POD:1547
     c_count = np.zeros(num_modes, dtype=np.int64)
     c_ind = np.zeros((num_modes, num_fcs), dtype=np.int32)
+    cmT = np.ascontiguousarray(np.abs(c).T)                                # float32 magnitudes, one row per mode
+    last = num_fcs - 1
+    rev_index = (last - np.arange(num_fcs)).astype(np.uint64)
     for i in range(num_modes):
-        cmod = np.abs(c[:, i])                                             # float32 magnitudes
-        order = np.lexsort((-np.arange(num_fcs), -cmod))                   # POD:1584 tuple sort, reversed
+        cmod = cmT[i]
+        # POD:1584 tuple sort, reversed: magnitude descending, ties -> higher index first.  The IEEE bit pattern of
+        # a non-negative float32 is monotone in its value, so (~bits(|c|), N-1-index) packed in one uint64 is a
+        # unique key whose plain ascending sort IS that order (no stable sort, no index indirection).
+        if np.isnan(cmod).any():
+            order = np.lexsort((-np.arange(num_fcs), -cmod))
+        else:
+            key = ((np.uint64(0xFFFFFFFF) - cmod.view(np.uint32).astype(np.uint64)) << np.uint64(32)) | rev_index
+            key.sort()
+            order = (last - (key & np.uint64(0xFFFFFFFF)).astype(np.int64))
         c_ind[i, :] = order
         # POD:1588-1593 under the numpy-1.x casting the reference ran with: float64 running sum of the
         # float32 magnitudes against float64(float32 total) * et

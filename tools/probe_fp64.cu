@@ -57,6 +57,25 @@ int main() {
       double tf = per_thread * iters * 256.0 * grid / (best * 1e-3) / 1e12;
       printf(", \"%s_x%d_tflops\": %.2f", names[mode], blocks_per_sm, tf);
     }
+  // sustained: the same kernels back to back for ~1.5 s each (the board's power controller settles within ~0.1 s)
+  const char* snames[2] = {"dfma_sustained_tflops", "dmma_sustained_tflops"};
+  for (int mode = 0; mode < 2; ++mode) {
+    const int grid = p.multiProcessorCount * 4;
+    const double per_thread = mode == 0 ? 4.0 * ILP : 16.0 * ILP;
+    probe<ILP><<<grid, 256>>>(d, iters, mode, 1e-9);
+    cudaDeviceSynchronize();
+    int n = 0;
+    float ms = 0;
+    cudaEventRecord(e0);
+    do {
+      for (int r = 0; r < 20; ++r) probe<ILP><<<grid, 256>>>(d, iters, mode, 1e-9);
+      n += 20;
+      cudaEventRecord(e1);
+      cudaEventSynchronize(e1);
+      cudaEventElapsedTime(&ms, e0, e1);
+    } while (ms < 1500.f);
+    printf(", \"%s\": %.2f", snames[mode], per_thread * iters * 256.0 * grid * n / (ms * 1e-3) / 1e12);
+  }
   printf("}\n");
   return 0;
 }
