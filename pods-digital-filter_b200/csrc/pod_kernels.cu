@@ -284,12 +284,15 @@ project_dmma_kernel(const double* __restrict__ A, const long M, const long N, co
   constexpr int ATILE = ProjSmem<LAYOUT>::ATILE, TTILE = ProjSmem<LAYOUT>::TTILE;
   double* sA = smem;
   double* sT = smem + PST * ATILE;
-  const long row0 = (long)blockIdx.x * PR;
-  const int m0 = blockIdx.y * PM;
+  // mode blocks of the same rows are neighbours in the grid: the second one finds its A tiles in L2
+  const int nmb = (nm + PM - 1) / PM;
+  const long row0 = (long)(blockIdx.x / nmb) * PR;
+  const int m0 = (int)(blockIdx.x % nmb) * PM;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int lr = lane & 3, lc = lane >> 2;
   const int wr = warp * 16;
   const int nchunks = (int)((N + PKB - 1) / PKB);
+  const int ntl = min(8, (nm - m0 + 7) / 8);      // 8-mode column tiles that hold real modes (CTA-uniform)
 
   auto load_stage = [&](int chunk, int stage) {
     const long t0 = (long)chunk * PKB;
@@ -337,11 +340,13 @@ project_dmma_kernel(const double* __restrict__ A, const long M, const long N, co
       for (int mt = 0; mt < 2; ++mt)
         af[mt] = (LAYOUT == 0) ? a[(wr + mt * 8 + lc) * PPA0 + t] : a[t * PPA1 + wr + mt * 8 + lc];
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) bf[nt] = tt[t * PPT + nt * 8 + lc];
+      for (int nt = 0; nt < 8; ++nt)
+        if (nt < ntl) bf[nt] = tt[t * PPT + nt * 8 + lc];
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
+        for (int nt = 0; nt < 8; ++nt)
+          if (nt < ntl) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
     }
   }
   cp_async_wait<0>();
@@ -360,7 +365,9 @@ project_dmma_kernel(const double* __restrict__ A, const long M, const long N, co
 
 int launch_project(const double* A, long M, long N, int layout, const double* T, long ldT, const double* dinv,
                    int nm, double scale, double* Phi, cudaStream_t st) {
-  dim3 grid(ceil_div(M, PR), ceil_div(nm, PM));
+  const long nblocks = ceil_div(M, (long)PR) * ceil_div(nm, PM);
+  if (nblocks > 2147483647L) return fail(PODSDF_ERR_UNSUPPORTED, "too many tiles for one projection launch");
+  dim3 grid((unsigned)nblocks);
   if (layout == 0) {
     auto k = project_dmma_kernel<0>;
     PODSDF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ProjSmem<0>::BYTES));
