@@ -143,7 +143,8 @@ def pod_resident(A, M, N, layout, nm, dt, et, device_index=0, group=None, timers
         import ctypes
         route = ctypes.c_int(0)
         _capi.check(L.podsdf_eig_sym_top_dev(device_index, C.data_ptr(), N, n_vec, lam.data_ptr(), ctypes.byref(route), st))
-        vec = lambda j: C[N - 1 - j].cpu().numpy()       # ascending index j -> row of the descending list
+        lead = C[:n_vec].cpu().numpy()                   # one copy of the leading rows instead of one per mode
+        vec = lambda j: lead[N - 1 - j]                  # ascending index j -> row of the descending list
     else:
         _capi.check(L.podsdf_eig_sym_dev(device_index, C.data_ptr(), N, lam.data_ptr(), st))   # rows of C = vectors
         vec = lambda j: C[j].cpu().numpy()
