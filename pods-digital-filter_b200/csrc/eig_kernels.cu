@@ -68,11 +68,12 @@ __device__ __forceinline__ int sturm_count(const double* __restrict__ d, const d
   return cnt;
 }
 
+// eigenvalues k < k_end (ascending index), one thread each
 __global__ void __launch_bounds__(64)
 tridiag_bisect_kernel(const double* __restrict__ d, const double* __restrict__ e2, const double* __restrict__ bounds,
-                      const long N, double* __restrict__ lam) {
+                      const long N, const long k_end, double* __restrict__ lam) {
   const long k = blockIdx.x * 64L + threadIdx.x;
-  if (k >= N) return;
+  if (k >= k_end) return;
   double lo = bounds[0], hi = bounds[1];
   const double pivmin = bounds[2], tnorm = bounds[3];
   for (int it = 0; it < 200; ++it) {
@@ -84,6 +85,44 @@ tridiag_bisect_kernel(const double* __restrict__ d, const double* __restrict__ e
     else lo = mid;
   }
   lam[k] = 0.5 * (lo + hi);
+}
+
+// eigenvalues k_first <= k < N, one WARP each: every round the 32 lanes count at 32 interior points, so the
+// bracket shrinks 33x per Sturm sweep instead of 2x (11 sweeps instead of ~55 on the critical path of the
+// leading eigenvalues, which the inverse iteration waits for).  Same tolerances as the bisection.
+__global__ void __launch_bounds__(32)
+tridiag_multisect_kernel(const double* __restrict__ d, const double* __restrict__ e2, const double* __restrict__ bounds,
+                         const long N, const long k_first, double* __restrict__ lam) {
+  const long k = k_first + blockIdx.x;
+  if (k >= N) return;
+  const int lane = threadIdx.x;
+  double lo = bounds[0], hi = bounds[1];
+  const double pivmin = bounds[2], tnorm = bounds[3];
+  for (int it = 0; it < 64; ++it) {
+    const double tol = fmax(2.0 * DBL_EPSILON * fmax(fabs(lo), fabs(hi)), DBL_EPSILON * tnorm) + 2.0 * pivmin;
+    if (hi - lo <= tol) break;
+    const double w = (hi - lo) / 33.0;
+    const double x = lo + (double)(lane + 1) * w;
+    const bool inside = (x > lo) && (x < hi);            // false once the points collapse onto the ends
+    const int c = inside ? sturm_count(d, e2, N, x, pivmin) : (x >= hi ? (int)N : 0);
+    const unsigned above = __ballot_sync(0xffffffffu, c > k);      // points with more than k eigenvalues below them
+    const unsigned any_inside = __ballot_sync(0xffffffffu, inside);
+    if (any_inside == 0u) break;
+    double nlo = lo, nhi = hi;
+    if (above == 0u) {
+      nlo = __shfl_sync(0xffffffffu, x, 31);
+    } else {
+      const int j = __ffs(above) - 1;
+      nhi = __shfl_sync(0xffffffffu, x, j);
+      if (j > 0) nlo = __shfl_sync(0xffffffffu, x, j - 1);
+    }
+    nlo = fmin(fmax(nlo, lo), hi);
+    nhi = fmax(fmin(nhi, hi), nlo);
+    if (nlo == lo && nhi == hi) break;                    // no progress (bracket at rounding level)
+    lo = nlo;
+    hi = nhi;
+  }
+  if (lane == 0) lam[k] = 0.5 * (lo + hi);
 }
 
 // Inverse iteration for the nm largest eigenvalues.  Thread j owns vector j (eigenvalue lam[N-1-j]); its seven
@@ -238,11 +277,27 @@ int launch_rows_gather_descending(const double* C, long N, int nm, double* Z, cu
   return 0;
 }
 
-int launch_tridiag_eigenvalues(const double* d, const double* e, long N, double* e2, double* bounds, double* lam,
-                               cudaStream_t st) {
+int launch_tridiag_prepare(const double* d, const double* e, long N, double* e2, double* bounds, cudaStream_t st) {
   tridiag_prepare_kernel<<<1, 1024, 0, st>>>(d, e, N, e2, bounds);
-  tridiag_bisect_kernel<<<(unsigned)ceil_div(N, 64L), 64, 0, st>>>(d, e2, bounds, N, lam);
-  count_launch(2);
+  count_launch();
+  PODSDF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_tridiag_bisect(const double* d, const double* e2, const double* bounds, long N, long k_end, double* lam,
+                          cudaStream_t st) {
+  if (k_end <= 0) return 0;
+  tridiag_bisect_kernel<<<(unsigned)ceil_div(k_end, 64L), 64, 0, st>>>(d, e2, bounds, N, k_end, lam);
+  count_launch();
+  PODSDF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_tridiag_multisect(const double* d, const double* e2, const double* bounds, long N, long k_first, double* lam,
+                             cudaStream_t st) {
+  if (k_first >= N) return 0;
+  tridiag_multisect_kernel<<<(unsigned)(N - k_first), 32, 0, st>>>(d, e2, bounds, N, k_first, lam);
+  count_launch();
   PODSDF_CUDA(cudaGetLastError());
   return 0;
 }

@@ -4,10 +4,14 @@
 
 namespace podsdf {
 
-// all N eigenvalues (ascending) of the tridiagonal matrix (d[N], e[N-1]) by bisection.
-// e2: N doubles of scratch; bounds: 4 doubles (out: Gershgorin interval, pivmin, |T|)
-int launch_tridiag_eigenvalues(const double* d, const double* e, long N, double* e2, double* bounds, double* lam,
-                               cudaStream_t st);
+// Eigenvalues (ascending) of the tridiagonal matrix (d[N], e[N-1]).  prepare: e2 = e^2 (N doubles of scratch) and
+// bounds[4] = Gershgorin interval, pivmin, |T|.  bisect: indices [0, k_end), one thread each.  multisect: indices
+// [k_first, N), one warp each (33-section: a fifth of the serial Sturm sweeps).
+int launch_tridiag_prepare(const double* d, const double* e, long N, double* e2, double* bounds, cudaStream_t st);
+int launch_tridiag_bisect(const double* d, const double* e2, const double* bounds, long N, long k_end, double* lam,
+                          cudaStream_t st);
+int launch_tridiag_multisect(const double* d, const double* e2, const double* bounds, long N, long k_first, double* lam,
+                             cudaStream_t st);
 size_t tridiag_invit_workspace_doubles(long N, int nm);
 // unit eigenvectors of T for the nm largest eigenvalues: Z[j][:] <-> lam[N-1-j]; resid[j] = scaled residual
 int launch_tridiag_invit(const double* d, const double* e, const double* bounds, const double* lam, long N, int nm,

@@ -131,6 +131,23 @@ int eig_inplace(int device, double* C_dev, long N, double* lambda_dev, cudaStrea
   return rc;
 }
 
+// second stream + fork/join events per device for the part of the tridiagonal route that is off the critical path
+struct SideStream {
+  cudaStream_t s = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  bool ok = false;
+};
+SideStream& side_stream(int device) {
+  static SideStream ss[64];
+  SideStream& x = ss[device & 63];
+  if (!x.ok) {
+    x.ok = cudaStreamCreateWithFlags(&x.s, cudaStreamNonBlocking) == cudaSuccess &&
+           cudaEventCreateWithFlags(&x.fork, cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&x.join, cudaEventDisableTiming) == cudaSuccess;
+  }
+  return x;
+}
+
 // All eigenvalues (ascending, lambda_dev) and the eigenvectors of the nm largest: on exit rows 0..nm-1 of C are
 // those eigenvectors in DESCENDING order of the eigenvalue (the other rows are scratch).
 // Route 1: Dsytrd -> bisection for all eigenvalues -> inverse iteration for nm vectors of T -> Dormtr -> Cholesky-QR
@@ -164,7 +181,7 @@ int eig_top_inplace(int device, double* C_dev, long N, int nm, double* lambda_de
   double* winv = S + (size_t)nm * nm + 2;
   *path = 0;
   int rc = 0;
-  bool fast_ok = false;
+  bool fast_ok = false, side_pending = false;
   if (eligible) {
     PODSDF_CUDA(cudaMemcpyAsync(Ccopy, C_dev, sizeof(double) * nn, cudaMemcpyDeviceToDevice, st));
     cusolverDnHandle_t& h = g_handles[device & 63];
@@ -181,10 +198,20 @@ int eig_top_inplace(int device, double* C_dev, long N, int nm, double* lambda_de
     DevBuf info;
     if (info.alloc(8) != cudaSuccess) return fail(PODSDF_ERR_CUDA, "eigen-solver workspace allocation failed");
     if (cs.sytrd(h, 0, n, C_dev, n, d, e, tau, work, lwork, (int*)info.p) != 0) return fail(PODSDF_ERR_CUDA, "Dsytrd failed");
-    PODSDF_TRY(launch_tridiag_eigenvalues(d, e, N, e2, bounds, lambda_dev, st));
+    // leading nm+1 eigenvalues first (warp-wide multisection, on the caller's stream: the inverse iteration waits
+    // for them); the other N-nm-1 by plain bisection on a side stream, concurrently with everything below
+    const long first = N - 1 - nm;      // ascending index of the (nm+1)-th largest (>= 0 because 4 nm <= N)
+    PODSDF_TRY(launch_tridiag_prepare(d, e, N, e2, bounds, st));
+    SideStream& side = side_stream(device);
+    if (!side.ok) return fail(PODSDF_ERR_CUDA, "side stream creation failed");
+    PODSDF_CUDA(cudaEventRecord(side.fork, st));
+    PODSDF_CUDA(cudaStreamWaitEvent(side.s, side.fork, 0));
+    PODSDF_TRY(launch_tridiag_bisect(d, e2, bounds, N, first, lambda_dev, side.s));
+    PODSDF_CUDA(cudaEventRecord(side.join, side.s));
+    side_pending = true;
+    PODSDF_TRY(launch_tridiag_multisect(d, e2, bounds, N, first, lambda_dev, st));
     // the leading nm+1 eigenvalues decide whether independent inverse iterations are safe
     std::vector<double> top((size_t)nm + 1);
-    const long first = N - 1 - nm;      // ascending index of the (nm+1)-th largest (>= 0 because 4 nm <= N)
     PODSDF_CUDA(cudaMemcpyAsync(top.data(), lambda_dev + first, sizeof(double) * (nm + 1), cudaMemcpyDeviceToHost, st));
     PODSDF_CUDA(cudaStreamSynchronize(st));
     const double lmax = std::fabs(top[nm]);
@@ -205,6 +232,7 @@ int eig_top_inplace(int device, double* C_dev, long N, int nm, double* lambda_de
       for (int j = 0; j < nm && fast_ok; ++j)
         if (!(hres[j] < 1.0e-12)) fast_ok = false;
     }
+    if (side_pending) PODSDF_CUDA(cudaStreamWaitEvent(st, side_stream(device).join, 0));   // all of lambda is written
     if (!fast_ok) PODSDF_CUDA(cudaMemcpyAsync(C_dev, Ccopy, sizeof(double) * nn, cudaMemcpyDeviceToDevice, st));
   }
   if (fast_ok) {
