@@ -68,61 +68,50 @@ __device__ __forceinline__ int sturm_count(const double* __restrict__ d, const d
   return cnt;
 }
 
-// eigenvalues k < k_end (ascending index), one thread each
+// Eigenvalues k_first <= k < k_end (ascending index), G lanes each: every sweep over the matrix the G lanes count at
+// the G interior points of a (G+1)-section of the bracket, so it shrinks (G+1)x per serial Sturm sweep instead of 2x.
+// G = 32 (a warp, 11 sweeps) serves the few leading eigenvalues the inverse iteration waits for; G = 4 (23 sweeps
+// instead of ~55, four times the threads) serves all the others -- more lanes per eigenvalue there would saturate
+// the SMs with divisions (measured).  Tolerances are dstebz's defaults: relative 2 ulp, absolute ulp * |T|.
+template <int G>
 __global__ void __launch_bounds__(64)
-tridiag_bisect_kernel(const double* __restrict__ d, const double* __restrict__ e2, const double* __restrict__ bounds,
-                      const long N, const long k_end, double* __restrict__ lam) {
-  const long k = blockIdx.x * 64L + threadIdx.x;
-  if (k >= k_end) return;
-  double lo = bounds[0], hi = bounds[1];
-  const double pivmin = bounds[2], tnorm = bounds[3];
-  for (int it = 0; it < 200; ++it) {
-    const double mid = 0.5 * (lo + hi);
-    // dstebz's default: relative 2 ulp, absolute ulp * |T| (eigenvalues far below |T| get absolute accuracy only)
-    const double tol = fmax(2.0 * DBL_EPSILON * fmax(fabs(lo), fabs(hi)), DBL_EPSILON * tnorm) + 2.0 * pivmin;
-    if (hi - lo <= tol || mid <= lo || mid >= hi) break;
-    if (sturm_count(d, e2, N, mid, pivmin) > k) hi = mid;
-    else lo = mid;
-  }
-  lam[k] = 0.5 * (lo + hi);
-}
-
-// eigenvalues k_first <= k < N, one WARP each: every round the 32 lanes count at 32 interior points, so the
-// bracket shrinks 33x per Sturm sweep instead of 2x (11 sweeps instead of ~55 on the critical path of the
-// leading eigenvalues, which the inverse iteration waits for).  Same tolerances as the bisection.
-__global__ void __launch_bounds__(32)
-tridiag_multisect_kernel(const double* __restrict__ d, const double* __restrict__ e2, const double* __restrict__ bounds,
-                         const long N, const long k_first, double* __restrict__ lam) {
-  const long k = k_first + blockIdx.x;
-  if (k >= N) return;
-  const int lane = threadIdx.x;
+tridiag_sect_kernel(const double* __restrict__ d, const double* __restrict__ e2, const double* __restrict__ bounds,
+                    const long N, const long k_first, const long k_end, double* __restrict__ lam) {
+  const long gid = (blockIdx.x * 64L + threadIdx.x) / G;          // eigenvalue handled by this group of lanes
+  const long k = k_first + gid;
+  const int lane = threadIdx.x & 31;
+  const int gl = lane % G;                                         // position inside the group
+  const int base = lane - gl;
+  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << base);
+  if (k >= k_end) return;                                          // whole groups leave together
   double lo = bounds[0], hi = bounds[1];
   const double pivmin = bounds[2], tnorm = bounds[3];
   for (int it = 0; it < 64; ++it) {
     const double tol = fmax(2.0 * DBL_EPSILON * fmax(fabs(lo), fabs(hi)), DBL_EPSILON * tnorm) + 2.0 * pivmin;
     if (hi - lo <= tol) break;
-    const double w = (hi - lo) / 33.0;
-    const double x = lo + (double)(lane + 1) * w;
-    const bool inside = (x > lo) && (x < hi);            // false once the points collapse onto the ends
+    const double w = (hi - lo) / (double)(G + 1);
+    const double x = lo + (double)(gl + 1) * w;
+    const bool inside = (x > lo) && (x < hi);                      // false once the points collapse onto the ends
     const int c = inside ? sturm_count(d, e2, N, x, pivmin) : (x >= hi ? (int)N : 0);
-    const unsigned above = __ballot_sync(0xffffffffu, c > k);      // points with more than k eigenvalues below them
-    const unsigned any_inside = __ballot_sync(0xffffffffu, inside);
+    const unsigned above = (__ballot_sync(gmask, c > k) >> base) & ((G == 32) ? 0xffffffffu : ((1u << G) - 1u));
+    const unsigned any_inside = __ballot_sync(gmask, inside) & gmask;
     if (any_inside == 0u) break;
     double nlo = lo, nhi = hi;
     if (above == 0u) {
-      nlo = __shfl_sync(0xffffffffu, x, 31);
+      nlo = __shfl_sync(gmask, x, base + G - 1);
     } else {
       const int j = __ffs(above) - 1;
-      nhi = __shfl_sync(0xffffffffu, x, j);
-      if (j > 0) nlo = __shfl_sync(0xffffffffu, x, j - 1);
+      nhi = __shfl_sync(gmask, x, base + j);
+      const double below = __shfl_sync(gmask, x, base + (j > 0 ? j - 1 : 0));
+      if (j > 0) nlo = below;
     }
     nlo = fmin(fmax(nlo, lo), hi);
     nhi = fmax(fmin(nhi, hi), nlo);
-    if (nlo == lo && nhi == hi) break;                    // no progress (bracket at rounding level)
+    if (nlo == lo && nhi == hi) break;                             // no progress: the bracket is at rounding level
     lo = nlo;
     hi = nhi;
   }
-  if (lane == 0) lam[k] = 0.5 * (lo + hi);
+  if (gl == 0) lam[k] = 0.5 * (lo + hi);
 }
 
 // Inverse iteration for the nm largest eigenvalues.  Thread j owns vector j (eigenvalue lam[N-1-j]); its seven
@@ -142,24 +131,39 @@ tridiag_invit_kernel(const double* __restrict__ d, const double* __restrict__ e,
   const double l = lam[N - 1 - j];
   const long st = nm;                                    // stride between consecutive i of one plane
   wP += j; wQ += j; wR += j; wM += j; wS += j; wX += j; wY += j;
+  // Every sweep below is a serial recurrence over i whose operands do not depend on the recurrence: they are
+  // fetched U steps at a time into registers first, so one memory latency is paid per U steps instead of per step.
+  constexpr int U = 8;
   // ---- LU of (T - l I) with partial pivoting: row i of U = (P[i], Q[i], R[i]), multiplier M[i], swap flag S[i]
   double p = __ldg(d) - l, q = (N > 1) ? __ldg(e) : 0.0;
-#pragma unroll 4
-  for (long i = 0; i + 1 < N; ++i) {
-    const double c = __ldg(e + i);                       // sub-diagonal entry of row i+1
-    const double a1 = __ldg(d + i + 1) - l;
-    const double b1 = (i + 2 < N) ? __ldg(e + i + 1) : 0.0;
-    if (fabs(p) >= fabs(c)) {
-      if (fabs(p) < floor_p) p = copysign(floor_p, p);
-      const double m = c / p;
-      wP[i * st] = p; wQ[i * st] = q; wR[i * st] = 0.0; wM[i * st] = m; wS[i * st] = 0.0;
-      p = a1 - m * q;
-      q = b1;
-    } else {
-      const double m = p / c;
-      wP[i * st] = c; wQ[i * st] = a1; wR[i * st] = b1; wM[i * st] = m; wS[i * st] = 1.0;
-      p = q - m * a1;
-      q = -m * b1;
+  for (long i0 = 0; i0 + 1 < N; i0 += U) {
+    double cc[U], aa[U], bb[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long i = i0 + u;
+      const bool ok = i + 1 < N;
+      cc[u] = ok ? __ldg(e + i) : 0.0;                   // sub-diagonal entry of row i+1
+      aa[u] = ok ? __ldg(d + i + 1) - l : 0.0;
+      bb[u] = (i + 2 < N) ? __ldg(e + i + 1) : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long i = i0 + u;
+      if (i + 1 < N) {
+        const double c = cc[u], a1 = aa[u], b1 = bb[u];
+        if (fabs(p) >= fabs(c)) {
+          if (fabs(p) < floor_p) p = copysign(floor_p, p);
+          const double m = c / p;
+          wP[i * st] = p; wQ[i * st] = q; wR[i * st] = 0.0; wM[i * st] = m; wS[i * st] = 0.0;
+          p = a1 - m * q;
+          q = b1;
+        } else {
+          const double m = p / c;
+          wP[i * st] = c; wQ[i * st] = a1; wR[i * st] = b1; wM[i * st] = m; wS[i * st] = 1.0;
+          p = q - m * a1;
+          q = -m * b1;
+        }
+      }
     }
   }
   if (fabs(p) < floor_p) p = copysign(floor_p, p);
@@ -173,24 +177,53 @@ tridiag_invit_kernel(const double* __restrict__ d, const double* __restrict__ e,
   for (int iter = 0; iter < 3; ++iter) {
     // forward sweep X -> Y: apply the row operations to the right-hand side (y carried in a register)
     double y = wX[0];
-#pragma unroll 8
-    for (long i = 0; i + 1 < N; ++i) {
-      double y1 = wX[(i + 1) * st];
-      if (wS[i * st] != 0.0) { const double t = y; y = y1; y1 = t; }
-      y1 -= wM[i * st] * y;
-      wY[i * st] = y;
-      y = y1;
+    for (long i0 = 0; i0 + 1 < N; i0 += U) {
+      double xs[U], ss[U], ms[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long i = i0 + u;
+        const bool ok = i + 1 < N;
+        xs[u] = ok ? wX[(i + 1) * st] : 0.0;
+        ss[u] = ok ? wS[i * st] : 0.0;
+        ms[u] = ok ? wM[i * st] : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long i = i0 + u;
+        if (i + 1 < N) {
+          double y1 = xs[u];
+          if (ss[u] != 0.0) { const double t = y; y = y1; y1 = t; }
+          y1 -= ms[u] * y;
+          wY[i * st] = y;
+          y = y1;
+        }
+      }
     }
     wY[(N - 1) * st] = y;
     // back substitution Y -> X with two super-diagonals
     double x1 = 0.0, x2 = 0.0, big = 0.0;
-#pragma unroll 8
-    for (long i = N - 1; i >= 0; --i) {
-      const double x0 = (wY[i * st] - wQ[i * st] * x1 - wR[i * st] * x2) / wP[i * st];
-      wX[i * st] = x0;
-      big = fmax(big, fabs(x0));
-      x2 = x1;
-      x1 = x0;
+    for (long i0 = N - 1; i0 >= 0; i0 -= U) {
+      double ys[U], qs[U], rs[U], ps[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long i = i0 - u;
+        const bool ok = i >= 0;
+        ys[u] = ok ? wY[i * st] : 0.0;
+        qs[u] = ok ? wQ[i * st] : 0.0;
+        rs[u] = ok ? wR[i * st] : 0.0;
+        ps[u] = ok ? wP[i * st] : 1.0;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long i = i0 - u;
+        if (i >= 0) {
+          const double x0 = (ys[u] - qs[u] * x1 - rs[u] * x2) / ps[u];
+          wX[i * st] = x0;
+          big = fmax(big, fabs(x0));
+          x2 = x1;
+          x1 = x0;
+        }
+      }
     }
     const double s = 1.0 / fmax(big, DBL_MIN);
     for (long i = 0; i < N; ++i) wX[i * st] *= s;
@@ -287,7 +320,8 @@ int launch_tridiag_prepare(const double* d, const double* e, long N, double* e2,
 int launch_tridiag_bisect(const double* d, const double* e2, const double* bounds, long N, long k_end, double* lam,
                           cudaStream_t st) {
   if (k_end <= 0) return 0;
-  tridiag_bisect_kernel<<<(unsigned)ceil_div(k_end, 64L), 64, 0, st>>>(d, e2, bounds, N, k_end, lam);
+  constexpr int G = 4;
+  tridiag_sect_kernel<G><<<(unsigned)ceil_div(k_end * G, 64L), 64, 0, st>>>(d, e2, bounds, N, 0, k_end, lam);
   count_launch();
   PODSDF_CUDA(cudaGetLastError());
   return 0;
@@ -296,7 +330,7 @@ int launch_tridiag_bisect(const double* d, const double* e2, const double* bound
 int launch_tridiag_multisect(const double* d, const double* e2, const double* bounds, long N, long k_first, double* lam,
                              cudaStream_t st) {
   if (k_first >= N) return 0;
-  tridiag_multisect_kernel<<<(unsigned)(N - k_first), 32, 0, st>>>(d, e2, bounds, N, k_first, lam);
+  tridiag_sect_kernel<32><<<(unsigned)ceil_div((N - k_first) * 32, 64L), 64, 0, st>>>(d, e2, bounds, N, k_first, N, lam);
   count_launch();
   PODSDF_CUDA(cudaGetLastError());
   return 0;

@@ -5,8 +5,8 @@
 namespace podsdf {
 
 // Eigenvalues (ascending) of the tridiagonal matrix (d[N], e[N-1]).  prepare: e2 = e^2 (N doubles of scratch) and
-// bounds[4] = Gershgorin interval, pivmin, |T|.  bisect: indices [0, k_end), one thread each.  multisect: indices
-// [k_first, N), one warp each (33-section: a fifth of the serial Sturm sweeps).
+// bounds[4] = Gershgorin interval, pivmin, |T|.  bisect: indices [0, k_end), four lanes each (5-section).  multisect:
+// indices [k_first, N), one warp each (33-section: a fifth of the serial Sturm sweeps of a plain bisection).
 int launch_tridiag_prepare(const double* d, const double* e, long N, double* e2, double* bounds, cudaStream_t st);
 int launch_tridiag_bisect(const double* d, const double* e2, const double* bounds, long N, long k_end, double* lam,
                           cudaStream_t st);
