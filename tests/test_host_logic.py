@@ -171,3 +171,23 @@ def test_bench_reference_arm_contract():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "planes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"]
+
+
+def test_fourier_ranking_matches_the_tuple_sort():
+    """`PODFS.select_fourier` ranks with one uint64 key sort per mode; the reference sorts (|c|, index) tuples in
+    reverse (POD:1584).  Same order, counts and complex64 storage, including ties, zeros and signed zeros."""
+    pod = pkg().PODFS
+    rs = np.random.RandomState(17)
+    for ns, nm, et in ((64, 5, 0.9), (257, 3, 0.5), (40, 4, 0.75), (31, 2, 0.999)):   # (et = 1 can overrun the reference's loop)
+        c = rs.standard_normal((ns, nm)) + 1j * rs.standard_normal((ns, nm))
+        c[3:9, 0] = c[2, 0]                       # a run of equal magnitudes
+        c[10:14, nm - 1] = 0.0                    # exact zeros
+        c[20, 0] = complex(-0.0, 0.0)
+        c[5, 1] = np.conj(c[6, 1])                # equal magnitude, different value
+        got = pod.select_fourier(c, et)
+        ref = podo.select_coefficients(c, et, nep50=False)
+        for g, r in zip(got, ref):
+            assert np.array_equal(g, r)
+    c = rs.standard_normal((50, 2)) + 0j
+    c[7, 1] = np.nan                              # NaN column: falls back to the two-key sort, must not raise
+    pod.select_fourier(c, 0.9)
