@@ -122,7 +122,10 @@ def POD(A, num_snapshots, num_points, num_components, correct_for_cell_volumes, 
         write_temporal_modes(num_valid_modes, ns, dt, temporal_modes, restart_dir)
         # POD:1366-1388: Welch PSD of the written temporal modes.  The reference plots them (POD_PSD_mode_j.png,
         # matplotlib); here the same numbers go to a two-column text file next to the temporal modes.
-        from . import nsigproclib_no_mpi as sp
+        try:
+            from . import nsigproclib_no_mpi as sp
+        except ImportError:                      # flat import: `python pods-digital-filter_b200/digitalfilters.py -v`
+            import nsigproclib_no_mpi as sp
         nw = num_modes_to_write
         if nw < 0 or nw > num_modes_trunc:
             nw = num_modes_trunc

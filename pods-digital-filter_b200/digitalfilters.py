@@ -435,6 +435,10 @@ def main(argv=None):
         nfx = int(math.ceil(float(options.fwidth) * lnx))
         print("Lengthscale in x-direction set to: ", lnx, "grid points")
         print("Filter width in x-direction set to: ", nfx, "grid points")
+    if max(nfx, nfy, nfz) > 64:
+        # the device kernels carry at most 129 taps per axis (include/podsdf.h); fail before any work starts
+        raise Exception("half filter width %d exceeds the supported maximum of 64 grid points "
+                        "(reduce -l/-f, or choose --dt closer to res/mean(U))" % max(nfx, nfy, nfz))
     if not from_prf:                                                     # DF:1345-1352
         for v in (uu, vv, ww):
             v[v < 0.0] = 0.0

@@ -8,7 +8,10 @@ import sys
 
 import numpy as np
 
-from . import _capi
+try:
+    from . import _capi
+except ImportError:                              # flat import (script mode), like the other shims
+    import _capi
 
 
 def _window(N, iwindow):

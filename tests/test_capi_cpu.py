@@ -69,3 +69,54 @@ def test_product_does_not_import_the_oracle():
         if fn.endswith(".py"):
             src = open(os.path.join(pdir, fn)).read()
             assert "oracle" not in src.replace("# oracle", ""), fn
+
+
+def test_flat_import_verbose_pod_with_stubbed_capi(tmp_path):
+    """Script mode (`python pods-digital-filter_b200/digitalfilters.py -v`): the shims are imported flat, with the
+    package directory on sys.path.  POD(verbose) reaches nsigproclib_no_mpi -> _capi through the same try/except
+    as the module tops.  _capi is stubbed with numpy so the test runs without a GPU."""
+    import subprocess
+    import sys
+    import textwrap
+    code = textwrap.dedent("""
+        import sys, types, os
+        import numpy as np
+        sys.path.insert(0, %r)
+        stub = types.ModuleType("_capi")
+        stub.LAYOUT_ROWS_BY_TIME, stub.LAYOUT_TIME_BY_ROWS = 0, 1
+        def gram(a, layout, w, scale, out, device=0):
+            A = a if layout == 0 else a.T
+            C = scale * A.T.dot(A)
+            if out is not None:
+                out[:, :] = C
+            return C
+        def eig_sym(C, device=0):
+            return np.linalg.eigh(C)
+        def project(a, T, dinv, nm, scale, layout, device=0):
+            A = a if layout == 0 else a.T
+            return scale * A.dot(T[:, :nm]) * dinv[None, :]
+        def dft_modes(a, nm, device=0):
+            N = a.shape[0]
+            return np.fft.fftshift(np.fft.fft(a[:, :nm], axis=0), axes=0) / N
+        stub.gram, stub.eig_sym, stub.project, stub.dft_modes = gram, eig_sym, project, dft_modes
+        sys.modules["_capi"] = stub
+        import PODFS as pod
+        import nsigproclib_no_mpi as sp
+        assert pod._capi is stub and sp._capi is stub
+        class Bag(object):
+            pass
+        i_d = Bag()
+        i_d.verbose = True
+        rng = np.random.RandomState(3)
+        ns, P = 16, 10
+        A = rng.standard_normal((3 * P, ns))
+        A -= A.mean(axis=1)[:, None]
+        os.makedirs("PODFS", exist_ok=True)
+        pod.POD(A, ns, P, 3, "false", [], "PODFS/", "false", 1.0e-15, 4, 4, "false", "false", None, None, 0.1,
+                "velocity", 1, ns, 1, 1, i_d)
+        assert i_d.PSD.shape == (ns, 4) and np.isfinite(i_d.PSD).all()
+        assert os.path.exists("PODFS/POD_PSD_mode_3.dat") and os.path.exists("PODFS/POD.temporal_mode_0001.dat")
+        print("flat-ok")
+    """) % os.path.join(ROOT, "pods-digital-filter_b200")
+    r = subprocess.run([sys.executable, "-c", code], cwd=str(tmp_path), capture_output=True, text=True)
+    assert r.returncode == 0 and "flat-ok" in r.stdout, r.stdout + r.stderr
