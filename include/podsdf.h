@@ -50,6 +50,12 @@ extern "C" {
 #define PODSDF_IMPL_GENERIC 1
 #define PODSDF_IMPL_TUNED 2
 
+/* random streams of the seeded DF entries (csrc/philox.cuh; oracle/philox.py restates both):
+ * U32 (default): Philox4x32-10, one call = 2 points x 2 slabs, 32 random bits per number, centred levels;
+ * U53: round 1's stream, one call = 2 points of one slab, numpy's 53-bit uniform(). */
+#define PODSDF_RNG_U53 0
+#define PODSDF_RNG_U32 1
+
 PODSDF_API const char* podsdf_last_error(void);
 PODSDF_API int podsdf_version(void);
 /* number of usable sm_100 devices (0 and PODSDF_ERR_NO_DEVICE if none) */
@@ -75,6 +81,10 @@ PODSDF_API int podsdf_df_plan_set_impl(podsdf_df_plan* plan, int impl);
  * Results do not depend on it bitwise. */
 PODSDF_API int podsdf_df_plan_set_chunk(podsdf_df_plan* plan, int chunk_planes);
 
+/* which Philox stream the *_seeded_* and random_slabs entries use (PODSDF_RNG_*; default U32).  The reference
+ * draws from the unseeded global MT19937 (DF:1344, 1361-1366), so there is no reference stream to match. */
+PODSDF_API int podsdf_df_plan_set_rng(podsdf_df_plan* plan, int kind);
+
 /* ref: adapt1d DF:143-178, adapt2prf DF:180-231, adapt2d DF:233-485, rotate_velocity DF:1119-1131.
  * All four are y = M(j,k) x + m(j,k) with time-invariant M (3x3) and m (3): the shim evaluates
  * the Cholesky / clamps / splines / rotation once on the host and hands over
@@ -97,7 +107,8 @@ PODSDF_API int podsdf_df_generate_injected_host(podsdf_df_plan* plan, const doub
                                      double* out_host);
 PODSDF_API int podsdf_df_generate_injected_dev(podsdf_df_plan* plan, const double* slabs_dev, long n_slabs,
                                     double* out_dev, void* stream);
-/* same loop with the random stream generated on the device (Philox4x32-10, see csrc/philox.cuh):
+/* same loop with the random stream generated on the device (Philox4x32-10, see csrc/philox.cuh and
+ * podsdf_df_plan_set_rng):
  * planes t0 .. t0+nsteps-1 of the infinite stream `seed` (any shard reproduces its own window). */
 PODSDF_API int podsdf_df_generate_seeded_host(podsdf_df_plan* plan, uint64_t seed, long t0, long nsteps,
                                    double* out_host);

@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(HERE, "libpodsdf.so")
 OK, ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_UNSUPPORTED, ERR_NUMERIC = range(6)
 LAYOUT_ROWS_BY_TIME, LAYOUT_TIME_BY_ROWS = 0, 1
 IMPL_AUTO, IMPL_GENERIC, IMPL_TUNED = 0, 1, 2
+RNG_U53, RNG_U32 = 0, 1
 
 
 class PodsdfError(RuntimeError):
@@ -38,6 +39,7 @@ SIGNATURES = {
     "podsdf_df_plan_destroy": [_vp],
     "podsdf_df_plan_set_impl": [_vp, _i],
     "podsdf_df_plan_set_chunk": [_vp, _i],
+    "podsdf_df_plan_set_rng": [_vp, _i],
     "podsdf_df_plan_info": [_vp, ctypes.POINTER(_i)],
     "podsdf_df_set_coefficients": [_vp, _vp, ctypes.c_uint],
     "podsdf_df_set_rotation": [_vp, _vp],
@@ -182,6 +184,10 @@ class DfPlan(object):
 
     def set_chunk(self, n):
         check(lib().podsdf_df_plan_set_chunk(self._h, int(n)))
+
+    def set_rng(self, kind):
+        """Philox stream of the seeded entries: RNG_U32 (default, 4 numbers per call) or RNG_U53 (round-1 stream)."""
+        check(lib().podsdf_df_plan_set_rng(self._h, int(kind)))
 
     def set_coefficients(self, coef, mask):
         """coef (12, J*K) planes M00..M22, m0..m2 (or None for identity); mask: present planes."""

@@ -8,6 +8,7 @@
 
 #include "../../include/podsdf.h"
 #include "df_kernels.cuh"
+#include "philox.cuh"
 
 namespace podsdf {
 
@@ -54,6 +55,7 @@ struct podsdf_df_plan {
   Taps bx{}, by{}, bz{};
   int impl = PODSDF_IMPL_AUTO;
   int chunk = 512;         // replaced at plan creation by default_chunk()
+  int rng = PODSDF_RNG_U32;  // stream of the seeded entries (podsdf_df_plan_set_rng)
   // device state
   double* d_coef = nullptr;  // [12][P]
   unsigned mask = 0;
@@ -153,14 +155,15 @@ int run_chunk(podsdf_df_plan* p, const double* X_dev, bool gen, uint64_t seed, l
   const double* X = X_dev;
   if (gen && !tt) {  // generic time filter needs materialised slabs
     PODSDF_TRY(ensure_x_ws(p, nsteps));
-    PODSDF_TRY(launch_df_random_slabs(p->g, seed, s_base, nsteps + 2 * p->g.nfx, p->d_X, st));
+    PODSDF_TRY(launch_df_random_slabs(p->g, seed, p->rng, s_base, nsteps + 2 * p->g.nfx, p->d_X, st));
     X = p->d_X;
     gen = false;
   }
   cudaEvent_t e0 = next_event(p), e1 = next_event(p), e2 = next_event(p);
   PODSDF_CUDA(cudaEventRecord(e0, st));
   const PanelGeom pg = panel_of(p);
-  PODSDF_TRY(launch_df_time(p->g, pg, p->bx, X, p->d_T1, nsteps, gen, seed, s_base, tt, st));
+  const int src = !gen ? 0 : (p->rng == PODSDF_RNG_U32 ? 2 : 1);
+  PODSDF_TRY(launch_df_time(p->g, pg, p->bx, X, p->d_T1, nsteps, src, seed, s_base, tt, st));
   PODSDF_CUDA(cudaEventRecord(e1, st));
   PODSDF_TRY(launch_df_plane(p->g, pg, p->by, p->bz, p->d_T1, out_dev, nsteps, 3, p->d_coef, p->mask, p->have_coef,
                              p->rot, p->d_T2, tp, st));
@@ -173,7 +176,7 @@ int run_chunk(podsdf_df_plan* p, const double* X_dev, bool gen, uint64_t seed, l
 extern "C" {
 
 const char* podsdf_last_error(void) { return g_last_error.c_str(); }
-int podsdf_version(void) { return 100; }  // 0.1.0
+int podsdf_version(void) { return 200; }  // 0.2.0
 long long podsdf_launch_count(void) { return g_launches.load(); }
 
 int podsdf_device_count(int* count) {
@@ -275,6 +278,12 @@ int podsdf_df_plan_set_chunk(podsdf_df_plan* p, int chunk) {
   return 0;
 }
 
+int podsdf_df_plan_set_rng(podsdf_df_plan* p, int kind) {
+  if (!p || (kind != PODSDF_RNG_U53 && kind != PODSDF_RNG_U32)) return fail(PODSDF_ERR_INVALID, "bad plan / rng kind");
+  p->rng = kind;
+  return 0;
+}
+
 int podsdf_df_set_coefficients(podsdf_df_plan* p, const double* coef_host, unsigned mask) {
   if (!p) return fail(PODSDF_ERR_INVALID, "plan is null");
   DeviceGuard guard(p->device);
@@ -333,7 +342,7 @@ int podsdf_df_filter_block_host(podsdf_df_plan* p, const double* x_host, double*
   }
   const bool tt = use_tuned_time(p), tp = use_tuned_plane(p);
   const PanelGeom pg = panel_of(p);
-  rc = launch_df_time(g, pg, p->bx, dX, dT1, 1, false, 0, 0, tt, st);
+  rc = launch_df_time(g, pg, p->bx, dX, dT1, 1, 0, 0, 0, tt, st);
   if (!rc) rc = launch_df_plane(g, pg, p->by, p->bz, dT1, dY, 1, 3, nullptr, 0, false, Rot(), dT2, tp, st);
   if (!rc) {
     e = cudaMemcpyAsync(y_host, dY, sizeof(double) * g.P, cudaMemcpyDeviceToHost, st);
@@ -450,7 +459,7 @@ int podsdf_df_generate_seeded_host(podsdf_df_plan* p, uint64_t seed, long t0, lo
 int podsdf_df_random_slabs_dev(podsdf_df_plan* p, uint64_t seed, long s0, long n, double* slabs_dev, void* stream) {
   if (!p || !slabs_dev || n < 0 || s0 < 0) return fail(PODSDF_ERR_INVALID, "bad argument");
   DeviceGuard guard(p->device);
-  return launch_df_random_slabs(p->g, seed, s0, n, slabs_dev, (cudaStream_t)stream);
+  return launch_df_random_slabs(p->g, seed, p->rng, s0, n, slabs_dev, (cudaStream_t)stream);
 }
 
 int podsdf_df_random_slabs_host(podsdf_df_plan* p, uint64_t seed, long s0, long n, double* slabs_host) {
@@ -464,7 +473,7 @@ int podsdf_df_random_slabs_host(podsdf_df_plan* p, uint64_t seed, long s0, long 
   int rc = 0;
   for (long s = 0; s < n && !rc; s += chunk) {
     const long c = std::min(chunk, n - s);
-    rc = launch_df_random_slabs(p->g, seed, s0 + s, c, d, p->s_compute);
+    rc = launch_df_random_slabs(p->g, seed, p->rng, s0 + s, c, d, p->s_compute);
     if (!rc) {
       cudaError_t e = cudaMemcpyAsync(slabs_host + s * 3 * p->g.Np, d, per * c, cudaMemcpyDeviceToHost, p->s_compute);
       if (e == cudaSuccess) e = cudaStreamSynchronize(p->s_compute);

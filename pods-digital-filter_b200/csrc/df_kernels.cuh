@@ -45,9 +45,10 @@ bool df_plane_has_tuned(int nty, int ntz, bool diagonal);
 bool df_transform_is_diagonal(bool lund, unsigned mask, const Rot& rot);
 
 // T1[t] = sum_m bx[m] X[t + (NTX-1-m)] for t in [0, nsteps);  X has nsteps + NTX - 1 slabs.
-// gen != 0: X is ignored and slab s is Philox(seed, s_base + s) (generated mode, tuned kernels only).
+// src: 0 = injected slabs X; 1 / 2 = X is ignored and slab s is the Philox U53 / U32 stream (seed, s_base + s)
+// (generated mode, tuned kernels only; the two streams are defined in philox.cuh).
 int launch_df_time(const DfGeom& g, const PanelGeom& panel, const Taps& bx, const double* X, double* T1, int nsteps,
-                   bool gen, uint64_t seed, long s_base, bool tuned, cudaStream_t st);
+                   int src, uint64_t seed, long s_base, bool tuned, cudaStream_t st);
 
 // out[t][c][j][k] = sum_c' M[c][c'] * (by (*) bz (*) T1[t][c'])[j][k] + m[c]   for t in [0, nplanes)
 // ncomp_in = 3 normally; lund = false writes the filtered field unchanged (coef ignored).
@@ -60,7 +61,7 @@ int launch_df_plane(const DfGeom& g, const PanelGeom& panel, const Taps& by, con
 int launch_df_lund(const DfGeom& g, double* planes, const double* coef, unsigned mask, bool lund, const Rot& rot,
                    cudaStream_t st);
 
-// materialise Philox slabs [s0, s0+n) -> X[n][3][Np]
-int launch_df_random_slabs(const DfGeom& g, uint64_t seed, long s0, long n, double* X, cudaStream_t st);
+// materialise Philox slabs [s0, s0+n) of stream `kind` (PODSDF_RNG_*) -> X[n][3][Np]
+int launch_df_random_slabs(const DfGeom& g, uint64_t seed, int kind, long s0, long n, double* X, cudaStream_t st);
 
 }  // namespace podsdf

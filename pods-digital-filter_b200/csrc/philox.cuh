@@ -1,15 +1,26 @@
 // Philox4x32-10 counter-based generator for the generated-RNG mode of the DF path.
 // The reference draws U(-sqrt3, sqrt3) from the unseeded global MT19937 (digitalfilters.py:1344,
-// 1361-1366, 1460-1467); there is no reference stream to reproduce, so the product defines one that
-// any time shard can regenerate on its own (oracle/philox.py is its CPU restatement):
-//   key     = (seed lo, seed hi)
-//   counter = (pair lo, pair hi, s lo, comp + 4 * s hi)      pair = idx/2, idx = p*Kp + q, s = slab
-//   words r0..r3: (r0, r1) -> point idx = 2*pair, (r2, r3) -> point 2*pair + 1
-//   u = ((a >> 5) * 2^26 + (b >> 6)) * 2^-53 ;  x = -sqrt3 + (2 sqrt3) * u   (numpy's uniform())
+// 1361-1366, 1460-1467); there is no reference stream to reproduce, so the product defines its own, which
+// any time shard can regenerate on its own (oracle/philox.py is the CPU restatement of both kinds):
+//
+//   key = (seed lo, seed hi);  idx = p*Kp + q in the padded plane, pair = idx/2, half = idx & 1
+//
+//   kind PODSDF_RNG_U32 (default): one call serves two points x two slabs, 32 random bits per number
+//     counter = (pair lo, pair hi, sp lo, comp + 4 * sp hi),  sp = s/2, sh = s & 1 (s = slab)
+//     word r[2*sh + half];  v = 1 + (r + 1/2) 2^-32  (bits dropped into the mantissa of [1, 2));
+//     x = (v - 3/2) * (2 sqrt3)      -- v - 3/2 is exact, one rounding, symmetric about 0
+//   kind PODSDF_RNG_U53 (round 1's stream, numpy's 53-bit uniform()): one call serves two points of one slab
+//     counter = (pair lo, pair hi, s lo, comp + 4 * s hi);  (r0, r1) -> half 0, (r2, r3) -> half 1
+//     u = ((a >> 5) * 2^26 + (b >> 6)) * 2^-53 ;  x = -sqrt3 + (2 sqrt3) * u
+//
+// U32 halves the wide integer multiplies per random number (5 instead of 10 IMAD.WIDE) and needs two FP64
+// operations per number instead of five; the integer pipe was the limiter of the time filter in round 1.
 #pragma once
 #include <cstdint>
 
 namespace podsdf {
+
+constexpr int kRngU53 = 0, kRngU32 = 1;
 
 // round keys k + i*W are uniform across the grid: computed once on the host, passed by value
 struct PhiloxKeys {
@@ -41,6 +52,7 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
   r[0] = c0; r[1] = c1; r[2] = c2; r[3] = c3;
 }
 
+// ---- kind U53 ------------------------------------------------------------------------------------
 // n = (a >> 5) * 2^26 + (b >> 6) as an exact double without I2F (XU pipe): the two halves are dropped into
 // the mantissa of 2^52 / 2^78 and the biases subtracted (exact: all values are integers below 2^53 * 2^26)
 __device__ __forceinline__ double philox_to_uniform(uint32_t a, uint32_t b) {
@@ -53,13 +65,41 @@ __device__ __forceinline__ double philox_to_uniform(uint32_t a, uint32_t b) {
   return __dadd_rn(-s3, __dmul_rn((s3 - (-s3)) * (1.0 / 9007199254740992.0), n));
 }
 
-// the two random numbers of points (2*pair, 2*pair+1) of component `comp`, slab `s`
+// the two random numbers of points (2*pair, 2*pair+1) of component `comp`, slab `s` (kind U53)
 __device__ __forceinline__ void philox_pair(const PhiloxKeys& k, uint64_t pair, uint64_t s, int comp,
                                             double& x0, double& x1) {
   uint32_t r[4];
   philox4x32_10((uint32_t)pair, (uint32_t)(pair >> 32), (uint32_t)s, (uint32_t)comp + 4u * (uint32_t)(s >> 32), k, r);
   x0 = philox_to_uniform(r[0], r[1]);
   x1 = philox_to_uniform(r[2], r[3]);
+}
+
+// ---- kind U32 ------------------------------------------------------------------------------------
+// 32 random bits -> U(-sqrt3, sqrt3): the word becomes the top of the mantissa of a double in [1, 2) (with the
+// half-step bit below it, so the 2^32 levels are centred), then one exact subtraction and one multiplication
+__device__ __forceinline__ double philox_u32_to_uniform(uint32_t r) {
+  const double v = __hiloint2double((int)(0x3FF00000u | (r >> 12)), (int)((r << 20) | 0x80000u));
+  return __dmul_rn(__dadd_rn(v, -1.5), 1.7320508075688772 + 1.7320508075688772);
+}
+
+// the four words of (pair, slab pair sp, comp): r[2*sh + half]
+__device__ __forceinline__ void philox_quad(const PhiloxKeys& k, uint64_t pair, uint64_t sp, int comp, uint32_t (&r)[4]) {
+  philox4x32_10((uint32_t)pair, (uint32_t)(pair >> 32), (uint32_t)sp, (uint32_t)comp + 4u * (uint32_t)(sp >> 32), k, r);
+}
+
+// one random number of either kind (generic paths: wide filters, materialised slabs)
+template <int KIND>
+__device__ __forceinline__ double philox_value(const PhiloxKeys& k, uint64_t idx, uint64_t s, int comp) {
+  if (KIND == kRngU32) {
+    uint32_t r[4];
+    philox_quad(k, idx >> 1, s >> 1, comp, r);
+    const int w = 2 * (int)(s & 1) + (int)(idx & 1);
+    return philox_u32_to_uniform(w == 0 ? r[0] : (w == 1 ? r[1] : (w == 2 ? r[2] : r[3])));
+  } else {
+    double a, b;
+    philox_pair(k, idx >> 1, s, comp, a, b);
+    return (idx & 1) ? b : a;
+  }
 }
 
 }  // namespace podsdf

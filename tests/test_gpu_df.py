@@ -139,6 +139,33 @@ def test_config3_round_jet_512(P):
     assert rel_err(planes.reshape(ns, -1).T, ref) < TOL * 1e-2
 
 
+@pytest.mark.parametrize("nf", [4, 6, 8, 10, 12, 16])
+@pytest.mark.parametrize("transform", ["diagonal", "shear", "rotated"])
+def test_tuned_instantiations_match_oracle(P, nf, transform):
+    """Every compile-time (2nf+1, 2nf+1) instantiation of the tuned plane kernels -- the per-component (diagonal)
+    variant, the coupled variant with a shear stress (adapt1d pattern) and the coupled variant with a rotated plane
+    normal -- and of the tuned time kernels, against the oracle port of the reference loop (DF:100-178, 1119-1131)
+    on an injected stream.  The plane is two 64-column strips wide with a ragged second strip."""
+    J, K, ns = 40, 80, 3
+    ln = nf / 2.0
+    if transform == "shear":
+        prof = dfo.channel_profile(K)
+    else:
+        prof = dfo.build_profile("hyperbolic-tangent", "top-hat", 1.0, 0.05, K)
+    normal = (0.6, -0.48, 0.64) if transform == "rotated" else None
+    X = dfo.reference_stream(100 + nf, ns, J, K, nf, nf, nf)
+    ref = dfo.generate(X, ns, J, K, ln, ln, ln, nf, nf, nf, ("1d",) + tuple(prof), rotate=normal)
+    fm = P._lund.lund_1d(*prof, J, K)
+    R = P.digitalfilters.prof_rotation_matrix(*normal) if normal else None
+    planes = P.digitalfilters.generate(ns, J, K, ln, ln, ln, nf, nf, nf, fm, R,
+                                       slabs=np.ascontiguousarray(np.moveaxis(X, 0, 1)), impl=P._capi.IMPL_TUNED)
+    df = P.digitalfilters
+    info = df._plan(J, K, nf, nf, nf, df._taps(nf, ln), df._taps(nf, ln), df._taps(nf, ln)).info()
+    assert info["tuned_time"] and info["tuned_plane"] and info["diagonal"] == (transform == "diagonal")
+    df._plan(J, K, nf, nf, nf, df._taps(nf, ln), df._taps(nf, ln), df._taps(nf, ln)).set_impl(P._capi.IMPL_AUTO)
+    assert rel_err(planes.reshape(ns, -1).T, ref) < TOL * 1e-2
+
+
 @pytest.mark.parametrize("J,K,nfx,nfy,nfz", [(1, 37, 3, 0, 4), (5, 1, 2, 3, 0), (7, 131, 4, 4, 4), (70, 65, 10, 10, 10),
                                              (9, 200, 6, 6, 6), (33, 40, 24, 5, 20), (3, 3, 0, 0, 0)])
 def test_ragged_and_degenerate_planes(P, J, K, nfx, nfy, nfz):
@@ -167,33 +194,65 @@ def test_filter_is_linear(P):
     assert rel_err(lhs, rhs) < 1e-13
 
 
-def test_philox_stream_and_time_shards(P):
-    """Generated-RNG mode: the device stream equals its numpy restatement bit for bit; seeded generation
-    equals injection of the materialised stream; any time shard reproduces its own window."""
+@pytest.mark.parametrize("kind", ["u32", "u53"])
+def test_philox_stream_and_time_shards(P, kind):
+    """Generated-RNG mode, both streams: the device stream equals its numpy restatement bit for bit; seeded
+    generation equals injection of the materialised stream; any time shard (even or odd offset -- the U32 stream
+    pairs slabs) reproduces its own window."""
     J, K, nf = 20, 27, 4
     df = P.digitalfilters
     p = df._plan(J, K, nf, nf, nf, df._taps(nf, 2.0), df._taps(nf, 2.0), df._taps(nf, 2.0))
-    seed = 0x1234567890ABCDEF
-    dev = p.random_slabs(seed, 5, 9)
-    assert np.array_equal(dev, ophilox.slabs(seed, 5, 9, J + 2 * nf, K + 2 * nf))
-    big = p.random_slabs(seed, (1 << 33) + 1, 2)       # slab index beyond 32 bits
-    assert np.array_equal(big, ophilox.slabs(seed, (1 << 33) + 1, 2, J + 2 * nf, K + 2 * nf))
-    ns = 30
+    p.set_rng(P._capi.RNG_U32 if kind == "u32" else P._capi.RNG_U53)
+    try:
+        seed = 0x1234567890ABCDEF
+        for s0, n in ((5, 9), (4, 3), (0, 1)):
+            dev = p.random_slabs(seed, s0, n)
+            assert np.array_equal(dev, ophilox.slabs(seed, s0, n, J + 2 * nf, K + 2 * nf, kind))
+        big = p.random_slabs(seed, (1 << 33) + 1, 2)       # slab index beyond 32 bits
+        assert np.array_equal(big, ophilox.slabs(seed, (1 << 33) + 1, 2, J + 2 * nf, K + 2 * nf, kind))
+        ns = 30
+        p.set_coefficients(None, 0)
+        for impl in IMPLS:
+            p.set_impl(impl)
+            p.set_chunk(11)
+            whole = p.generate_seeded(seed, 0, ns)
+            inj = p.generate_injected(p.random_slabs(seed, 0, ns + 2 * nf))
+            # same numbers; the two modes may run different time-filter kernels (DFMA window / DMMA Toeplitz)
+            assert rel_err(whole, inj) < 1e-14
+            shard = p.generate_seeded(seed, 16, ns - 16)          # shard offsets that are multiples of 8: bitwise
+            assert np.array_equal(shard, whole[16:])
+            shard = p.generate_seeded(seed, 17, ns - 17)          # any other offset: same numbers to rounding
+            assert rel_err(shard, whole[17:]) < 1e-14
+            odd = p.generate_seeded(seed + 1, 3, 9)               # odd start of the stream itself
+            assert rel_err(odd, p.generate_injected(p.random_slabs(seed + 1, 3, 9 + 2 * nf))) < 1e-14
+        ref = dfo.generate(np.moveaxis(ophilox.slabs(seed, 0, ns + 2 * nf, J + 2 * nf, K + 2 * nf, kind), 1, 0),
+                           ns, J, K, 2.0, 2.0, 2.0, nf, nf, nf, None)
+        assert rel_err(whole.reshape(ns, -1).T, ref) < 1e-13
+    finally:
+        p.set_rng(P._capi.RNG_U32)
+
+
+@pytest.mark.parametrize("nf", [8, 10, 16])
+def test_seeded_equals_injected_tuned_sizes(P, nf):
+    """Every tuned time-filter size the seeded path can take (DFMA window at 17 / 21 taps, DMMA Toeplitz at 33)
+    against injection of the same materialised U32 stream, odd and even chunk starts."""
+    J = K = 64
+    df = P.digitalfilters
+    ln = nf / 2.0
+    p = df._plan(J, K, nf, nf, nf, df._taps(nf, ln), df._taps(nf, ln), df._taps(nf, ln))
     p.set_coefficients(None, 0)
-    for impl in IMPLS:
-        p.set_impl(impl)
-        p.set_chunk(11)
-        whole = p.generate_seeded(seed, 0, ns)
-        inj = p.generate_injected(p.random_slabs(seed, 0, ns + 2 * nf))
-        # same numbers; the two modes may run different time-filter kernels (DFMA window / DMMA Toeplitz)
-        assert rel_err(whole, inj) < 1e-14
-        shard = p.generate_seeded(seed, 16, ns - 16)          # shard offsets that are multiples of 8: bitwise
-        assert np.array_equal(shard, whole[16:])
-        shard = p.generate_seeded(seed, 17, ns - 17)          # any other offset: same numbers to rounding
-        assert rel_err(shard, whole[17:]) < 1e-14
-    ref = dfo.generate(np.moveaxis(ophilox.slabs(seed, 0, ns + 2 * nf, J + 2 * nf, K + 2 * nf), 1, 0),
-                       ns, J, K, 2.0, 2.0, 2.0, nf, nf, nf, None)
-    assert rel_err(whole.reshape(ns, -1).T, ref) < 1e-13
+    p.set_impl(P._capi.IMPL_TUNED)
+    try:
+        for t0, ns, chunk in ((0, 50, 1280), (7, 45, 16), (1, 96, 40)):
+            p.set_chunk(chunk)
+            a = p.generate_seeded(11, t0, ns)
+            X = p.random_slabs(11, t0, ns + 2 * nf)
+            assert np.array_equal(X, ophilox.slabs(11, t0, ns + 2 * nf, J + 2 * nf, K + 2 * nf))
+            assert rel_err(a, p.generate_injected(X)) < 1e-14
+        ref = dfo.generate(np.moveaxis(X, 1, 0), ns, J, K, ln, ln, ln, nf, nf, nf, None)
+        assert rel_err(a.reshape(ns, -1).T, ref) < 1e-13
+    finally:
+        p.set_impl(P._capi.IMPL_AUTO)
 
 
 def test_generated_field_statistics(P):

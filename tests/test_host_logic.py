@@ -191,3 +191,29 @@ def test_fourier_ranking_matches_the_tuple_sort():
     c = rs.standard_normal((50, 2)) + 0j
     c[7, 1] = np.nan                              # NaN column: falls back to the two-key sort, must not raise
     pod.select_fourier(c, 0.9)
+
+
+def test_philox_restatement_known_answers_and_u32_stream():
+    """oracle/philox.py: Philox4x32-10 against the Random123 known-answer vectors (kat_vectors of the Random123
+    distribution: zero, all-ones and pi-digit inputs), and the properties of the U32 stream the device kernels
+    use by default: exactly centred levels, exact end points, slab pairs sharing one call, shard reproducibility."""
+    from oracle import philox as ph
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff, 0xffffffff), (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        got = ph.philox4x32_10(*[np.array([c], dtype=np.uint64) for c in ctr], key[0], key[1])
+        assert tuple(int(g[0]) for g in got) == want
+    # conversion: word 0 -> lowest level, 2^32-1 -> highest, symmetric, spacing 2 sqrt3 / 2^32
+    x = ph.u32_to_uniform(np.array([0, 2 ** 32 - 1, 2 ** 31 - 1, 2 ** 31], dtype=np.uint64))
+    s3 = np.sqrt(3.0)
+    assert x[0] == -x[1] and x[2] == -x[3]
+    assert abs(x[1] - s3 * (1 - 2.0 ** -32)) < 1e-15 and abs(x[3] - s3 * 2.0 ** -32) < 1e-24
+    # stream structure
+    Jp, Kp = 9, 11          # odd number of points: the last pair is half used
+    a = ph.slabs(5, 0, 6, Jp, Kp)
+    assert np.array_equal(ph.slabs(5, 3, 2, Jp, Kp), a[3:5])
+    assert np.abs(a).max() < s3 and abs(a.mean()) < 0.1 and abs(a.var() - 1.0) < 0.1
+    b = ph.slabs(5, 0, 6, Jp, Kp, kind="u53")
+    assert not np.array_equal(a, b) and np.abs(b).max() < s3
