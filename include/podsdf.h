@@ -153,14 +153,21 @@ PODSDF_API int podsdf_eig_sym_host(int device, const double* C_host, long N, dou
 /* "All eigenvalues + the nm leading eigenvectors" (what PODFS.py:1329-1333 consumes of linalg.eig's result):
  * lambda[N] ascending as above; on exit rows 0..nm-1 of C (dev) / V[nm][N] (host) are the unit eigenvectors of the
  * nm LARGEST eigenvalues in DESCENDING order; the remaining rows of C are scratch.  *path (may be NULL) = 1 when the
- * tridiagonal route ran (Dsytrd, bisection, inverse iteration, Dormtr, re-orthonormalisation: the divide-and-conquer
- * and the N x N back-transformation are skipped), 0 when the leading eigenvalues were not well separated (relative
- * gap below 1e-7), a residual check failed or the size is unusual, and the full solver of podsdf_eig_sym_* ran. */
+ * tridiagonal route ran -- all of it this library's kernels: two-stage reduction (dense -> band -> tridiagonal),
+ * multisection / bisection, inverse iteration, back-transformation of the nm vectors, re-orthonormalisation --
+ * 0 when the leading eigenvalues were not well separated (relative gap below 1e-7), a residual check failed or the
+ * size is unusual (N < 256, N > 28000, 4 nm > N), and the full library solver of podsdf_eig_sym_* ran. */
 PODSDF_API int podsdf_eig_sym_top_dev(int device, double* C_dev_inout_V, long N, int nm, double* lambda_dev, int* path,
                            void* stream);
 PODSDF_API int podsdf_eig_sym_top_host(int device, const double* C_host, long N, int nm, double* lambda_host,
                             double* V_host, int* path);
 PODSDF_API int podsdf_eig_sym_dev(int device, double* C_dev_inout_V, long N, double* lambda_dev, void* stream);
+/* The reduction behind podsdf_eig_sym_top_*: two-stage tridiagonalisation of the symmetric C (N >= 3) with this
+ * library's own kernels (dense -> band of half-width 32 -> tridiagonal).  d[N], e[N-1]: diagonal and sub-diagonal of
+ * the similar tridiagonal matrix.  band (may be NULL): the intermediate band matrix, band[c*33 + k] = B[c+k][c],
+ * k = 0..32.  ms2 (may be NULL): device time of the two stages in ms.  Testing / profiling entry. */
+PODSDF_API int podsdf_sym_tridiag_host(int device, const double* C_host, long N, double* d_host, double* e_host,
+                            double* band_host, double* ms2);
 
 /* ref: projection POD:1329-1333.  Phi[M][nm] = A (M x N) . T (N x nm) . diag(dinv) * scale,
  * T = scaled temporal modes (row-major N x ldT, first nm columns used), dinv[nm] = 1/lambda. */

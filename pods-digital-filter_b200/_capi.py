@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpodsdf.so")
+LIB_PATH = os.environ.get("PODSDF_LIB") or os.path.join(HERE, "libpodsdf.so")   # PODSDF_LIB: A/B builds (tools/)
 
 OK, ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_UNSUPPORTED, ERR_NUMERIC = range(6)
 LAYOUT_ROWS_BY_TIME, LAYOUT_TIME_BY_ROWS = 0, 1
@@ -60,6 +60,7 @@ SIGNATURES = {
     "podsdf_eig_sym_top_dev": [_i, _vp, _l, _i, _vp, ctypes.POINTER(_i), _vp],
     "podsdf_eig_sym_top_host": [_i, _vp, _l, _i, _vp, _vp, ctypes.POINTER(_i)],
     "podsdf_eig_sym_dev": [_i, _vp, _l, _vp, _vp],
+    "podsdf_sym_tridiag_host": [_i, _vp, _l, _vp, _vp, _vp, _vp],
     "podsdf_project_host": [_i, _vp, _l, _l, _i, _vp, _l, _vp, _i, _d, _vp],
     "podsdf_project_dev": [_i, _vp, _l, _l, _i, _vp, _l, _vp, _i, _d, _vp, _vp],
     "podsdf_dft_modes_host": [_i, _vp, _l, _l, _i, _vp],
@@ -298,6 +299,17 @@ def eig_sym_top(C, nm, device=0):
     path = _i(0)
     check(lib().podsdf_eig_sym_top_host(device, ptr(C), N, int(nm), ptr(lam), ptr(V), ctypes.byref(path)))
     return lam, V, path.value
+
+
+def sym_tridiag(C, want_band=False, device=0):
+    """Two-stage tridiagonalisation of the symmetric C on the device: (d, e, band or None, (ms stage 1, ms stage 2))."""
+    C = f64(C, name="C")
+    N = C.shape[0]
+    d, e = np.empty(N), np.empty(max(N - 1, 0))
+    band = np.empty((N, 33)) if want_band else None
+    ms = np.zeros(2)
+    check(lib().podsdf_sym_tridiag_host(device, ptr(C), N, ptr(d), ptr(e), ptr(band), ptr(ms)))
+    return d, e, band, (float(ms[0]), float(ms[1]))
 
 
 def project(A, T, dinv, nm, scale, layout=LAYOUT_ROWS_BY_TIME, device=0):

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "csrc", "_obj")
 LIB = os.path.join(HERE, "libpodsdf.so")
-SOURCES = ["df_kernels.cu", "df_time_kernels.cu", "df_api.cu", "pod_kernels.cu", "eig_kernels.cu", "pod_api.cu"]
+SOURCES = ["df_kernels.cu", "df_time_kernels.cu", "df_api.cu", "pod_kernels.cu", "eig_kernels.cu", "sbr_kernels.cu", "pod_api.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"] + os.environ.get("PODSDF_EXTRA_NVCC_FLAGS", "").split()

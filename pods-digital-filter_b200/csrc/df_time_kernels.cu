@@ -196,6 +196,118 @@ df_time_tuned_kernel(const double* __restrict__ X, double* __restrict__ T1, cons
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// K-time, ring-of-4: ONE point per thread, steps in groups of FOUR.  The U32Q stream gives the four numbers
+// of (point, slabs 4g .. 4g+3) in one Philox call, so a group costs one call + 4 NT DFMA; the window is a ring
+// of NT + 3 registers (exactly the slabs a group touches), its pattern repeats after (NT + 3) / 4 groups, and
+// the unrolled body is NT + 3 steps of ONE point -- a quarter of the instructions of the pair kernel above,
+// small enough for the instruction cache.  Lanes <-> consecutive panel entries: 256-byte stores per warp.
+// ------------------------------------------------------------------------------------------------
+#ifndef PODSDF_R4_MINB
+#define PODSDF_R4_MINB 3
+#endif
+template <int NT, int SRC>
+__global__ void __launch_bounds__(256, PODSDF_R4_MINB)
+df_time_ring4_kernel(const double* __restrict__ X, double* __restrict__ T1, const Taps bx, const DfGeom g,
+                     const PanelGeom panel, const long npoint, const int nsteps, const int tchunk,
+                     const PhiloxKeys keys, const long s_base) {
+  static_assert(NT % 4 == 1, "the ring of NT + 3 slots must hold whole groups of four");
+  constexpr int R = NT + 3;
+  const long L = blockIdx.x * 256L + threadIdx.x;
+  if (L >= npoint) return;
+  const int c = blockIdx.y;
+  const int t0 = blockIdx.z * tchunk;
+  const int t1 = min(t0 + tchunk, nsteps);
+  const long Np = g.Np;
+  long ridx, wstride;
+  bool valid = true;
+  if (panel.PB > 0) {          // panel layout: L = (pb * Qpad + q) * 16 + r
+    const int r = (int)(L & 15);
+    const long col = L >> 4;
+    const int pb = (int)(col / panel.Qpad), q = (int)(col % panel.Qpad);
+    const int p = pb * 16 + r;
+    valid = (p < g.Jp) && (q < g.Kp);
+    ridx = (long)p * g.Kp + q;
+    wstride = panel.comp_stride;
+  } else {
+    ridx = L;
+    wstride = Np;
+  }
+  double* out = T1 + (long)c * wstride + L;
+  const long ostride = 3 * wstride;
+  if (!valid) {
+    for (int t = t0; t < t1; ++t) out[(long)t * ostride] = 0.0;
+    return;
+  }
+  const int last_slab = nsteps + NT - 2;
+  // groups start on a global slab that is a multiple of 4 (NT - 1 is one, so the slab entering at step tt is
+  // congruent to s_base + tt); up to three extra leading steps are computed and not written
+  const int E = (SRC != kSrcInjected) ? t0 - (int)((s_base + t0) & 3) : t0;
+
+  double w[R];
+  auto load4 = [&](int s, double& a0, double& a1, double& a2, double& a3) {
+    if (SRC != kSrcInjected) {
+      uint32_t r[4];
+      philox_quad(keys, (uint64_t)ridx, (uint64_t)((s_base + s) >> 2), c, r);
+      a0 = philox_u32_to_uniform(r[0]);
+      a1 = philox_u32_to_uniform(r[1]);
+      a2 = philox_u32_to_uniform(r[2]);
+      a3 = philox_u32_to_uniform(r[3]);
+    } else {
+      const double* p = X + (long)c * Np + ridx;
+      a0 = __ldcs(p + (long)min(s, last_slab) * 3 * Np);
+      a1 = __ldcs(p + (long)min(s + 1, last_slab) * 3 * Np);
+      a2 = __ldcs(p + (long)min(s + 2, last_slab) * 3 * Np);
+      a3 = __ldcs(p + (long)min(s + 3, last_slab) * 3 * Np);
+    }
+  };
+#pragma unroll
+  for (int i = 0; i < NT - 1; i += 4) load4(E + i, w[i], w[i + 1], w[i + 2], w[i + 3]);
+
+  for (int t = E; t < t1; t += R) {
+#pragma unroll
+    for (int gq = 0; gq < R; gq += 4) {
+      const int tt = t + gq;
+      if (tt < t1) {                             // CTA-uniform
+        load4(tt + NT - 1, w[(gq + NT - 1) % R], w[(gq + NT) % R], w[(gq + NT + 1) % R], w[(gq + NT + 2) % R]);
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          // true convolution (scipy.signal.convolve flips the taps): tap m meets slab tt + h + NT-1-m
+          double pa[4];
+#pragma unroll
+          for (int m = 0; m < NT; ++m) {
+            const int idx = (gq + h + NT - 1 - m) % R;
+            if (m < 4) pa[m] = bx.b[m] * w[idx];
+            else pa[m % 4] = fma(bx.b[m], w[idx], pa[m % 4]);
+          }
+          const int ts = tt + h;
+          if (ts >= t0 && ts < t1) out[(long)ts * ostride] = (pa[0] + pa[1]) + (pa[2] + pa[3]);
+        }
+      }
+    }
+  }
+}
+
+template <int NT>
+static void launch_time_ring4(const DfGeom& g, const PanelGeom& panel, const Taps& bx, const double* X, double* T1,
+                              int nsteps, int src, uint64_t seed, long s_base, cudaStream_t st) {
+  constexpr int R = NT + 3;
+  const long npoint = panel.PB > 0 ? (long)panel.PB * panel.Qpad * 16 : g.Np;
+  int nchunk = 1;
+  const long ctas_per_chunk = 3L * ceil_div(npoint, 256);
+  while (nchunk < 64 && ctas_per_chunk * nchunk < 148L * 3 * 8 && nsteps / (nchunk * 2) >= 8 * NT) nchunk *= 2;
+  int tchunk = ceil_div(nsteps, nchunk);
+  tchunk = ceil_div(tchunk, R) * R;              // whole unrolled blocks; a multiple of 4
+  nchunk = ceil_div(nsteps, tchunk);
+  dim3 grid(ceil_div(npoint, 256), 3, nchunk);
+  const PhiloxKeys keys = philox_keys(seed);
+  if (src != kSrcInjected)
+    df_time_ring4_kernel<NT, kSrcU32><<<grid, 256, 0, st>>>(X, T1, bx, g, panel, npoint, nsteps, tchunk, keys, s_base);
+  else
+    df_time_ring4_kernel<NT, kSrcInjected><<<grid, 256, 0, st>>>(X, T1, bx, g, panel, npoint, nsteps, tchunk, keys, s_base);
+  count_launch();
+}
+
 // K-time for wide filters (nfx = 24 .. 64): one point per thread (the window alone is NT doubles), and the
 // tap vector is cut in passes of <= 65 taps -- T1 = sum of the passes, each the same sliding-window kernel on
 // a shifted slab range (`s_off`), the later ones accumulating.  Config 5's wide end runs here.
@@ -505,6 +617,14 @@ int launch_df_time(const DfGeom& g, const PanelGeom& panel, const Taps& bx, cons
   if (nsteps <= 0) return 0;
   const int nt = 2 * g.nfx + 1;
   if (tuned) {
+    if (g_time_variant == 3) {                  // EXPERIMENT: ring-of-4 kernel (its own stream layout)
+      switch (nt) {
+#define F(N) case N: launch_time_ring4<N>(g, panel, bx, X, T1, nsteps, src, seed, s_base, st); PODSDF_CUDA(cudaGetLastError()); return 0;
+        F(9) F(13) F(17) F(21) F(25) F(33)
+#undef F
+        default: break;
+      }
+    }
     if (panel.PB > 0 && g_time_variant != 1) {
 #define F(N) case N: launch_time_mma<N>(g, panel, bx, X, T1, nsteps, src, seed, s_base, st); PODSDF_CUDA(cudaGetLastError()); return 0;
       if (g_time_variant == 2 || src == kSrcInjected) {   // injected slabs: the tensor-path kernel's 8-byte loads pattern is faster

@@ -41,8 +41,11 @@ inline PhiloxKeys philox_keys(uint64_t seed) {
 __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                               const PhiloxKeys& k, uint32_t (&r)[4]) {
   constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+#ifndef PODSDF_PHILOX_ROUNDS
+#define PODSDF_PHILOX_ROUNDS 10
+#endif
 #pragma unroll
-  for (int i = 0; i < 10; ++i) {
+  for (int i = 0; i < PODSDF_PHILOX_ROUNDS; ++i) {
     const uint64_t p0 = (uint64_t)M0 * c0, p1 = (uint64_t)M1 * c2;   // IMAD.WIDE.U32: hi and lo at once
     c0 = (uint32_t)(p1 >> 32) ^ c1 ^ k.k0[i];
     c1 = (uint32_t)p1;

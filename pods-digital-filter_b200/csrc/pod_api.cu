@@ -9,6 +9,7 @@
 #include "../../include/podsdf.h"
 #include "eig_kernels.cuh"
 #include "pod_kernels.cuh"
+#include "sbr_kernels.cuh"
 
 using namespace podsdf;
 
@@ -47,7 +48,8 @@ struct DevBuf {  // RAII device allocation
 };
 
 // ---- cuSOLVER, bound at run time -------------------------------------------------------------
-// The dense symmetric eigen-solve (PODFS.py:1309) is the one library call on this path.  cuSOLVER is
+// The FULL dense symmetric eigen-solve (all N eigenvectors: the drop-in POD() publishes every temporal mode,
+// PODFS.py:1309, 1391) and the fallback of the leading-pairs route are the one library call left.  cuSOLVER is
 // dlopen()ed so the library has no link-time dependency on a particular cuBLAS/cuSOLVER build: inside
 // a PyTorch process the copy PyTorch already loaded is reused, otherwise the toolkit's is taken.
 typedef void* cusolverDnHandle_t;
@@ -59,14 +61,6 @@ struct Cusolver {
   cusolverStatus_t (*set_stream)(cusolverDnHandle_t, cudaStream_t) = nullptr;
   cusolverStatus_t (*bufsize)(cusolverDnHandle_t, int, int, int, const double*, int, const double*, int*) = nullptr;
   cusolverStatus_t (*syevd)(cusolverDnHandle_t, int, int, int, double*, int, double*, double*, int, int*) = nullptr;
-  // tridiagonal reduction and its back-transformation (the "eigenvalues + leading vectors" route)
-  cusolverStatus_t (*sytrd_bufsize)(cusolverDnHandle_t, int, int, const double*, int, const double*, const double*,
-                                    const double*, int*) = nullptr;
-  cusolverStatus_t (*sytrd)(cusolverDnHandle_t, int, int, double*, int, double*, double*, double*, double*, int, int*) = nullptr;
-  cusolverStatus_t (*ormtr_bufsize)(cusolverDnHandle_t, int, int, int, int, int, const double*, int, const double*,
-                                    const double*, int, int*) = nullptr;
-  cusolverStatus_t (*ormtr)(cusolverDnHandle_t, int, int, int, int, int, double*, int, double*, double*, int, double*, int,
-                            int*) = nullptr;
   std::string err;
 };
 
@@ -90,10 +84,6 @@ Cusolver& cusolver() {
     cs.bufsize = (decltype(cs.bufsize))dlsym(cs.lib, "cusolverDnDsyevd_bufferSize");
     cs.syevd = (decltype(cs.syevd))dlsym(cs.lib, "cusolverDnDsyevd");
     if (!cs.create || !cs.destroy || !cs.set_stream || !cs.bufsize || !cs.syevd) cs.err = "libcusolver lacks Dsyevd";
-    cs.sytrd_bufsize = (decltype(cs.sytrd_bufsize))dlsym(cs.lib, "cusolverDnDsytrd_bufferSize");
-    cs.sytrd = (decltype(cs.sytrd))dlsym(cs.lib, "cusolverDnDsytrd");
-    cs.ormtr_bufsize = (decltype(cs.ormtr_bufsize))dlsym(cs.lib, "cusolverDnDormtr_bufferSize");
-    cs.ormtr = (decltype(cs.ormtr))dlsym(cs.lib, "cusolverDnDormtr");
   });
   return cs;
 }
@@ -150,54 +140,43 @@ SideStream& side_stream(int device) {
 
 // All eigenvalues (ascending, lambda_dev) and the eigenvectors of the nm largest: on exit rows 0..nm-1 of C are
 // those eigenvectors in DESCENDING order of the eigenvalue (the other rows are scratch).
-// Route 1: Dsytrd -> bisection for all eigenvalues -> inverse iteration for nm vectors of T -> Dormtr -> Cholesky-QR
-// (the divide-and-conquer and the N x N back-transformation of Dsyevd are skipped).  Route 0 (taken when the
-// leading eigenvalues are not well separated, when a check of route 1 fails, or for small / unusual sizes): the
-// full Dsyevd on a saved copy of C, then the leading rows are gathered.  *path reports which one ran.
+// Route 1 (all of it this library's own kernels): two-stage tridiagonalisation (sbr_kernels.cu: dense -> band with
+// FP64 tensor-core rank-2b updates, band -> tridiagonal by bulge chasing) -> multisection / bisection for all
+// eigenvalues -> inverse iteration for nm vectors of T -> back-transformation through both stages -> Cholesky-QR.
+// Route 0 (taken when the leading eigenvalues are not well separated, when a check of route 1 fails, or for small /
+// unusual sizes): cuSOLVER's full Dsyevd on a saved copy of C, then the leading rows are gathered.
+// *path reports which one ran.  PODSDF_EIG_ROUTE=0 forces route 0 (A/B timing).
 int eig_top_inplace(int device, double* C_dev, long N, int nm, double* lambda_dev, cudaStream_t st, int* path) {
   if (N > 46340) return fail(PODSDF_ERR_UNSUPPORTED, "N too large for the 32-bit cuSOLVER interface");
   if (nm < 1 || nm > N) return fail(PODSDF_ERR_INVALID, "nm must be in 1..N");
-  Cusolver& cs = cusolver();
-  if (!cs.err.empty()) return fail(PODSDF_ERR_CUDA, cs.err);
   std::lock_guard<std::recursive_mutex> lk(g_solver_mu);
-  const int n = (int)N;
-  const bool eligible = cs.sytrd && cs.sytrd_bufsize && cs.ormtr && cs.ormtr_bufsize && N >= 256 && nm <= 512 && 4L * nm <= N;
-  // scratch: [C copy | Z nm*N | d | e | tau | e2 | lam host-mirror unused | bounds 4 | resid nm | S nm*nm | flag | invit]
+  const char* force = getenv("PODSDF_EIG_ROUTE");
+  const bool eligible = N >= 256 && N <= 28000 && nm <= 512 && 4L * nm <= N && !(force && atoi(force) == 0);
+  // scratch: [C copy | Z nm*N | d | e | e2 | bounds 8 | resid nm | S nm*nm | flag | invit | sbr workspace]
   const size_t nn = (size_t)N * N, zn = (size_t)nm * N;
   const size_t invit = eligible ? tridiag_invit_workspace_doubles(N, nm) : 0;
-  const size_t total = nn + zn + 4 * (size_t)N + 8 + (size_t)nm + (size_t)nm * nm + 2 + invit;
+  const size_t sbrw = eligible ? sbr_workspace_doubles(N) : 0;
+  const size_t total = nn + zn + 3 * (size_t)N + 8 + (size_t)nm + (size_t)nm * nm + 2 + invit + sbrw + 64;
   double* ws = nullptr;
   PODSDF_TRY(scratch_get(device, 2, sizeof(double) * total, &ws));
   double* Ccopy = ws;
   double* Z = Ccopy + nn;
   double* d = Z + zn;
   double* e = d + N;
-  double* tau = e + N;
-  double* e2 = tau + N;
+  double* e2 = e + N;
   double* bounds = e2 + N;
   double* resid = bounds + 8;
   double* S = resid + nm;
   int* flag = reinterpret_cast<int*>(S + (size_t)nm * nm);
   double* winv = S + (size_t)nm * nm + 2;
+  double* wsbr = winv + invit;
+  wsbr += (32 - ((wsbr - ws) & 31)) & 31;             // keep the 256-byte alignment of the scratch base
   *path = 0;
   int rc = 0;
   bool fast_ok = false, side_pending = false;
   if (eligible) {
     PODSDF_CUDA(cudaMemcpyAsync(Ccopy, C_dev, sizeof(double) * nn, cudaMemcpyDeviceToDevice, st));
-    cusolverDnHandle_t& h = g_handles[device & 63];
-    if (!h && cs.create(&h) != 0) return fail(PODSDF_ERR_CUDA, "cusolverDnCreate failed");
-    if (cs.set_stream(h, st) != 0) return fail(PODSDF_ERR_CUDA, "cusolverDnSetStream failed");
-    int lw1 = 0, lw2 = 0;
-    // CUBLAS_FILL_MODE_LOWER = 0, CUBLAS_SIDE_LEFT = 0, CUBLAS_OP_N = 0
-    if (cs.sytrd_bufsize(h, 0, n, C_dev, n, d, e, tau, &lw1) != 0) return fail(PODSDF_ERR_CUDA, "Dsytrd_bufferSize failed");
-    if (cs.ormtr_bufsize(h, 0, 0, 0, n, nm, C_dev, n, tau, Z, n, &lw2) != 0)
-      return fail(PODSDF_ERR_CUDA, "Dormtr_bufferSize failed");
-    const int lwork = std::max(lw1, lw2);
-    double* work = nullptr;
-    PODSDF_TRY(scratch_get(device, 1, sizeof(double) * (size_t)std::max(lwork, 1), &work));
-    DevBuf info;
-    if (info.alloc(8) != cudaSuccess) return fail(PODSDF_ERR_CUDA, "eigen-solver workspace allocation failed");
-    if (cs.sytrd(h, 0, n, C_dev, n, d, e, tau, work, lwork, (int*)info.p) != 0) return fail(PODSDF_ERR_CUDA, "Dsytrd failed");
+    PODSDF_TRY(sbr_tridiagonalize(C_dev, N, d, e, wsbr, st, nullptr));
     // leading nm+1 eigenvalues first (warp-wide multisection, on the caller's stream: the inverse iteration waits
     // for them); the other N-nm-1 by plain bisection on a side stream, concurrently with everything below
     const long first = N - 1 - nm;      // ascending index of the (nm+1)-th largest (>= 0 because 4 nm <= N)
@@ -206,33 +185,59 @@ int eig_top_inplace(int device, double* C_dev, long N, int nm, double* lambda_de
     if (!side.ok) return fail(PODSDF_ERR_CUDA, "side stream creation failed");
     PODSDF_CUDA(cudaEventRecord(side.fork, st));
     PODSDF_CUDA(cudaStreamWaitEvent(side.s, side.fork, 0));
-    PODSDF_TRY(launch_tridiag_bisect(d, e2, bounds, N, first, lambda_dev, side.s));
-    PODSDF_CUDA(cudaEventRecord(side.join, side.s));
-    side_pending = true;
-    PODSDF_TRY(launch_tridiag_multisect(d, e2, bounds, N, first, lambda_dev, st));
+    rc = launch_tridiag_bisect(d, e2, bounds, N, first, lambda_dev, side.s);
+    if (!rc) {
+      PODSDF_CUDA(cudaEventRecord(side.join, side.s));
+      side_pending = true;
+    }
+    auto join_side = [&]() {            // every exit below waits for the side stream: it shares the scratch
+      if (side_pending) cudaStreamWaitEvent(st, side.join, 0);
+      side_pending = false;
+    };
+    if (!rc) rc = launch_tridiag_multisect(d, e2, bounds, N, first, lambda_dev, st);
     // the leading nm+1 eigenvalues decide whether independent inverse iterations are safe
     std::vector<double> top((size_t)nm + 1);
-    PODSDF_CUDA(cudaMemcpyAsync(top.data(), lambda_dev + first, sizeof(double) * (nm + 1), cudaMemcpyDeviceToHost, st));
-    PODSDF_CUDA(cudaStreamSynchronize(st));
+    double hb[4] = {0, 0, 0, 0};
+    if (!rc) {
+      cudaError_t ce = cudaMemcpyAsync(top.data(), lambda_dev + first, sizeof(double) * (nm + 1), cudaMemcpyDeviceToHost, st);
+      if (ce == cudaSuccess) ce = cudaMemcpyAsync(hb, bounds, sizeof(double) * 4, cudaMemcpyDeviceToHost, st);
+      if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+      if (ce != cudaSuccess) rc = cuda_fail(ce, "eigenvalue readback", __FILE__, __LINE__);
+    }
+    if (rc) {
+      join_side();
+      cudaStreamSynchronize(st);
+      return rc;
+    }
     const double lmax = std::fabs(top[nm]);
     bool separated = lmax > 0.0;
     for (int j = 0; j < nm && separated; ++j)
       if (!(top[j + 1] - top[j] > 1.0e-7 * lmax)) separated = false;
     if (separated) {
-      PODSDF_TRY(launch_tridiag_invit(d, e, bounds, lambda_dev, N, nm, winv, Z, resid, st));
-      if (cs.ormtr(h, 0, 0, 0, n, nm, C_dev, n, tau, Z, n, work, lwork, (int*)info.p) != 0)
-        return fail(PODSDF_ERR_CUDA, "Dormtr failed");
-      PODSDF_TRY(launch_orthonormalize_rows(Z, N, nm, S, flag, st));
+      rc = launch_tridiag_invit(d, e, bounds, lambda_dev, N, nm, winv, Z, resid, st);
+      if (!rc) rc = sbr_back_transform(wsbr, N, Z, nm, st);
+      if (!rc) rc = launch_orthonormalize_rows(Z, N, nm, S, flag, st);
       std::vector<double> hres((size_t)nm);
       int hflag = 1;
-      PODSDF_CUDA(cudaMemcpyAsync(hres.data(), resid, sizeof(double) * nm, cudaMemcpyDeviceToHost, st));
-      PODSDF_CUDA(cudaMemcpyAsync(&hflag, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
-      PODSDF_CUDA(cudaStreamSynchronize(st));
+      if (!rc) {
+        cudaError_t ce = cudaMemcpyAsync(hres.data(), resid, sizeof(double) * nm, cudaMemcpyDeviceToHost, st);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(&hflag, flag, sizeof(int), cudaMemcpyDeviceToHost, st);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+        if (ce != cudaSuccess) rc = cuda_fail(ce, "eigenvector check readback", __FILE__, __LINE__);
+      }
+      if (rc) {
+        join_side();
+        cudaStreamSynchronize(st);
+        return rc;
+      }
+      // acceptance: the tridiagonal residual |T z - lambda z|_inf / |T| of every vector at rounding level
+      // (inverse iteration with an eigenvalue accurate to eps |T| gives ~eps; with gaps > 1e-7 |T| the vector
+      // error is then below ~1e-8 before, and at rounding level after, the re-orthonormalisation)
       fast_ok = hflag == 0;
       for (int j = 0; j < nm && fast_ok; ++j)
-        if (!(hres[j] < 1.0e-12)) fast_ok = false;
+        if (!(hres[j] < 1.0e-13)) fast_ok = false;
     }
-    if (side_pending) PODSDF_CUDA(cudaStreamWaitEvent(st, side_stream(device).join, 0));   // all of lambda is written
+    join_side();                                             // all of lambda is written
     if (!fast_ok) PODSDF_CUDA(cudaMemcpyAsync(C_dev, Ccopy, sizeof(double) * nn, cudaMemcpyDeviceToDevice, st));
   }
   if (fast_ok) {
@@ -359,6 +364,37 @@ int podsdf_eig_sym_host(int device, const double* C_host, long N, double* lambda
   PODSDF_TRY(launch_transpose(C.p, V.p, N, nullptr));  // rows = vectors  ->  columns = vectors
   PODSDF_CUDA(cudaMemcpy(V_host, V.p, nn, cudaMemcpyDeviceToHost));
   PODSDF_CUDA(cudaMemcpy(lambda_host, lam.p, sizeof(double) * (size_t)N, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int podsdf_sym_tridiag_host(int device, const double* C_host, long N, double* d_host, double* e_host, double* band_host,
+                            double* ms2) {
+  if (!C_host || !d_host || !e_host || N < 3) return fail(PODSDF_ERR_INVALID, "bad argument");
+  PODSDF_TRY(check_device(device));
+  DeviceGuard guard(device);
+  DevBuf C, ws, de, band;
+  const size_t nn = sizeof(double) * (size_t)N * N;
+  PODSDF_CUDA(C.alloc(nn));
+  PODSDF_CUDA(ws.alloc(sizeof(double) * sbr_workspace_doubles(N)));
+  PODSDF_CUDA(de.alloc(sizeof(double) * 2 * (size_t)N));
+  if (band_host) {      // stage 1 alone on a first copy
+    PODSDF_CUDA(band.alloc(sizeof(double) * (size_t)N * kSbrLdb));
+    PODSDF_CUDA(cudaMemcpy(C.p, C_host, nn, cudaMemcpyHostToDevice));
+    PODSDF_TRY(sbr_stage1_only(C.p, N, ws.p, band.p, nullptr));
+    std::vector<double> hb((size_t)N * kSbrLdb);
+    PODSDF_CUDA(cudaMemcpy(hb.data(), band.p, sizeof(double) * hb.size(), cudaMemcpyDeviceToHost));
+    for (long c = 0; c < N; ++c)
+      for (int dd = 0; dd <= kSbrB; ++dd) band_host[c * (kSbrB + 1) + dd] = hb[(size_t)c * kSbrLdb + dd];
+  }
+  PODSDF_CUDA(cudaMemcpy(C.p, C_host, nn, cudaMemcpyHostToDevice));
+  float t[2] = {0, 0};
+  PODSDF_TRY(sbr_tridiagonalize(C.p, N, de.p, de.p + N, ws.p, nullptr, t));
+  if (ms2) {
+    ms2[0] = t[0];
+    ms2[1] = t[1];
+  }
+  PODSDF_CUDA(cudaMemcpy(d_host, de.p, sizeof(double) * (size_t)N, cudaMemcpyDeviceToHost));
+  PODSDF_CUDA(cudaMemcpy(e_host, de.p + N, sizeof(double) * (size_t)(N - 1), cudaMemcpyDeviceToHost));
   return 0;
 }
 

@@ -1,0 +1,906 @@
+// Two-stage symmetric tridiagonalisation on sm_100a (successive band reduction) + back-transformation.
+//
+// Reference behaviour being replaced (file:line under /root/reference): PODFS.py:1309 `linalg.eig(C)` -- LAPACK's
+// dense eigen-solver, of which PODFS consumes all eigenvalues (PODFS.py:1312-1320, 1409-1427) and the nm leading
+// eigenvectors (PODFS.py:1323-1333).  Round 1 reduced C with cuSOLVER's one-stage Dsytrd (half of its flops are
+// matrix-vector products: 0.64 s at N = 10^4); here:
+//
+//   stage 1  dense -> band of half-width b = 32.  Per 32-column panel:
+//              QR of the panel below the band    one cooperative kernel, thread = panel row (registers), one grid
+//                                                barrier per column; also yields the T factor of the block reflector
+//              X = A22 V                         FP64 tensor-core MMA (mma.sync m8n8k4), lower triangle read in both
+//                                                orientations, split over K
+//              W = X T - 1/2 V (T^T V^T X T)     two small kernels
+//              A22 -= V W^T + W V^T              FP64 tensor-core MMA rank-2b update, lower tiles + full diagonal tiles
+//   stage 2  band -> tridiagonal by bulge chasing (Murata-Horikoshi / Lang): sweep i = chain of b x b tasks, one warp
+//            per sweep, sweeps pipelined two tasks apart through progress counters in global memory (persistent
+//            cooperative kernel)
+//   back     eigenvectors of T -> eigenvectors of C: stage-2 reflectors (reverse order), then the block reflectors of
+//            stage 1, one CTA per vector with the vector in shared memory
+//
+// Storage: A is N x N with element (r, c) at A[c*N + r] (symmetric, so row- and column-major coincide); skinny
+// matrices are k-major: V[m*N + r] is entry (r, m).  tools/proto_sbr.py is the numpy model of every step below.
+#include "sbr_kernels.cuh"
+
+#include <cfloat>
+
+namespace podsdf {
+
+namespace {
+
+constexpr int B = kSbrB;
+constexpr int LDB = kSbrLdb;
+
+__device__ __forceinline__ void dmma884s(double& c0, double& c1, const double a, const double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void cpa8(void* smem_dst, const void* gsrc, bool valid) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int bytes = valid ? 8 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(d), "l"(gsrc), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cpa_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N_>
+__device__ __forceinline__ void cpa_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N_) : "memory");
+}
+
+// ---- grid barrier for the cooperative kernels (all CTAs co-resident: launched with cudaLaunchCooperativeKernel).
+// Monotone counter: barrier number `phase` (1, 2, ...) is passed when the counter reaches phase * gridDim.x.
+// Spins are bounded: a lost CTA raises the error flag instead of hanging the GPU.
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ bool grid_barrier(unsigned* counter, unsigned* err, unsigned phase) {
+  __shared__ int s_ok;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    const unsigned target = phase * gridDim.x;
+    int ok = 1;
+    unsigned spins = 0;
+    while (ld_acquire_u32(counter) < target) {
+      if (++spins > (1u << 24)) {
+        if ((spins & 0xFFFFu) == 0 && ld_acquire_u32(err) != 0) { ok = 0; break; }
+        if (spins > (1u << 28)) { atomicExch(err, 1u); ok = 0; break; }
+      }
+    }
+    s_ok = ok;
+  }
+  __syncthreads();
+  return s_ok != 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stage 1a: Householder QR of the panel A[r0:N, c0:c0+B] (n = N - r0 rows), LAPACK dgeqr2 + dlarft in one pass.
+//   thread = one panel row, its B entries in registers; column j needs only ONE global reduction: with
+//   S_m = sum_{rows > j} P[r][j] P[r][m] (m >= j) every thread derives beta, tau, v and the update of its row
+//   (v^T P[:, m] = P[j][m] + S_m / (alpha - beta)).  The same reduction carries g_i = V[:, i]^T v_{j-1} (i < j-1)
+//   for the T factor: T[:j, j] = -tau_j T[:j, :j] (V[:, :j]^T v_j).
+//   Partials go through part[phase & 1][cta][B]; every CTA sums them in the same order -> identical values.
+// Outputs: R (upper triangle) back into A, V rows c0 .. c0+B-1 of Vall (explicit ones / zeros), T (B x B, row-major).
+// ------------------------------------------------------------------------------------------------
+constexpr int QR_THREADS = 512;
+
+__global__ void __launch_bounds__(QR_THREADS, 1)
+sbr_panel_qr_kernel(double* __restrict__ A, const long N, const int c0, double* __restrict__ Vall,
+                    double* __restrict__ Tout, double* __restrict__ part, double* __restrict__ rowj,
+                    unsigned* __restrict__ bar) {
+  __shared__ double s_red[QR_THREADS / 32][B];
+  __shared__ double s_S[B], s_R[B], s_T[B][B + 1], s_tau[B];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int G = gridDim.x, cta = blockIdx.x;
+  const long r0 = c0 + B;
+  const long n = N - r0;
+  const long row = (long)cta * QR_THREADS + tid;
+  const bool active = row < n;
+  unsigned* counter = bar;
+  unsigned* err = bar + 1;
+
+  double p[B];
+#pragma unroll
+  for (int m = 0; m < B; ++m) p[m] = active ? A[(long)(c0 + m) * N + r0 + row] : 0.0;
+  if (cta == 0)
+    for (int e = tid; e < B * (B + 1); e += QR_THREADS) (&s_T[0][0])[e] = 0.0;
+
+  unsigned phase = 0;
+#pragma unroll 1
+  for (int j = 0; j <= B; ++j) {
+    // p[j] and p[j-1] without dynamic register indexing
+    double pj = 0.0, pjm1 = 0.0;
+#pragma unroll
+    for (int m = 0; m < B; ++m) {
+      if (m == j) pj = p[m];
+      if (m == j - 1) pjm1 = p[m];
+    }
+    // ---- phase A: this row's contributions.  slots m >= j: P[r][j] P[r][m] over rows > j (column j's norm and dots);
+    // slots i < j-1: V[r][i] v_{j-1}[r] over rows >= j-1 (T factor of the column finished in the previous step)
+    const double fa = (j < B && active && row > j) ? pj : 0.0;
+    const double fb = (j >= 1 && active) ? ((row > j - 1) ? pjm1 : (row == j - 1 ? 1.0 : 0.0)) : 0.0;
+#pragma unroll
+    for (int m = 0; m < B; ++m) {
+      double v = (m >= j) ? fa * p[m] : ((m < j - 1) ? fb * p[m] : 0.0);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) s_red[warp][m] = v;
+    }
+    __syncthreads();
+    if (tid < B) {
+      double v = 0.0;
+#pragma unroll
+      for (int w = 0; w < QR_THREADS / 32; ++w) v += s_red[w][tid];
+      __stcg(part + ((long)(j & 1) * G + cta) * B + tid, v);
+    }
+    if (j < B && active && row == j) {
+#pragma unroll
+      for (int m = 0; m < B; ++m) __stcg(rowj + (j & 1) * B + m, p[m]);
+    }
+    if (!grid_barrier(counter, err, ++phase)) return;
+    // ---- phase B: everyone sums the partials in the same order
+    if (tid < B) {
+      double v = 0.0;
+      for (int g2 = 0; g2 < G; ++g2) v += __ldcg(part + ((long)(j & 1) * G + g2) * B + tid);   // L2: other CTAs' data
+      s_S[tid] = v;
+      s_R[tid] = (j < B) ? __ldcg(rowj + (j & 1) * B + tid) : 0.0;
+    }
+    __syncthreads();
+    if (cta == 0 && j >= 1 && tid < j - 1) {            // T[:j-1, j-1] = -tau_{j-1} T[:j-1, :j-1] g, g = s_S[0 .. j-2]
+      double acc = 0.0;
+      for (int l = tid; l < j - 1; ++l) acc = fma(s_T[tid][l], s_S[l], acc);
+      s_T[tid][j - 1] = -s_tau[j - 1] * acc;
+    }
+    if (j < B) {
+      const double alpha = s_R[j], sigma = s_S[j];
+      double beta = alpha, tau = 0.0, scale = 0.0;
+      if (sigma > 0.0) {
+        beta = -copysign(sqrt(fma(alpha, alpha, sigma)), alpha);
+        tau = (beta - alpha) / beta;
+        scale = 1.0 / (alpha - beta);
+      }
+      if (cta == 0 && tid == 0) {
+        s_tau[j] = tau;
+        s_T[j][j] = tau;
+      }
+      if (active && row >= j) {
+        const bool top = row == j;
+        const double v = top ? 1.0 : pj * scale;
+        const double tv = tau * v;
+#pragma unroll
+        for (int m = 0; m < B; ++m) {
+          if (m > j) p[m] = fma(-tv, fma(scale, s_S[m], s_R[m]), p[m]);
+          if (m == j) p[m] = top ? beta : v;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // ---- write back: R (rows < B, upper triangle incl. diagonal) into A; V (unit lower trapezoid) into Vall
+  if (active) {
+#pragma unroll
+    for (int m = 0; m < B; ++m) {
+      if (row <= m) A[(long)(c0 + m) * N + r0 + row] = p[m];
+      Vall[(long)(c0 + m) * N + r0 + row] = (row > m) ? p[m] : (row == m ? 1.0 : 0.0);
+    }
+  }
+  if (cta == 0)
+    for (int e = tid; e < B * B; e += QR_THREADS) Tout[e] = s_T[e / B][e % B];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stage 1b: Xp[split][m][r] = sum over this split's t of A22[r][t] V[t][m]   (rows r0 .. N-1, t in r0 .. N-1)
+//   CTA = 128 rows x 32 columns, 8 warps (16 rows x 32 columns each), K in chunks of 16, 3-stage cp.async.
+//   Only the lower triangle of A22 is valid (plus full diagonal tiles): a chunk whose t-block lies left of / on the
+//   row block is read as A[t*N + r] ("t-major": tile [16 t][128 + 4]), one to the right of it as A[r*N + t]
+//   ("row-major": tile [128 r][16 + 4]) -- the two smem layouts of the projection kernel, chosen per chunk.
+// ------------------------------------------------------------------------------------------------
+constexpr int XR = 128, XKB = 16, XST = 3;
+constexpr int XPA0 = XKB + 4, XPA1 = XR + 4, XPV = XKB + 4;
+constexpr int XATILE = (XR * XPA0 > XKB * XPA1) ? XR * XPA0 : XKB * XPA1;
+constexpr int XVTILE = B * XPV;
+constexpr size_t XSMEM = (size_t)XST * (XATILE + XVTILE) * sizeof(double);
+
+__global__ void __launch_bounds__(256, 1)
+sbr_symm_kernel(const double* __restrict__ A, const long N, const long r0, const double* __restrict__ V,
+                double* __restrict__ Xp, const int chunks_per_split) {
+  extern __shared__ double smem[];
+  double* sA = smem;
+  double* sV = smem + XST * XATILE;
+  // tiles are anchored at absolute multiples of 128 (not at r0), so "diagonal tile" means the same elements for
+  // every panel; rows / columns below r0 are masked
+  const long tile = r0 / XR + blockIdx.x;                    // absolute row-tile index
+  const long row0 = tile * XR;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lr = lane & 3, lc = lane >> 2;
+  const int wr = warp * 16;
+  const int chunk_lo = (int)(r0 / XKB), chunk_hi = (int)((N + XKB - 1) / XKB);   // absolute 16-column chunks
+  const int c_begin = chunk_lo + blockIdx.y * chunks_per_split;
+  const int c_end = min(chunk_hi, c_begin + chunks_per_split);
+  const int nchunks = max(0, c_end - c_begin);
+
+  auto tmajor = [&](int chunk) { return ((long)chunk * XKB) / XR <= tile; };   // t-block <= row block
+  auto load_stage = [&](int chunk, int stage) {
+    const long t0 = (long)chunk * XKB;
+    double* a = sA + stage * XATILE;
+    double* vv = sV + stage * XVTILE;
+    if (tmajor(chunk)) {                                      // A[t*N + row]: rows contiguous
+      for (int e = tid; e < XKB * XR; e += 256) {
+        const int t = e / XR, r = e % XR;
+        cpa8(a + t * XPA1 + r, A + (t0 + t) * N + row0 + r, (row0 + r >= r0) && (row0 + r < N) && (t0 + t < N));
+      }
+    } else {                                                  // A[row*N + t]: t contiguous
+      for (int e = tid; e < XR * XKB; e += 256) {
+        const int r = e / XKB, t = e % XKB;
+        cpa8(a + r * XPA0 + t, A + (row0 + r) * N + t0 + t, (row0 + r >= r0) && (row0 + r < N) && (t0 + t < N));
+      }
+    }
+    for (int e = tid; e < B * XKB; e += 256) {                // V[m][t] -> sV[m][t]
+      const int m = e / XKB, t = e % XKB;
+      cpa8(vv + m * XPV + t, V + (long)m * N + t0 + t, t0 + t < N);
+    }
+  };
+
+  double acc[2][4][2];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+
+  for (int s = 0; s < XST - 1; ++s) {
+    if (s < nchunks) load_stage(c_begin + s, s);
+    cpa_commit();
+  }
+  for (int c = 0; c < nchunks; ++c) {
+    cpa_wait<XST - 2>();
+    __syncthreads();
+    if (c + XST - 1 < nchunks) load_stage(c_begin + c + XST - 1, (c + XST - 1) % XST);
+    cpa_commit();
+    const double* a = sA + (c % XST) * XATILE;
+    const double* vv = sV + (c % XST) * XVTILE;
+    const bool tm = tmajor(c_begin + c);
+#pragma unroll
+    for (int k4 = 0; k4 < XKB; k4 += 4) {
+      double af[2], bf[4];
+      const int t = k4 + lr;
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) af[mt] = tm ? a[t * XPA1 + wr + mt * 8 + lc] : a[(wr + mt * 8 + lc) * XPA0 + t];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) bf[nt] = vv[(nt * 8 + lc) * XPV + t];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) dmma884s(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
+    }
+  }
+  cpa_wait<0>();
+  double* Xs = Xp + (long)blockIdx.y * B * N;
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const long row = row0 + wr + mt * 8 + lc;
+      const int m = nt * 8 + 2 * lr;
+      if (row >= r0 && row < N) {
+        Xs[(long)m * N + row] = acc[mt][nt][0];
+        Xs[(long)(m + 1) * N + row] = acc[mt][nt][1];
+      }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stage 1c: X = sum of the split partials; Zp[cta] = V_chunk^T X_chunk (B x B partial of V^T X)
+// ------------------------------------------------------------------------------------------------
+constexpr int WR = 64;    // rows per CTA of sbr_w1_kernel
+constexpr int WR2 = 32;   // rows per CTA of sbr_w2_kernel
+
+__global__ void __launch_bounds__(256)
+sbr_w1_kernel(const double* __restrict__ Xp, const int nsplit, const double* __restrict__ V, const long N,
+              const long r0, double* __restrict__ X, double* __restrict__ Zp) {
+  __shared__ double sV[B][WR + 1], sX[B][WR + 1];
+  const long n = N - r0;
+  const long row0 = (long)blockIdx.x * WR;
+  const int tid = threadIdx.x;
+  for (int e = tid; e < B * WR; e += 256) {
+    const int m = e / WR, r = e % WR;
+    const bool ok = row0 + r < n;
+    double x = 0.0;
+    if (ok)
+      for (int s = 0; s < nsplit; ++s) x += Xp[((long)s * B + m) * N + r0 + row0 + r];
+    sX[m][r] = x;
+    sV[m][r] = ok ? V[(long)m * N + r0 + row0 + r] : 0.0;
+    if (ok) X[(long)m * N + r0 + row0 + r] = x;
+  }
+  __syncthreads();
+  for (int e = tid; e < B * B; e += 256) {
+    const int m1 = e / B, m2 = e % B;
+    double acc = 0.0;
+#pragma unroll 8
+    for (int r = 0; r < WR; ++r) acc = fma(sV[m1][r], sX[m2][r], acc);
+    Zp[(long)blockIdx.x * B * B + e] = acc;
+  }
+}
+
+// Stage 1d: Z = sum Zp;  S = T^T Z T;  W = X T - 1/2 V S   (every CTA recomputes the 32 x 32 products)
+__global__ void __launch_bounds__(256)
+sbr_w2_kernel(const double* __restrict__ X, const double* __restrict__ V, const double* __restrict__ T,
+              const double* __restrict__ Zp, const int nz, const long N, const long r0, double* __restrict__ W) {
+  __shared__ double sT[B][B + 1], sZ[B][B + 1], sU[B][B + 1];      // sZ: Z, later S
+  __shared__ double sV[B][WR2 + 1], sX[B][WR2 + 1];
+  const long n = N - r0;
+  const long row0 = (long)blockIdx.x * WR2;
+  const int tid = threadIdx.x;
+  for (int e = tid; e < B * B; e += 256) {
+    double z = 0.0;
+    for (int g2 = 0; g2 < nz; ++g2) z += Zp[(long)g2 * B * B + e];
+    sZ[e / B][e % B] = z;
+    sT[e / B][e % B] = T[e];
+  }
+  for (int e = tid; e < B * WR2; e += 256) {
+    const int m = e / WR2, r = e % WR2;
+    const bool ok = row0 + r < n;
+    sX[m][r] = ok ? X[(long)m * N + r0 + row0 + r] : 0.0;
+    sV[m][r] = ok ? V[(long)m * N + r0 + row0 + r] : 0.0;
+  }
+  __syncthreads();
+  for (int e = tid; e < B * B; e += 256) {                    // U = Z T
+    const int a = e / B, c = e % B;
+    double acc = 0.0;
+    for (int l = 0; l <= c; ++l) acc = fma(sZ[a][l], sT[l][c], acc);     // T upper triangular
+    sU[a][c] = acc;
+  }
+  __syncthreads();
+  for (int e = tid; e < B * B; e += 256) {                    // S = T^T U  (into sZ)
+    const int a = e / B, c = e % B;
+    double acc = 0.0;
+    for (int l = 0; l <= a; ++l) acc = fma(sT[l][a], sU[l][c], acc);
+    sZ[a][c] = acc;
+  }
+  __syncthreads();
+  for (int e = tid; e < B * WR2; e += 256) {
+    const int m = e / WR2, r = e % WR2;
+    if (row0 + r < n) {
+      double acc = 0.0;
+      for (int l = 0; l <= m; ++l) acc = fma(sX[l][r], sT[l][m], acc);
+      double acc2 = 0.0;
+#pragma unroll 8
+      for (int l = 0; l < B; ++l) acc2 = fma(sV[l][r], sZ[l][m], acc2);
+      W[(long)m * N + r0 + row0 + r] = fma(-0.5, acc2, acc);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stage 1e: A22 -= V W^T + W V^T on the tiles (I >= J) of the trailing matrix (diagonal tiles in full).
+//   CTA = 128 x 128 tile, 8 warps x (64 x 32), K = 2B in chunks of 16 (gram-kernel micro-kernel, layout [k][128+4]):
+//   operand a (rows i): k < B -> -V[k][i], else -W[k-B][i];  operand b (rows j): k < B -> W[k][j], else V[k-B][j].
+//   The accumulators start as the old tile, so the epilogue is a plain store.
+// ------------------------------------------------------------------------------------------------
+constexpr int UT = 128, UKB = 16, UP = UT + 4;
+constexpr size_t USMEM = (size_t)2 * 2 * B * UP * sizeof(double);
+
+__global__ void __launch_bounds__(256, 1)
+sbr_syr2k_kernel(double* __restrict__ A, const long N, const long r0, const double* __restrict__ V,
+                 const double* __restrict__ W) {
+  extern __shared__ double smem[];
+  double* sA = smem;                    // [2B][UP]
+  double* sB = smem + 2 * B * UP;       // [2B][UP]
+  int ib = 0, rem = blockIdx.x;         // linear id -> (ib >= jb): row ib holds ib + 1 tiles
+  while (rem > ib) { rem -= ib + 1; ++ib; }
+  const long tile0 = r0 / UT;           // tiles anchored at absolute multiples of 128 (see sbr_symm_kernel)
+  const long i0 = (tile0 + ib) * UT, j0 = (tile0 + rem) * UT;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = (warp >> 2) * 64, wn = (warp & 3) * 32;
+  const int lr = lane & 3, lc = lane >> 2;
+
+  for (int e = tid; e < 2 * B * UT; e += 256) {
+    const int k = e / UT, x = e % UT;
+    const double* pa = (k < B) ? V + (long)k * N : W + (long)(k - B) * N;
+    const double* pb = (k < B) ? W + (long)k * N : V + (long)(k - B) * N;
+    cpa8(sA + k * UP + x, pa + i0 + x, (i0 + x >= r0) && (i0 + x < N));
+    cpa8(sB + k * UP + x, pb + j0 + x, (j0 + x >= r0) && (j0 + x < N));
+  }
+  cpa_commit();
+
+  double acc[8][4][2];
+#pragma unroll
+  for (int mt = 0; mt < 8; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const long i = i0 + wm + mt * 8 + lc, j = j0 + wn + nt * 8 + 2 * lr;
+      const bool iok = i >= r0 && i < N;
+      acc[mt][nt][0] = (iok && j >= r0 && j < N) ? A[j * N + i] : 0.0;
+      acc[mt][nt][1] = (iok && j + 1 >= r0 && j + 1 < N) ? A[(j + 1) * N + i] : 0.0;
+    }
+  cpa_wait<0>();
+  __syncthreads();
+#pragma unroll 4
+  for (int k4 = 0; k4 < 2 * B; k4 += 4) {
+    double af[8], bf[4];
+    const int r = k4 + lr;
+#pragma unroll
+    for (int mt = 0; mt < 8; ++mt) af[mt] = -sA[r * UP + wm + mt * 8 + lc];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) bf[nt] = sB[r * UP + wn + nt * 8 + lc];
+#pragma unroll
+    for (int mt = 0; mt < 8; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) dmma884s(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
+  }
+#pragma unroll
+  for (int mt = 0; mt < 8; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const long i = i0 + wm + mt * 8 + lc, j = j0 + wn + nt * 8 + 2 * lr;
+      const bool iok = i >= r0 && i < N;
+      if (iok && j >= r0 && j < N) A[j * N + i] = acc[mt][nt][0];
+      if (iok && j + 1 >= r0 && j + 1 < N) A[(j + 1) * N + i] = acc[mt][nt][1];
+    }
+}
+
+// Stage 1f: lower band storage Bb[c][d] = A[c][c + d] (d <= B), zero where the bulge will live (B < d < LDB)
+__global__ void __launch_bounds__(256)
+sbr_extract_band_kernel(const double* __restrict__ A, const long N, double* __restrict__ Bb) {
+  const long e = blockIdx.x * 256L + threadIdx.x;
+  if (e >= N * LDB) return;
+  const long c = e / LDB;
+  const int d = (int)(e % LDB);
+  Bb[e] = (d <= B && c + d < N) ? A[c * N + c + d] : 0.0;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Stage 2: band -> tridiagonal by bulge chasing (tools/proto_sbr.py: task()).  Band storage Bb[c*LDB + d] = B[c+d][c].
+//   Sweep i annihilates column i below the sub-diagonal and chases the bulge down the band: task k works on the
+//   diagonal block D = B[J_k, J_k] (two-sided reflector H_k) and on E = B[J_{k+1}, J_k] (E <- E H_k, new reflector
+//   H_{k+1} from its first column, E <- H_{k+1} E), J_k = [i+1+k b, i+(k+1) b].
+//   One warp per sweep (lane = block row, blocks staged in shared memory); chain c runs sweeps c, c+G, ...;
+//   task (i, k) starts when sweep i-1 has finished task k+1: prog[i-1] >= k+2 (progress counters in global memory,
+//   release / acquire).  Reflectors go to V2[i][row] / TAU2[i][k] for the back-transformation.
+// ------------------------------------------------------------------------------------------------
+constexpr int TP = B + 1;   // tile pitch
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// LAPACK dlarfg on a warp: lane l holds x[l] (l < len, zero beyond); returns v (v[0] = 1), tau, beta
+__device__ __forceinline__ void warp_house(const double x, const int lane, double& v, double& tau, double& beta) {
+  const double alpha = __shfl_sync(0xffffffffu, x, 0);
+  const double sigma = warp_sum(lane >= 1 ? x * x : 0.0);
+  if (sigma == 0.0) {
+    tau = 0.0;
+    beta = alpha;
+    v = (lane == 0) ? 1.0 : 0.0;
+  } else {
+    beta = -copysign(sqrt(fma(alpha, alpha, sigma)), alpha);
+    tau = (beta - alpha) / beta;
+    const double scale = 1.0 / (alpha - beta);
+    v = (lane == 0) ? 1.0 : x * scale;
+  }
+}
+
+__global__ void __launch_bounds__(32)
+sbr_chase_kernel(double* __restrict__ Bb, const long N, double* __restrict__ V2, double* __restrict__ TAU2,
+                 const long ntask_max, unsigned* __restrict__ bar) {
+  __shared__ double sD[B][TP], sE[B][TP], sv[B], sq[B];
+  const int lane = threadIdx.x;
+  unsigned* err = bar + 1;
+  unsigned* prog = bar + 2;
+  const long nsweep = N - 2;
+  for (long i = blockIdx.x; i < nsweep; i += gridDim.x) {
+    const int nt = (int)((N - 1 - i + B - 1) / B);
+    double v = 0.0, tau = 0.0;                       // reflector of the current task (lane = row inside J_k)
+    for (int k = 0; k < nt; ++k) {
+      // ---- dependency: sweep i-1 has finished task k+1
+      if (i > 0) {
+        int ok = 1;
+        if (lane == 0) {
+          const unsigned need = (unsigned)(k + 2);
+          unsigned spins = 0;
+          while (ld_acquire_u32(prog + i - 1) < need) {
+            if (++spins > (1u << 22)) {
+              if ((spins & 0xFFFFu) == 0 && ld_acquire_u32(err) != 0) { ok = 0; break; }
+              if (spins > (1u << 27)) { atomicExch(err, 2u); ok = 0; break; }
+            }
+          }
+        }
+        ok = __shfl_sync(0xffffffffu, ok, 0);
+        if (!ok) return;
+      }
+      const long j0 = i + 1 + (long)k * B;
+      const int L = (int)min((long)B, N - j0);
+      const long j1 = j0 + B;
+      const int L2 = (int)max(0L, min((long)B, N - j1));
+      if (k == 0) {                                  // reflector of column i
+        const double x = (lane < L) ? __ldcg(Bb + i * LDB + 1 + lane) : 0.0;
+        double beta;
+        warp_house(x, lane, v, tau, beta);
+        if (lane < L) __stcg(Bb + i * LDB + 1 + lane, lane == 0 ? beta : 0.0);
+      }
+      if (lane >= L) v = 0.0;
+      if (lane < L) V2[i * N + j0 + lane] = v;
+      if (lane == 0) TAU2[i * ntask_max + k] = tau;
+      sv[lane] = v;
+      // ---- D = B[J, J] (symmetric): column c of the lower band is contiguous
+      for (int c = 0; c < B; ++c) {
+        const double val = (c < L && c + lane < L) ? __ldcg(Bb + (j0 + c) * LDB + lane) : 0.0;
+        if (c + lane < B) {
+          sD[c + lane][c] = val;
+          sD[c][c + lane] = val;
+        }
+      }
+      __syncwarp();
+      {
+        double pl = 0.0;                             // p = tau D v
+#pragma unroll 8
+        for (int c = 0; c < B; ++c) pl = fma(sD[lane][c], sv[c], pl);
+        pl *= tau;
+        const double kk = 0.5 * tau * warp_sum(pl * v);
+        const double ql = fma(-kk, v, pl);           // q = p - (tau/2)(p^T v) v
+        sq[lane] = ql;
+        __syncwarp();
+#pragma unroll 8
+        for (int c = 0; c < B; ++c) sD[lane][c] -= fma(v, sq[c], ql * sv[c]);
+      }
+      __syncwarp();
+      for (int c = 0; c < L; ++c)
+        if (c + lane < L) __stcg(Bb + (j0 + c) * LDB + lane, sD[c + lane][c]);
+      double v2 = 0.0, tau2 = 0.0;
+      if (L2 > 0) {
+        // ---- E = B[J_{k+1}, J_k]: column c holds rows j1 .. at offsets B - c + a
+        for (int c = 0; c < B; ++c)
+          sE[lane][c] = (c < L && lane < L2) ? __ldcg(Bb + (j0 + c) * LDB + B - c + lane) : 0.0;
+        __syncwarp();
+        double yl = 0.0;                             // y = E v ; E <- E - tau y v^T
+#pragma unroll 8
+        for (int c = 0; c < B; ++c) yl = fma(sE[lane][c], sv[c], yl);
+        yl *= tau;
+#pragma unroll 8
+        for (int c = 0; c < B; ++c) sE[lane][c] = fma(-yl, sv[c], sE[lane][c]);
+        double beta2;
+        warp_house(lane < L2 ? sE[lane][0] : 0.0, lane, v2, tau2, beta2);
+        if (lane >= L2) v2 = 0.0;
+        sq[lane] = v2;
+        __syncwarp();
+        double zl = 0.0;                             // z_c = v2^T E[:, c] (lane = column c)
+#pragma unroll 8
+        for (int a = 0; a < B; ++a) zl = fma(sq[a], sE[a][lane], zl);
+        zl *= tau2;
+        __syncwarp();
+        sq[lane] = zl;
+        __syncwarp();
+#pragma unroll 8
+        for (int c = 0; c < B; ++c) sE[lane][c] = fma(-v2, sq[c], sE[lane][c]);
+        sE[lane][0] = (lane == 0) ? beta2 : 0.0;     // exactly (beta, 0, ..., 0)
+        __syncwarp();
+        for (int c = 0; c < L; ++c)
+          if (lane < L2) __stcg(Bb + (j0 + c) * LDB + B - c + lane, sE[lane][c]);
+      }
+      v = v2;
+      tau = tau2;
+      // ---- publish progress (the stores above must be visible first)
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) st_release_u32(prog + i, (k + 1 == nt) ? 0x7fffffffu : (unsigned)(k + 1));
+      __syncwarp();
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+sbr_band_to_tridiag_kernel(const double* __restrict__ Bb, const long N, double* __restrict__ d, double* __restrict__ e) {
+  const long c = blockIdx.x * 256L + threadIdx.x;
+  if (c >= N) return;
+  d[c] = Bb[c * LDB];
+  if (c + 1 < N) e[c] = Bb[c * LDB + 1];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Back-transformation: CTA = NV eigenvectors of T held in shared memory (N doubles each).
+//   Q2: sweeps in descending order; the reflectors of one sweep act on disjoint index ranges -> one warp each.
+//   Q1: panels in descending order: z[r0:] -= V (T (V^T z[r0:])).
+// ------------------------------------------------------------------------------------------------
+constexpr int BT_THREADS = 512;
+
+template <int NV>
+__global__ void __launch_bounds__(BT_THREADS, 1)
+sbr_back_kernel(const double* __restrict__ V2, const double* __restrict__ TAU2, const long ntask_max,
+                const double* __restrict__ Vall, const double* __restrict__ Tall, const long npanel, const long N,
+                double* __restrict__ Z, const int nvec) {
+  extern __shared__ double zs[];                     // [NV][N]
+  __shared__ double s_y[NV][B], s_t[NV][B], s_T[B][B + 1], s_part[BT_THREADS / 32][NV][B];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NW = BT_THREADS / 32;
+  const int vec0 = blockIdx.x * NV;
+  for (int q = 0; q < NV; ++q)
+    for (long r = tid; r < N; r += BT_THREADS) zs[q * N + r] = (vec0 + q < nvec) ? Z[(long)(vec0 + q) * N + r] : 0.0;
+  __syncthreads();
+  // ---- Q2
+  for (long i = N - 3; i >= 0; --i) {
+    const int nt = (int)((N - 1 - i + B - 1) / B);
+    const double* vrow = V2 + i * N;
+    const double* trow = TAU2 + i * ntask_max;
+#pragma unroll 4
+    for (int k = warp; k < nt; k += NW) {
+      const long j0 = i + 1 + (long)k * B;
+      const bool in = j0 + lane < N;
+      const double v = in ? __ldg(vrow + j0 + lane) : 0.0;
+      const double tau = __ldg(trow + k);
+#pragma unroll
+      for (int q = 0; q < NV; ++q) {
+        const double zz = in ? zs[q * N + j0 + lane] : 0.0;
+        const double dot = warp_sum(v * zz);
+        if (in) zs[q * N + j0 + lane] = fma(-tau * dot, v, zz);
+      }
+    }
+    __syncthreads();
+  }
+  // ---- Q1
+  for (long kp = npanel - 1; kp >= 0; --kp) {
+    const long c0 = kp * B, r0 = c0 + B;
+    const double* Vk = Vall + c0 * N;
+    for (int e = tid; e < B * B; e += BT_THREADS) s_T[e / B][e % B] = Tall[kp * B * B + e];
+    // y = V^T z: thread strides over rows, partial sums per vector (16 columns at a time) -> warp reduce -> smem
+#pragma unroll 1
+    for (int mh = 0; mh < B; mh += 16) {
+      double acc[NV][16];
+#pragma unroll
+      for (int q = 0; q < NV; ++q)
+#pragma unroll
+        for (int m = 0; m < 16; ++m) acc[q][m] = 0.0;
+      for (long r = r0 + tid; r < N; r += BT_THREADS) {
+        double zz[NV];
+#pragma unroll
+        for (int q = 0; q < NV; ++q) zz[q] = zs[q * N + r];
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+          const double vv = __ldg(Vk + (long)(mh + m) * N + r);
+#pragma unroll
+          for (int q = 0; q < NV; ++q) acc[q][m] = fma(vv, zz[q], acc[q][m]);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < NV; ++q)
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+          const double v = warp_sum(acc[q][m]);
+          if (lane == 0) s_part[warp][q][mh + m] = v;
+        }
+    }
+    __syncthreads();
+    if (tid < NV * B) {
+      const int q = tid / B, m = tid % B;
+      double v = 0.0;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) v += s_part[w][q][m];
+      s_y[q][m] = v;
+    }
+    __syncthreads();
+    if (tid < NV * B) {                              // t = T y (T upper triangular)
+      const int q = tid / B, m = tid % B;
+      double v = 0.0;
+      for (int l = m; l < B; ++l) v = fma(s_T[m][l], s_y[q][l], v);
+      s_t[q][m] = v;
+    }
+    __syncthreads();
+    for (long r = r0 + tid; r < N; r += BT_THREADS) {
+      double dz[NV];
+#pragma unroll
+      for (int q = 0; q < NV; ++q) dz[q] = 0.0;
+#pragma unroll
+      for (int m = 0; m < B; ++m) {
+        const double vv = __ldg(Vk + (long)m * N + r);
+#pragma unroll
+        for (int q = 0; q < NV; ++q) dz[q] = fma(vv, s_t[q][m], dz[q]);
+      }
+#pragma unroll
+      for (int q = 0; q < NV; ++q) zs[q * N + r] -= dz[q];
+    }
+    __syncthreads();
+  }
+  for (int q = 0; q < NV; ++q)
+    if (vec0 + q < nvec)
+      for (long r = tid; r < N; r += BT_THREADS) Z[(long)(vec0 + q) * N + r] = zs[q * N + r];
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// workspace layout
+// ------------------------------------------------------------------------------------------------
+struct SbrWs {
+  double *Vall, *Tall, *W, *X, *Xp, *Zp, *part, *rowj, *Bb, *V2, *TAU2;
+  unsigned* bar;      // [0] barrier counter, [1] error flag, [2..] sweep progress (N)
+  long npanel, ntask_max;
+  int max_split, max_qr_ctas;
+};
+
+static long sbr_npanel(long N) {
+  long k = 0;
+  while (N - (k + 1) * B >= 2) ++k;
+  return k;
+}
+
+static SbrWs sbr_layout(double* ws, long N, size_t* total) {
+  SbrWs w;
+  w.npanel = sbr_npanel(N);
+  w.ntask_max = (N + B - 1) / B + 1;
+  w.max_split = 8;
+  w.max_qr_ctas = (int)((N + QR_THREADS - 1) / QR_THREADS);
+  size_t off = 0;
+  auto take = [&](size_t cnt) {
+    double* q = ws + off;
+    off += (cnt + 31) & ~(size_t)31;
+    return q;
+  };
+  w.Vall = take((size_t)N * N);
+  w.Tall = take((size_t)(w.npanel + 1) * B * B);
+  w.W = take((size_t)B * N);
+  w.X = take((size_t)B * N);
+  w.Xp = take((size_t)w.max_split * B * N);
+  w.Zp = take((size_t)((N + WR - 1) / WR) * B * B);
+  w.part = take((size_t)2 * w.max_qr_ctas * B);
+  w.rowj = take((size_t)2 * B);
+  w.Bb = take((size_t)N * LDB);
+  w.V2 = take((size_t)N * N);
+  w.TAU2 = take((size_t)N * w.ntask_max);
+  w.bar = reinterpret_cast<unsigned*>(take((size_t)(N + 64) / 2 + 64));
+  if (total) *total = off;
+  return w;
+}
+
+size_t sbr_workspace_doubles(long N) {
+  size_t total = 0;
+  sbr_layout(nullptr, N, &total);
+  return total;
+}
+
+static int sbr_stage1(double* A, long N, const SbrWs& w, cudaStream_t st) {
+  static bool configured[64] = {};
+  int dev = 0;
+  PODSDF_CUDA(cudaGetDevice(&dev));
+  if (!configured[dev & 63]) {
+    PODSDF_CUDA(cudaFuncSetAttribute(sbr_symm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XSMEM));
+    PODSDF_CUDA(cudaFuncSetAttribute(sbr_syr2k_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)USMEM));
+    configured[dev & 63] = true;
+  }
+  for (long k = 0; k < w.npanel; ++k) {
+    const int c0 = (int)(k * B);
+    const long r0 = c0 + B, n = N - r0;
+    double* Vk = w.Vall + (long)c0 * N;
+    double* Tk = w.Tall + k * B * B;
+    // 1a: panel QR (cooperative: one grid barrier per column)
+    PODSDF_CUDA(cudaMemsetAsync(w.bar, 0, sizeof(unsigned), st));     // barrier counter (the error flag stays)
+    {
+      const int G = (int)((n + QR_THREADS - 1) / QR_THREADS);
+      double* Aarg = A;
+      long Narg = N;
+      int c0arg = c0;
+      double *Varg = w.Vall, *Targ = Tk, *parg = w.part, *rarg = w.rowj;
+      unsigned* barg = w.bar;
+      void* args[] = {&Aarg, &Narg, &c0arg, &Varg, &Targ, &parg, &rarg, &barg};
+      PODSDF_CUDA(cudaLaunchCooperativeKernel((const void*)sbr_panel_qr_kernel, dim3(G), dim3(QR_THREADS), args, 0, st));
+      count_launch();
+    }
+    // 1b: X = A22 V, split over K so that the grid fills the machine
+    const int row_tiles = (int)((N + XR - 1) / XR - r0 / XR);        // absolute tiles that reach rows >= r0
+    const int total_chunks = (int)((N + XKB - 1) / XKB - r0 / XKB);
+    int nsplit = (2 * 148 + row_tiles - 1) / row_tiles;
+    if (nsplit > w.max_split) nsplit = w.max_split;
+    int cps = (total_chunks + nsplit - 1) / nsplit;
+    cps = ((cps + 7) / 8) * 8;                               // whole 128-column blocks per split
+    nsplit = (total_chunks + cps - 1) / cps;
+    sbr_symm_kernel<<<dim3(row_tiles, nsplit), 256, XSMEM, st>>>(A, N, r0, Vk, w.Xp, cps);
+    // 1c / 1d: W
+    const int wct = (int)((n + WR - 1) / WR);
+    sbr_w1_kernel<<<wct, 256, 0, st>>>(w.Xp, nsplit, Vk, N, r0, w.X, w.Zp);
+    sbr_w2_kernel<<<(int)((n + WR2 - 1) / WR2), 256, 0, st>>>(w.X, Vk, Tk, w.Zp, wct, N, r0, w.W);
+    // 1e: rank-2b update of the lower tiles
+    const int side = (int)((N + UT - 1) / UT - r0 / UT);
+    sbr_syr2k_kernel<<<side * (side + 1) / 2, 256, USMEM, st>>>(A, N, r0, Vk, w.W);
+    count_launch(4);
+  }
+  sbr_extract_band_kernel<<<ceil_div(N * LDB, 256L), 256, 0, st>>>(A, N, w.Bb);
+  count_launch();
+  PODSDF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+
+static int sbr_stage2(long N, const SbrWs& w, double* d, double* e, cudaStream_t st) {
+  // progress counters: one per sweep, zeroed; [0] barrier, [1] error flag keep their values
+  PODSDF_CUDA(cudaMemsetAsync(w.bar + 2, 0, sizeof(unsigned) * (size_t)(N + 2), st));
+  const long nsweep = N - 2;
+  if (nsweep > 0) {
+    int dev = 0, sms = 148, per_sm = 1;
+    PODSDF_CUDA(cudaGetDevice(&dev));
+    PODSDF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    PODSDF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sbr_chase_kernel, 32, 0));
+    long G = (long)sms * (per_sm < 4 ? per_sm : 4);          // all chains co-resident (cooperative launch checks it)
+    const long useful = (N + 2 * B - 1) / (2 * B) + 8;       // sweeps that can be in flight at once
+    if (G > useful) G = useful;
+    if (G > nsweep) G = nsweep;
+    double* Bb = w.Bb;
+    long Narg = N, ntm = w.ntask_max;
+    double *V2 = w.V2, *TAU2 = w.TAU2;
+    unsigned* bar = w.bar;
+    void* args[] = {&Bb, &Narg, &V2, &TAU2, &ntm, &bar};
+    PODSDF_CUDA(cudaLaunchCooperativeKernel((const void*)sbr_chase_kernel, dim3((unsigned)G), dim3(32), args, 0, st));
+    count_launch();
+  }
+  sbr_band_to_tridiag_kernel<<<ceil_div(N, 256L), 256, 0, st>>>(w.Bb, N, d, e);
+  count_launch();
+  PODSDF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int sbr_tridiagonalize(double* A, long N, double* d, double* e, double* ws, cudaStream_t st, float* timings) {
+  if (N < 3) return fail(PODSDF_ERR_INVALID, "sbr_tridiagonalize needs N >= 3");
+  SbrWs w = sbr_layout(ws, N, nullptr);
+  PODSDF_CUDA(cudaMemsetAsync(w.bar, 0, 2 * sizeof(unsigned), st));
+  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+  if (timings) {
+    for (auto& x : ev) PODSDF_CUDA(cudaEventCreate(&x));
+    cudaEventRecord(ev[0], st);
+  }
+  PODSDF_TRY(sbr_stage1(A, N, w, st));
+  if (timings) cudaEventRecord(ev[1], st);
+  PODSDF_TRY(sbr_stage2(N, w, d, e, st));
+  if (timings) cudaEventRecord(ev[2], st);
+  unsigned herr = 0;
+  PODSDF_CUDA(cudaMemcpyAsync(&herr, w.bar + 1, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+  PODSDF_CUDA(cudaStreamSynchronize(st));
+  if (timings) {
+    cudaEventElapsedTime(&timings[0], ev[0], ev[1]);
+    cudaEventElapsedTime(&timings[1], ev[1], ev[2]);
+    for (auto& x : ev) cudaEventDestroy(x);
+  }
+  if (herr != 0) return fail(PODSDF_ERR_CUDA, "tridiagonalisation: a grid-wide wait timed out (code " + std::to_string(herr) + ")");
+  return 0;
+}
+
+int sbr_stage1_only(double* A, long N, double* ws, double* band, cudaStream_t st) {
+  SbrWs w = sbr_layout(ws, N, nullptr);
+  PODSDF_CUDA(cudaMemsetAsync(w.bar, 0, 2 * sizeof(unsigned), st));
+  PODSDF_TRY(sbr_stage1(A, N, w, st));
+  PODSDF_CUDA(cudaMemcpyAsync(band, w.Bb, sizeof(double) * (size_t)N * LDB, cudaMemcpyDeviceToDevice, st));
+  unsigned herr = 0;
+  PODSDF_CUDA(cudaMemcpyAsync(&herr, w.bar + 1, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+  PODSDF_CUDA(cudaStreamSynchronize(st));
+  if (herr != 0) return fail(PODSDF_ERR_CUDA, "band reduction: a grid barrier timed out");
+  return 0;
+}
+
+int sbr_back_transform(const double* ws, long N, double* Z, int nvec, cudaStream_t st) {
+  SbrWs w = sbr_layout(const_cast<double*>(ws), N, nullptr);
+  const size_t one = sizeof(double) * (size_t)N;
+  int dev = 0, max_smem = 0;
+  PODSDF_CUDA(cudaGetDevice(&dev));
+  PODSDF_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  const size_t fixed = 48 * 1024;                            // static shared memory of the kernel, generous
+  if (2 * one + fixed <= (size_t)max_smem) {
+    auto k = sbr_back_kernel<2>;
+    PODSDF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * one)));
+    k<<<(nvec + 1) / 2, BT_THREADS, 2 * one, st>>>(w.V2, w.TAU2, w.ntask_max, w.Vall, w.Tall, w.npanel, N, Z, nvec);
+  } else if (one + fixed <= (size_t)max_smem) {
+    auto k = sbr_back_kernel<1>;
+    PODSDF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)one));
+    k<<<nvec, BT_THREADS, one, st>>>(w.V2, w.TAU2, w.ntask_max, w.Vall, w.Tall, w.npanel, N, Z, nvec);
+  } else {
+    return fail(PODSDF_ERR_UNSUPPORTED, "back-transformation: one eigenvector does not fit shared memory");
+  }
+  count_launch();
+  PODSDF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace podsdf
