@@ -8,9 +8,9 @@ their CPU restatement (Salmon et al. 2011, Random123 constants).
 Layout (shared with pods-digital-filter_b200/csrc/philox.cuh):
   key     = (seed & 0xffffffff, seed >> 32);  pair = idx // 2, half = idx % 2, idx = p*Kp + q in the padded
             plane (Jp x Kp), s = global slab index, comp in 0..2
-  kind "u32" (PODSDF_RNG_U32, the default): one call = 2 points x 2 slabs
-    counter = (pair & 0xffffffff, pair >> 32, sp & 0xffffffff, comp + 4*(sp >> 32)),  sp = s // 2
-    word r[2*(s % 2) + half];  v = 1 + (r + 1/2) 2^-32 built bitwise in the mantissa of [1, 2);
+  kind "u32" (PODSDF_RNG_U32, the default): one call = ONE point x FOUR consecutive slabs
+    counter = (idx & 0xffffffff, idx >> 32, sq & 0xffffffff, comp + 4*(sq >> 32)),  sq = s // 4
+    word r[s % 4];  v = 1 + (r + 1/2) 2^-32 built bitwise in the mantissa of [1, 2);
     x = (v - 1.5) * (2 sqrt(3))                    (exact subtraction, one rounding)
   kind "u53" (PODSDF_RNG_U53, round 1's stream): one call = 2 points of one slab
     counter = (pair & 0xffffffff, pair >> 32, s & 0xffffffff, comp + 4*(s >> 32))
@@ -83,23 +83,18 @@ def slabs(seed, s0, n, Jp, Kp, kind="u32"):
 
 def _slabs_u32(seed, s0, n, Jp, Kp):
     npts = Jp * Kp
-    npair = (npts + 1) // 2
-    pair = np.arange(npair, dtype=np.uint64)
+    idx = np.arange(npts, dtype=np.uint64)
     out = np.empty((n, 3, Jp, Kp))
     k0, k1 = seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF
     cache = {}
     for i in range(n):
         s = s0 + i
-        sp, sh = s >> 1, s & 1
+        sq, w = s >> 2, s & 3
         for comp in range(3):
-            if (sp, comp) not in cache:
-                cache[(sp, comp)] = philox4x32_10(pair & MASK, pair >> np.uint64(32),
-                                                  np.full_like(pair, sp & 0xFFFFFFFF),
-                                                  np.full_like(pair, comp + 4 * (sp >> 32)), k0, k1)
-            r = cache[(sp, comp)]
-            flat = np.empty(2 * npair)
-            flat[0::2] = u32_to_uniform(r[2 * sh])
-            flat[1::2] = u32_to_uniform(r[2 * sh + 1])
-            out[i, comp] = flat[:npts].reshape(Jp, Kp)
-        cache = {k: v for k, v in cache.items() if k[0] >= sp}
+            if (sq, comp) not in cache:
+                cache[(sq, comp)] = philox4x32_10(idx & MASK, idx >> np.uint64(32),
+                                                  np.full_like(idx, sq & 0xFFFFFFFF),
+                                                  np.full_like(idx, comp + 4 * (sq >> 32)), k0, k1)
+            out[i, comp] = u32_to_uniform(cache[(sq, comp)][w]).reshape(Jp, Kp)
+        cache = {k: v for k, v in cache.items() if k[0] >= sq}
     return out

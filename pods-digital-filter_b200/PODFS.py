@@ -230,7 +230,9 @@ def fourier_coefficients(i_d):
     time = np.linspace(0, (num_snapshots - 1) * dt * 1, num_snapshots)
     period = time[-1] + (time[1] - time[0])
 
-    c128 = _capi.dft_modes(i_d.temporal_modes, num_modes, device=DEVICE)   # (ns, nm), k = n - ns//2
+    c128 = getattr(i_d, "c128", None)              # the device pipeline has already transformed the kept modes
+    if c128 is None or c128.shape != (num_fcs, num_modes):
+        c128 = _capi.dft_modes(i_d.temporal_modes, num_modes, device=DEVICE)   # (ns, nm), k = n - ns//2
     c, c_ind, c_count = select_fourier(c128, energy_target)
     for i in range(num_modes):
         print("The number of fourier coeffients used for mode ", i + 1, " is ", c_count[i])

@@ -23,12 +23,9 @@ __global__ void __launch_bounds__(256) df_random_slabs_kernel(double* __restrict
   const int c = blockIdx.y;
   const long s = blockIdx.z;
   double a, b;
-  if (KIND == kRngU32) {
-    uint32_t r[4];
-    const uint64_t sg = (uint64_t)(s0 + s);
-    philox_quad(keys, (uint64_t)pair, sg >> 1, c, r);
-    a = philox_u32_to_uniform((sg & 1) ? r[2] : r[0]);
-    b = philox_u32_to_uniform((sg & 1) ? r[3] : r[1]);
+  if (KIND == kRngU32) {       // (the time filters take four slabs per call; this materialiser is not a hot path)
+    a = philox_value<kRngU32>(keys, (uint64_t)(2 * pair), (uint64_t)(s0 + s), c);
+    b = philox_value<kRngU32>(keys, (uint64_t)(2 * pair + 1), (uint64_t)(s0 + s), c);
   } else {
     philox_pair(keys, (uint64_t)pair, (uint64_t)(s0 + s), c, a, b);
   }
@@ -59,9 +56,8 @@ int launch_df_random_slabs(const DfGeom& g, uint64_t seed, int kind, long s0, lo
 // T1 is written either in the canonical plane layout [p][q] (panel.PB == 0) or in the row-panel layout
 // [pb][q][16] the tuned plane kernel bulk-copies from (PanelGeom); thread L owns the two points (p, q), (p, q+1)
 // either way (one Philox call / one 16-byte read), and a warp's writes are whole 128-byte lines in both.
-// Steps are taken in PAIRS that start on an even global slab: in the U32 stream ONE Philox call then yields the
-// four new numbers of the pair (2 points x 2 slabs), issued before the 4 NT DFMA of the two steps so that the
-// integer pipe (Philox) and the FP64 pipe (filter) overlap inside one instruction stream.
+// Steps are taken in pairs (two Philox calls / four loads issued ahead of the 4 NT DFMA of the two steps).
+// Serves the U53 stream and injected slabs in the canonical layout; the U32 stream runs in df_time_ring8_kernel.
 template <int NT, int SRC>
 __global__ void __launch_bounds__(256, (NT <= 21 ? 2 : 1))
 df_time_tuned_kernel(const double* __restrict__ X, double* __restrict__ T1, const Taps bx, const DfGeom g,
@@ -105,21 +101,13 @@ df_time_tuned_kernel(const double* __restrict__ X, double* __restrict__ T1, cons
     }
     return;
   }
-  // first step of the pair loop: one step early when the chunk starts on an odd global slab (NT - 1 is even, so
-  // the slab entering at step tt has the parity of s_base + tt); that extra step's output is not written
-  const int E = (SRC == kSrcU32) ? t0 - (int)((s_base + t0) & 1) : t0;
+  static_assert(SRC != kSrcU32, "the U32 stream runs in df_time_ring8_kernel");
+  const int E = t0;
 
   double w0[NT], w1[NT];
   // slabs s and s + 1 of this thread's two points: (a0, b0) and (a1, b1)
   auto load2 = [&](int s, double& a0, double& b0, double& a1, double& b1) {
-    if (SRC == kSrcU32) {      // s_base + s is even: both slabs come from one call
-      uint32_t r[4];
-      philox_quad(keys, (uint64_t)(ridx >> 1), (uint64_t)((s_base + s) >> 1), c, r);
-      a0 = philox_u32_to_uniform(r[0]);
-      b0 = philox_u32_to_uniform(r[1]);
-      a1 = philox_u32_to_uniform(r[2]);
-      b1 = philox_u32_to_uniform(r[3]);
-    } else if (SRC == kSrcU53) {
+    if (SRC == kSrcU53) {
       philox_pair(keys, (uint64_t)(ridx >> 1), (uint64_t)(s_base + s), c, a0, b0);
       philox_pair(keys, (uint64_t)(ridx >> 1), (uint64_t)(s_base + s + 1), c, a1, b1);
     } else {
@@ -197,28 +185,28 @@ df_time_tuned_kernel(const double* __restrict__ X, double* __restrict__ T1, cons
 }
 
 // ------------------------------------------------------------------------------------------------
-// K-time, ring-of-4: ONE point per thread, steps in groups of FOUR.  The U32Q stream gives the four numbers
-// of (point, slabs 4g .. 4g+3) in one Philox call, so a group costs one call + 4 NT DFMA; the window is a ring
-// of NT + 3 registers (exactly the slabs a group touches), its pattern repeats after (NT + 3) / 4 groups, and
-// the unrolled body is NT + 3 steps of ONE point -- a quarter of the instructions of the pair kernel above,
-// small enough for the instruction cache.  Lanes <-> consecutive panel entries: 256-byte stores per warp.
+// K-time, U32 stream: ONE point per thread, steps in blocks of EIGHT.  A block costs two Philox calls (the U32
+// stream yields four consecutive slabs of one point per call) + 8 NT DFMA in eight independent accumulator chains,
+// written like the z-pass of the plane kernel: every window value is read once and feeds up to eight outputs.
+// The window is a ring of R = 8 ceil((NT+7)/8) registers (the slabs one block touches); its pattern repeats after
+// R/8 blocks, so the unrolled body is R steps of one point (about a fifth of the pair kernel's code, which ran
+// 33 % of its cycles waiting for instruction fetches -- profiles/r02_ktime_ncu.md).  Lanes <-> consecutive panel
+// entries: 256-byte stores per warp and plane.
 // ------------------------------------------------------------------------------------------------
-#ifndef PODSDF_R4_MINB
-#define PODSDF_R4_MINB 3
+#ifndef PODSDF_R8_MINB
+#define PODSDF_R8_MINB 2
 #endif
-template <int NT, int SRC>
-__global__ void __launch_bounds__(256, PODSDF_R4_MINB)
-df_time_ring4_kernel(const double* __restrict__ X, double* __restrict__ T1, const Taps bx, const DfGeom g,
-                     const PanelGeom panel, const long npoint, const int nsteps, const int tchunk,
-                     const PhiloxKeys keys, const long s_base) {
-  static_assert(NT % 4 == 1, "the ring of NT + 3 slots must hold whole groups of four");
-  constexpr int R = NT + 3;
+template <int NT>
+__global__ void __launch_bounds__(256, PODSDF_R8_MINB)
+df_time_ring8_kernel(double* __restrict__ T1, const Taps bx, const DfGeom g, const PanelGeom panel, const long npoint,
+                     const int nsteps, const int tchunk, const PhiloxKeys keys, const long s_base) {
+  static_assert(NT % 4 == 1, "whole Philox quads in the NT - 1 warm-up slabs");
+  constexpr int R = ((NT + 7 + 7) / 8) * 8;
   const long L = blockIdx.x * 256L + threadIdx.x;
   if (L >= npoint) return;
   const int c = blockIdx.y;
   const int t0 = blockIdx.z * tchunk;
   const int t1 = min(t0 + tchunk, nsteps);
-  const long Np = g.Np;
   long ridx, wstride;
   bool valid = true;
   if (panel.PB > 0) {          // panel layout: L = (pb * Qpad + q) * 16 + r
@@ -231,57 +219,57 @@ df_time_ring4_kernel(const double* __restrict__ X, double* __restrict__ T1, cons
     wstride = panel.comp_stride;
   } else {
     ridx = L;
-    wstride = Np;
+    wstride = g.Np;
   }
-  double* out = T1 + (long)c * wstride + L;
   const long ostride = 3 * wstride;
   if (!valid) {
-    for (int t = t0; t < t1; ++t) out[(long)t * ostride] = 0.0;
+    double* o = T1 + (long)c * wstride + L + (long)t0 * ostride;
+    for (int t = t0; t < t1; ++t, o += ostride) *o = 0.0;
     return;
   }
-  const int last_slab = nsteps + NT - 2;
-  // groups start on a global slab that is a multiple of 4 (NT - 1 is one, so the slab entering at step tt is
-  // congruent to s_base + tt); up to three extra leading steps are computed and not written
-  const int E = (SRC != kSrcInjected) ? t0 - (int)((s_base + t0) & 3) : t0;
+  // blocks start on a global slab that is a multiple of 4 (NT - 1 is one, so the slab entering at step tt is
+  // congruent to s_base + tt): up to three extra leading steps are computed and not written
+  const int E = t0 - (int)((s_base + t0) & 3);
+  const uint64_t q_base = (uint64_t)((s_base + E) >> 2);       // quad index of slab E
+  double* out = T1 + (long)c * wstride + L + (long)E * ostride; // walks one plane per step
 
   double w[R];
-  auto load4 = [&](int s, double& a0, double& a1, double& a2, double& a3) {
-    if (SRC != kSrcInjected) {
-      uint32_t r[4];
-      philox_quad(keys, (uint64_t)ridx, (uint64_t)((s_base + s) >> 2), c, r);
-      a0 = philox_u32_to_uniform(r[0]);
-      a1 = philox_u32_to_uniform(r[1]);
-      a2 = philox_u32_to_uniform(r[2]);
-      a3 = philox_u32_to_uniform(r[3]);
-    } else {
-      const double* p = X + (long)c * Np + ridx;
-      a0 = __ldcs(p + (long)min(s, last_slab) * 3 * Np);
-      a1 = __ldcs(p + (long)min(s + 1, last_slab) * 3 * Np);
-      a2 = __ldcs(p + (long)min(s + 2, last_slab) * 3 * Np);
-      a3 = __ldcs(p + (long)min(s + 3, last_slab) * 3 * Np);
-    }
+  auto load4 = [&](uint64_t quad, double& a0, double& a1, double& a2, double& a3) {
+    uint32_t r[4];
+    philox_quad(keys, (uint64_t)ridx, quad, c, r);
+    a0 = philox_u32_to_uniform(r[0]);
+    a1 = philox_u32_to_uniform(r[1]);
+    a2 = philox_u32_to_uniform(r[2]);
+    a3 = philox_u32_to_uniform(r[3]);
   };
 #pragma unroll
-  for (int i = 0; i < NT - 1; i += 4) load4(E + i, w[i], w[i + 1], w[i + 2], w[i + 3]);
+  for (int i = 0; i < NT - 1; i += 4) load4(q_base + i / 4, w[i], w[i + 1], w[i + 2], w[i + 3]);
+  uint64_t quad = q_base + (NT - 1) / 4;                       // next quad to draw
 
   for (int t = E; t < t1; t += R) {
 #pragma unroll
-    for (int gq = 0; gq < R; gq += 4) {
-      const int tt = t + gq;
-      if (tt < t1) {                             // CTA-uniform
-        load4(tt + NT - 1, w[(gq + NT - 1) % R], w[(gq + NT) % R], w[(gq + NT + 1) % R], w[(gq + NT + 2) % R]);
+    for (int bq = 0; bq < R; bq += 8) {
+      const int tt = t + bq;
+      if (tt < t1) {                                           // CTA-uniform
+        load4(quad, w[(bq + NT - 1) % R], w[(bq + NT) % R], w[(bq + NT + 1) % R], w[(bq + NT + 2) % R]);
+        load4(quad + 1, w[(bq + NT + 3) % R], w[(bq + NT + 4) % R], w[(bq + NT + 5) % R], w[(bq + NT + 6) % R]);
+        quad += 2;
+        // out[tt + o] = sum_m bx[m] X[tt + o + NT-1-m]  (true convolution: scipy.signal.convolve flips the taps)
+        double acc[8];
 #pragma unroll
-        for (int h = 0; h < 4; ++h) {
-          // true convolution (scipy.signal.convolve flips the taps): tap m meets slab tt + h + NT-1-m
-          double pa[4];
+        for (int i = 0; i < NT + 7; ++i) {
+          const double v = w[(bq + i) % R];
 #pragma unroll
-          for (int m = 0; m < NT; ++m) {
-            const int idx = (gq + h + NT - 1 - m) % R;
-            if (m < 4) pa[m] = bx.b[m] * w[idx];
-            else pa[m % 4] = fma(bx.b[m], w[idx], pa[m % 4]);
+          for (int o = 0; o < 8; ++o) {
+            const int m = i - o;
+            if (m == 0) acc[o] = bx.b[NT - 1] * v;
+            else if (m > 0 && m < NT) acc[o] = fma(bx.b[NT - 1 - m], v, acc[o]);
           }
-          const int ts = tt + h;
-          if (ts >= t0 && ts < t1) out[(long)ts * ostride] = (pa[0] + pa[1]) + (pa[2] + pa[3]);
+        }
+#pragma unroll
+        for (int o = 0; o < 8; ++o) {
+          if (tt + o >= t0 && tt + o < t1) *out = acc[o];
+          out += ostride;
         }
       }
     }
@@ -289,22 +277,18 @@ df_time_ring4_kernel(const double* __restrict__ X, double* __restrict__ T1, cons
 }
 
 template <int NT>
-static void launch_time_ring4(const DfGeom& g, const PanelGeom& panel, const Taps& bx, const double* X, double* T1,
-                              int nsteps, int src, uint64_t seed, long s_base, cudaStream_t st) {
-  constexpr int R = NT + 3;
+static void launch_time_ring8(const DfGeom& g, const PanelGeom& panel, const Taps& bx, double* T1, int nsteps,
+                              uint64_t seed, long s_base, cudaStream_t st) {
+  constexpr int R = ((NT + 7 + 7) / 8) * 8;
   const long npoint = panel.PB > 0 ? (long)panel.PB * panel.Qpad * 16 : g.Np;
   int nchunk = 1;
   const long ctas_per_chunk = 3L * ceil_div(npoint, 256);
-  while (nchunk < 64 && ctas_per_chunk * nchunk < 148L * 3 * 8 && nsteps / (nchunk * 2) >= 8 * NT) nchunk *= 2;
+  while (nchunk < 64 && ctas_per_chunk * nchunk < 148L * 2 * 8 && nsteps / (nchunk * 2) >= 8 * NT) nchunk *= 2;
   int tchunk = ceil_div(nsteps, nchunk);
-  tchunk = ceil_div(tchunk, R) * R;              // whole unrolled blocks; a multiple of 4
+  tchunk = ceil_div(tchunk, R) * R;              // whole unrolled blocks; a multiple of 8
   nchunk = ceil_div(nsteps, tchunk);
   dim3 grid(ceil_div(npoint, 256), 3, nchunk);
-  const PhiloxKeys keys = philox_keys(seed);
-  if (src != kSrcInjected)
-    df_time_ring4_kernel<NT, kSrcU32><<<grid, 256, 0, st>>>(X, T1, bx, g, panel, npoint, nsteps, tchunk, keys, s_base);
-  else
-    df_time_ring4_kernel<NT, kSrcInjected><<<grid, 256, 0, st>>>(X, T1, bx, g, panel, npoint, nsteps, tchunk, keys, s_base);
+  df_time_ring8_kernel<NT><<<grid, 256, 0, st>>>(T1, bx, g, panel, npoint, nsteps, tchunk, philox_keys(seed), s_base);
   count_launch();
 }
 
@@ -411,9 +395,11 @@ static void launch_time_tuned(const DfGeom& g, const PanelGeom& panel, const Tap
   nchunk = ceil_div(nsteps, tchunk);
   dim3 grid(ceil_div(nthread, 256), 3, nchunk);
   const PhiloxKeys keys = philox_keys(seed);
-  if (src == kSrcU32)
-    df_time_tuned_kernel<NT, kSrcU32><<<grid, 256, 0, st>>>(X, T1, bx, g, panel, nthread, nsteps, tchunk, keys, s_base);
-  else if (src == kSrcU53)
+  if (src == kSrcU32) {
+    launch_time_ring8<NT>(g, panel, bx, T1, nsteps, seed, s_base, st);
+    return;
+  }
+  if (src == kSrcU53)
     df_time_tuned_kernel<NT, kSrcU53><<<grid, 256, 0, st>>>(X, T1, bx, g, panel, nthread, nsteps, tchunk, keys, s_base);
   else
     df_time_tuned_kernel<NT, kSrcInjected><<<grid, 256, 0, st>>>(X, T1, bx, g, panel, nthread, nsteps, tchunk, keys, s_base);
@@ -518,19 +504,33 @@ df_time_mma_kernel(const double* __restrict__ X, double* __restrict__ T1, const 
       const long pair = ((long)p * g.Kp + q0) >> 1;
       const int smine = base + k + 4 * co;     // even column computes slab S1, odd column S2
       double x0, x1;
-      if (SRC == kSrcU32) {                    // the call covers slabs (2 sp, 2 sp + 1): take this lane's slab
-        const long sg = s_base + smine;
-        uint32_t r[4];
-        philox_quad(keys, (uint64_t)pair, (uint64_t)(sg >> 1), c, r);
-        x0 = philox_u32_to_uniform((sg & 1) ? r[2] : r[0]);
-        x1 = philox_u32_to_uniform((sg & 1) ? r[3] : r[1]);
+      if (SRC == kSrcU32) {                    // one call = 4 slabs of ONE point: this lane's point, its slab
+        x0 = x1 = 0.0;
       } else {
         philox_pair(keys, (uint64_t)pair, (uint64_t)(s_base + smine), c, x0, x1);
       }
-      const double keep = co ? x1 : x0, send = co ? x0 : x1;
-      const double recv = __shfl_xor_sync(0xffffffffu, send, 4);
-      v1 = co ? recv : keep;
-      v2 = co ? keep : recv;
+      if (SRC == kSrcU32) {
+        // lanes k = 0..3 of one point need word k of quads (base/4) and (base/4 + 1): even k computes the first,
+        // odd k the second, and neighbours swap the word the other one needs (aligned streams); otherwise two calls
+        const long sg = s_base + base;
+        const uint64_t idx = (uint64_t)((long)p * g.Kp + q0 + co);
+        if ((sg & 3) == 0) {
+          uint32_t r[4];
+          philox_quad(keys, idx, (uint64_t)((sg >> 2) + (k & 1)), c, r);
+          const uint32_t mine = philox_pick(r, k), give = philox_pick(r, k ^ 1);
+          const uint32_t got = __shfl_xor_sync(0xffffffffu, give, 1);
+          v1 = philox_u32_to_uniform((k & 1) ? got : mine);
+          v2 = philox_u32_to_uniform((k & 1) ? mine : got);
+        } else {
+          v1 = philox_value<kRngU32>(keys, idx, (uint64_t)(sg + k), c);
+          v2 = philox_value<kRngU32>(keys, idx, (uint64_t)(sg + 4 + k), c);
+        }
+      } else {
+        const double keep = co ? x1 : x0, send = co ? x0 : x1;
+        const double recv = __shfl_xor_sync(0xffffffffu, send, 4);
+        v1 = co ? recv : keep;
+        v2 = co ? keep : recv;
+      }
       if (!ok) v1 = v2 = 0.0;
     } else {
       const int s1 = min(max(base + k, 0), last_slab), s2 = min(max(base + 4 + k, 0), last_slab);
@@ -617,14 +617,6 @@ int launch_df_time(const DfGeom& g, const PanelGeom& panel, const Taps& bx, cons
   if (nsteps <= 0) return 0;
   const int nt = 2 * g.nfx + 1;
   if (tuned) {
-    if (g_time_variant == 3) {                  // EXPERIMENT: ring-of-4 kernel (its own stream layout)
-      switch (nt) {
-#define F(N) case N: launch_time_ring4<N>(g, panel, bx, X, T1, nsteps, src, seed, s_base, st); PODSDF_CUDA(cudaGetLastError()); return 0;
-        F(9) F(13) F(17) F(21) F(25) F(33)
-#undef F
-        default: break;
-      }
-    }
     if (panel.PB > 0 && g_time_variant != 1) {
 #define F(N) case N: launch_time_mma<N>(g, panel, bx, X, T1, nsteps, src, seed, s_base, st); PODSDF_CUDA(cudaGetLastError()); return 0;
       if (g_time_variant == 2 || src == kSrcInjected) {   // injected slabs: the tensor-path kernel's 8-byte loads pattern is faster

@@ -5,16 +5,17 @@
 //
 //   key = (seed lo, seed hi);  idx = p*Kp + q in the padded plane, pair = idx/2, half = idx & 1
 //
-//   kind PODSDF_RNG_U32 (default): one call serves two points x two slabs, 32 random bits per number
-//     counter = (pair lo, pair hi, sp lo, comp + 4 * sp hi),  sp = s/2, sh = s & 1 (s = slab)
-//     word r[2*sh + half];  v = 1 + (r + 1/2) 2^-32  (bits dropped into the mantissa of [1, 2));
+//   kind PODSDF_RNG_U32 (default): one call serves ONE point x FOUR consecutive slabs, 32 random bits per number
+//     counter = (idx lo, idx hi, sq lo, comp + 4 * sq hi),  sq = s/4 (s = slab);  word r[s & 3]
+//     v = 1 + (r + 1/2) 2^-32  (bits dropped into the mantissa of [1, 2));
 //     x = (v - 3/2) * (2 sqrt3)      -- v - 3/2 is exact, one rounding, symmetric about 0
 //   kind PODSDF_RNG_U53 (round 1's stream, numpy's 53-bit uniform()): one call serves two points of one slab
 //     counter = (pair lo, pair hi, s lo, comp + 4 * s hi);  (r0, r1) -> half 0, (r2, r3) -> half 1
 //     u = ((a >> 5) * 2^26 + (b >> 6)) * 2^-53 ;  x = -sqrt3 + (2 sqrt3) * u
 //
 // U32 halves the wide integer multiplies per random number (5 instead of 10 IMAD.WIDE) and needs two FP64
-// operations per number instead of five; the integer pipe was the limiter of the time filter in round 1.
+// operations per number instead of five.  Four slabs of one point per call is what a time filter wants: a thread
+// owns one point and consumes its stream four steps at a time (df_time_ring8_kernel).
 #pragma once
 #include <cstdint>
 
@@ -85,9 +86,12 @@ __device__ __forceinline__ double philox_u32_to_uniform(uint32_t r) {
   return __dmul_rn(__dadd_rn(v, -1.5), 1.7320508075688772 + 1.7320508075688772);
 }
 
-// the four words of (pair, slab pair sp, comp): r[2*sh + half]
-__device__ __forceinline__ void philox_quad(const PhiloxKeys& k, uint64_t pair, uint64_t sp, int comp, uint32_t (&r)[4]) {
-  philox4x32_10((uint32_t)pair, (uint32_t)(pair >> 32), (uint32_t)sp, (uint32_t)comp + 4u * (uint32_t)(sp >> 32), k, r);
+// the four words of (point idx, slab quad sq, comp): r[s & 3] belongs to slab s = 4 sq + (s & 3)
+__device__ __forceinline__ void philox_quad(const PhiloxKeys& k, uint64_t idx, uint64_t sq, int comp, uint32_t (&r)[4]) {
+  philox4x32_10((uint32_t)idx, (uint32_t)(idx >> 32), (uint32_t)sq, (uint32_t)comp + 4u * (uint32_t)(sq >> 32), k, r);
+}
+__device__ __forceinline__ uint32_t philox_pick(const uint32_t (&r)[4], int w) {
+  return w == 0 ? r[0] : (w == 1 ? r[1] : (w == 2 ? r[2] : r[3]));
 }
 
 // one random number of either kind (generic paths: wide filters, materialised slabs)
@@ -95,9 +99,8 @@ template <int KIND>
 __device__ __forceinline__ double philox_value(const PhiloxKeys& k, uint64_t idx, uint64_t s, int comp) {
   if (KIND == kRngU32) {
     uint32_t r[4];
-    philox_quad(k, idx >> 1, s >> 1, comp, r);
-    const int w = 2 * (int)(s & 1) + (int)(idx & 1);
-    return philox_u32_to_uniform(w == 0 ? r[0] : (w == 1 ? r[1] : (w == 2 ? r[2] : r[3])));
+    philox_quad(k, idx, s >> 2, comp, r);
+    return philox_u32_to_uniform(philox_pick(r, (int)(s & 3)));
   } else {
     double a, b;
     philox_pair(k, idx >> 1, s, comp, a, b);

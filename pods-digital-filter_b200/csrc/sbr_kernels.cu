@@ -96,6 +96,7 @@ sbr_panel_qr_kernel(double* __restrict__ A, const long N, const int c0, double* 
                     unsigned* __restrict__ bar) {
   __shared__ double s_red[QR_THREADS / 32][B];
   __shared__ double s_S[B], s_R[B], s_T[B][B + 1], s_tau[B];
+  __shared__ double s_part[QR_THREADS];         // the partials of up to QR_THREADS / B CTAs at a time
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int G = gridDim.x, cta = blockIdx.x;
   const long r0 = c0 + B;
@@ -145,11 +146,25 @@ sbr_panel_qr_kernel(double* __restrict__ A, const long N, const int c0, double* 
     }
     if (!grid_barrier(counter, err, ++phase)) return;
     // ---- phase B: everyone sums the partials in the same order
-    if (tid < B) {
-      double v = 0.0;
-      for (int g2 = 0; g2 < G; ++g2) v += __ldcg(part + ((long)(j & 1) * G + g2) * B + tid);   // L2: other CTAs' data
-      s_S[tid] = v;
-      s_R[tid] = (j < B) ? __ldcg(rowj + (j & 1) * B + tid) : 0.0;
+    {
+      // all threads fetch (L2: other CTAs' data) -- one round trip per QR_THREADS / B CTAs -- then B threads add
+      // them up in CTA order, the same order everywhere
+      double rj = 0.0, v = 0.0;
+      if (tid < B && j < B) rj = __ldcg(rowj + (j & 1) * B + tid);
+      for (int g0 = 0; g0 < G; g0 += QR_THREADS / B) {
+        const int g2 = g0 + tid / B;
+        s_part[tid] = (g2 < G) ? __ldcg(part + ((long)(j & 1) * G + g2) * B + (tid % B)) : 0.0;
+        __syncthreads();
+        if (tid < B) {
+          const int cnt = min(QR_THREADS / B, G - g0);
+          for (int q = 0; q < cnt; ++q) v += s_part[q * B + tid];
+        }
+        __syncthreads();
+      }
+      if (tid < B) {
+        s_S[tid] = v;
+        s_R[tid] = rj;
+      }
     }
     __syncthreads();
     if (cta == 0 && j >= 1 && tid < j - 1) {            // T[:j-1, j-1] = -tau_{j-1} T[:j-1, :j-1] g, g = s_S[0 .. j-2]
@@ -387,12 +402,20 @@ constexpr size_t USMEM = (size_t)2 * 2 * B * UP * sizeof(double);
 
 __global__ void __launch_bounds__(256, 1)
 sbr_syr2k_kernel(double* __restrict__ A, const long N, const long r0, const double* __restrict__ V,
-                 const double* __restrict__ W) {
+                 const double* __restrict__ W, const int part) {
   extern __shared__ double smem[];
   double* sA = smem;                    // [2B][UP]
   double* sB = smem + 2 * B * UP;       // [2B][UP]
+  // part 0: every lower tile (ib >= jb);  part 1: the first tile column only (jb = 0: it holds the next panel);
+  // part 2: the other tile columns (jb >= 1) -- parts 1 + 2 let the next panel's QR overlap most of the update
   int ib = 0, rem = blockIdx.x;         // linear id -> (ib >= jb): row ib holds ib + 1 tiles
-  while (rem > ib) { rem -= ib + 1; ++ib; }
+  if (part == 1) {
+    ib = blockIdx.x;
+    rem = 0;
+  } else {
+    while (rem > ib) { rem -= ib + 1; ++ib; }
+    if (part == 2) { ++ib; ++rem; }
+  }
   const long tile0 = r0 / UT;           // tiles anchored at absolute multiples of 128 (see sbr_symm_kernel)
   const long i0 = (tile0 + ib) * UT, j0 = (tile0 + rem) * UT;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -488,10 +511,20 @@ __device__ __forceinline__ void warp_house(const double x, const int lane, doubl
   }
 }
 
+__device__ __forceinline__ void cpa16_cg(void* smem_dst, const void* gsrc, bool valid) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int bytes = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gsrc), "r"(bytes) : "memory");
+}
+
+// The blocks of a task are worked on in the band layout itself: sB[c][d] = B[j0 + c + d][j0 + c] is a copy of
+// band columns j0 .. j0+L-1 (64 doubles each, fetched with ONE batch of 16-byte L2 copies: a task costs one
+// memory round trip in, one out).  D(r, c) = sB[c][r - c] (r >= c, mirrored otherwise), E(a, c) = sB[c][B - c + a].
 __global__ void __launch_bounds__(32)
 sbr_chase_kernel(double* __restrict__ Bb, const long N, double* __restrict__ V2, double* __restrict__ TAU2,
                  const long ntask_max, unsigned* __restrict__ bar) {
-  __shared__ double sD[B][TP], sE[B][TP], sv[B], sq[B];
+  __shared__ __align__(16) double sB[B][LDB];
+  __shared__ double sv[B], sq[B];
   const int lane = threadIdx.x;
   unsigned* err = bar + 1;
   unsigned* prog = bar + 2;
@@ -518,9 +551,12 @@ sbr_chase_kernel(double* __restrict__ Bb, const long N, double* __restrict__ V2,
       }
       const long j0 = i + 1 + (long)k * B;
       const int L = (int)min((long)B, N - j0);
-      const long j1 = j0 + B;
-      const int L2 = (int)max(0L, min((long)B, N - j1));
-      if (k == 0) {                                  // reflector of column i
+      const int L2 = (int)max(0L, min((long)B, N - j0 - B));
+      // ---- fetch band columns j0 .. j0+L-1 (zero-filled beyond)
+#pragma unroll
+      for (int c = 0; c < B; ++c) cpa16_cg(&sB[c][2 * lane], Bb + (j0 + c) * LDB + 2 * lane, c < L);
+      cpa_commit();
+      if (k == 0) {                                  // reflector of column i (overlaps the copies)
         const double x = (lane < L) ? __ldcg(Bb + i * LDB + 1 + lane) : 0.0;
         double beta;
         warp_house(x, lane, v, tau, beta);
@@ -530,60 +566,62 @@ sbr_chase_kernel(double* __restrict__ Bb, const long N, double* __restrict__ V2,
       if (lane < L) V2[i * N + j0 + lane] = v;
       if (lane == 0) TAU2[i * ntask_max + k] = tau;
       sv[lane] = v;
-      // ---- D = B[J, J] (symmetric): column c of the lower band is contiguous
-      for (int c = 0; c < B; ++c) {
-        const double val = (c < L && c + lane < L) ? __ldcg(Bb + (j0 + c) * LDB + lane) : 0.0;
-        if (c + lane < B) {
-          sD[c + lane][c] = val;
-          sD[c][c + lane] = val;
-        }
-      }
+      cpa_wait<0>();
       __syncwarp();
+      // ---- D <- H D H, H = I - tau v v^T: p = tau D v, q = p - (tau/2)(p^T v) v, D -= v q^T + q v^T
       {
-        double pl = 0.0;                             // p = tau D v
-#pragma unroll 8
-        for (int c = 0; c < B; ++c) pl = fma(sD[lane][c], sv[c], pl);
-        pl *= tau;
+        double pp[4] = {0.0, 0.0, 0.0, 0.0};        // four independent chains: one warp has no other latency cover
+#pragma unroll
+        for (int c = 0; c < B; ++c) {
+          const int idx = (c <= lane) ? c * LDB + lane - c : lane * LDB + c - lane;
+          pp[c & 3] = fma((&sB[0][0])[idx], sv[c], pp[c & 3]);
+        }
+        const double pl = tau * ((pp[0] + pp[1]) + (pp[2] + pp[3]));
         const double kk = 0.5 * tau * warp_sum(pl * v);
-        const double ql = fma(-kk, v, pl);           // q = p - (tau/2)(p^T v) v
+        const double ql = fma(-kk, v, pl);
         sq[lane] = ql;
         __syncwarp();
-#pragma unroll 8
-        for (int c = 0; c < B; ++c) sD[lane][c] -= fma(v, sq[c], ql * sv[c]);
+#pragma unroll
+        for (int c = 0; c < B; ++c)
+          if (c <= lane) sB[c][lane - c] -= fma(v, sq[c], ql * sv[c]);     // lower part: every entry once
+        __syncwarp();
       }
-      __syncwarp();
-      for (int c = 0; c < L; ++c)
-        if (c + lane < L) __stcg(Bb + (j0 + c) * LDB + lane, sD[c + lane][c]);
       double v2 = 0.0, tau2 = 0.0;
       if (L2 > 0) {
-        // ---- E = B[J_{k+1}, J_k]: column c holds rows j1 .. at offsets B - c + a
-        for (int c = 0; c < B; ++c)
-          sE[lane][c] = (c < L && lane < L2) ? __ldcg(Bb + (j0 + c) * LDB + B - c + lane) : 0.0;
+        // ---- E <- E H (lane = row a of E)
+        double yy[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int c = 0; c < B; ++c) yy[c & 3] = fma(sB[c][B - c + lane], sv[c], yy[c & 3]);
+        const double yl = tau * ((yy[0] + yy[1]) + (yy[2] + yy[3]));
+#pragma unroll
+        for (int c = 0; c < B; ++c) sB[c][B - c + lane] = fma(-yl, sv[c], sB[c][B - c + lane]);
         __syncwarp();
-        double yl = 0.0;                             // y = E v ; E <- E - tau y v^T
-#pragma unroll 8
-        for (int c = 0; c < B; ++c) yl = fma(sE[lane][c], sv[c], yl);
-        yl *= tau;
-#pragma unroll 8
-        for (int c = 0; c < B; ++c) sE[lane][c] = fma(-yl, sv[c], sE[lane][c]);
         double beta2;
-        warp_house(lane < L2 ? sE[lane][0] : 0.0, lane, v2, tau2, beta2);
+        warp_house(lane < L2 ? sB[0][B + lane] : 0.0, lane, v2, tau2, beta2);
         if (lane >= L2) v2 = 0.0;
         sq[lane] = v2;
         __syncwarp();
-        double zl = 0.0;                             // z_c = v2^T E[:, c] (lane = column c)
-#pragma unroll 8
-        for (int a = 0; a < B; ++a) zl = fma(sq[a], sE[a][lane], zl);
-        zl *= tau2;
+        // ---- E <- H2 E: z_c = tau2 v2^T E[:, c] (lane = column c), then lane = row a again
+        double zz[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int a2 = 0; a2 < B; ++a2) zz[a2 & 3] = fma(sq[a2], sB[lane][B - lane + a2], zz[a2 & 3]);
+        const double zl = tau2 * ((zz[0] + zz[1]) + (zz[2] + zz[3]));
         __syncwarp();
         sq[lane] = zl;
         __syncwarp();
-#pragma unroll 8
-        for (int c = 0; c < B; ++c) sE[lane][c] = fma(-v2, sq[c], sE[lane][c]);
-        sE[lane][0] = (lane == 0) ? beta2 : 0.0;     // exactly (beta, 0, ..., 0)
+#pragma unroll
+        for (int c = 0; c < B; ++c) sB[c][B - c + lane] = fma(-v2, sq[c], sB[c][B - c + lane]);
+        sB[0][B + lane] = (lane == 0) ? beta2 : 0.0;       // exactly (beta, 0, ..., 0)
         __syncwarp();
-        for (int c = 0; c < L; ++c)
-          if (lane < L2) __stcg(Bb + (j0 + c) * LDB + B - c + lane, sE[lane][c]);
+      }
+      // ---- write back the entries of this task: column c, d in [0, len_c)
+#pragma unroll
+      for (int c = 0; c < B; ++c) {
+        const int len = (c < L) ? ((L2 > 0) ? B - c + L2 : L - c) : 0;
+        const int d0 = 2 * lane;
+        double* dst = Bb + (j0 + c) * LDB + d0;
+        if (d0 + 1 < len) __stcg(reinterpret_cast<double2*>(dst), make_double2(sB[c][d0], sB[c][d0 + 1]));
+        else if (d0 < len) __stcg(dst, sB[c][d0]);
       }
       v = v2;
       tau = tau2;
@@ -610,12 +648,43 @@ sbr_band_to_tridiag_kernel(const double* __restrict__ Bb, const long N, double* 
 //   Q1: panels in descending order: z[r0:] -= V (T (V^T z[r0:])).
 // ------------------------------------------------------------------------------------------------
 constexpr int BT_THREADS = 512;
+constexpr int Q2_THREADS = 1024;
 
+// Q2: one eigenvector per CTA (the work per sweep is a handful of 32-element reflectors: latency, not throughput)
+__global__ void __launch_bounds__(Q2_THREADS, 1)
+sbr_back_q2_kernel(const double* __restrict__ V2, const double* __restrict__ TAU2, const long ntask_max, const long N,
+                   double* __restrict__ Z) {
+  extern __shared__ double zs[];                     // [N]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NW = Q2_THREADS / 32;
+  double* z = Z + (long)blockIdx.x * N;
+  for (long r = tid; r < N; r += Q2_THREADS) zs[r] = z[r];
+  __syncthreads();
+  for (long i = N - 3; i >= 0; --i) {
+    const int nt = (int)((N - 1 - i + B - 1) / B);
+    const double* vrow = V2 + i * N + i + 1;
+    const double* trow = TAU2 + i * ntask_max;
+    double* zz = zs + i + 1;
+#pragma unroll 2
+    for (int k = warp; k < nt; k += NW) {
+      const long o = (long)k * B + lane;
+      const bool in = i + 1 + o < N;
+      const double v = in ? __ldg(vrow + o) : 0.0;
+      const double tau = __ldg(trow + k);
+      const double x = in ? zz[o] : 0.0;
+      const double dot = warp_sum(v * x);
+      if (in) zz[o] = fma(-tau * dot, v, x);
+    }
+    __syncthreads();
+  }
+  for (long r = tid; r < N; r += Q2_THREADS) z[r] = zs[r];
+}
+
+// Q1: NV eigenvectors per CTA share every read of the panel reflectors
 template <int NV>
 __global__ void __launch_bounds__(BT_THREADS, 1)
-sbr_back_kernel(const double* __restrict__ V2, const double* __restrict__ TAU2, const long ntask_max,
-                const double* __restrict__ Vall, const double* __restrict__ Tall, const long npanel, const long N,
-                double* __restrict__ Z, const int nvec) {
+sbr_back_q1_kernel(const double* __restrict__ Vall, const double* __restrict__ Tall, const long npanel, const long N,
+                   double* __restrict__ Z, const int nvec) {
   extern __shared__ double zs[];                     // [NV][N]
   __shared__ double s_y[NV][B], s_t[NV][B], s_T[B][B + 1], s_part[BT_THREADS / 32][NV][B];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -624,27 +693,6 @@ sbr_back_kernel(const double* __restrict__ V2, const double* __restrict__ TAU2, 
   for (int q = 0; q < NV; ++q)
     for (long r = tid; r < N; r += BT_THREADS) zs[q * N + r] = (vec0 + q < nvec) ? Z[(long)(vec0 + q) * N + r] : 0.0;
   __syncthreads();
-  // ---- Q2
-  for (long i = N - 3; i >= 0; --i) {
-    const int nt = (int)((N - 1 - i + B - 1) / B);
-    const double* vrow = V2 + i * N;
-    const double* trow = TAU2 + i * ntask_max;
-#pragma unroll 4
-    for (int k = warp; k < nt; k += NW) {
-      const long j0 = i + 1 + (long)k * B;
-      const bool in = j0 + lane < N;
-      const double v = in ? __ldg(vrow + j0 + lane) : 0.0;
-      const double tau = __ldg(trow + k);
-#pragma unroll
-      for (int q = 0; q < NV; ++q) {
-        const double zz = in ? zs[q * N + j0 + lane] : 0.0;
-        const double dot = warp_sum(v * zz);
-        if (in) zs[q * N + j0 + lane] = fma(-tau * dot, v, zz);
-      }
-    }
-    __syncthreads();
-  }
-  // ---- Q1
   for (long kp = npanel - 1; kp >= 0; --kp) {
     const long c0 = kp * B, r0 = c0 + B;
     const double* Vk = Vall + c0 * N;
@@ -764,6 +812,41 @@ size_t sbr_workspace_doubles(long N) {
   return total;
 }
 
+// second (high-priority) stream + events per device: the QR of panel k+1 runs beside the bulk of panel k's update
+struct SbrStreams {
+  cudaStream_t qr = nullptr;
+  cudaEvent_t head = nullptr, qr_done = nullptr;
+  bool ok = false;
+};
+static SbrStreams& sbr_streams(int dev) {
+  static SbrStreams ss[64];
+  SbrStreams& x = ss[dev & 63];
+  if (!x.ok) {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    x.ok = cudaStreamCreateWithPriority(&x.qr, cudaStreamNonBlocking, hi) == cudaSuccess &&
+           cudaEventCreateWithFlags(&x.head, cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&x.qr_done, cudaEventDisableTiming) == cudaSuccess;
+  }
+  return x;
+}
+
+static int sbr_launch_qr(double* A, long N, long k, const SbrWs& w, cudaStream_t st) {
+  const int c0 = (int)(k * B);
+  const long n = N - c0 - B;
+  PODSDF_CUDA(cudaMemsetAsync(w.bar, 0, sizeof(unsigned), st));       // barrier counter (the error flag stays)
+  const int G = (int)((n + QR_THREADS - 1) / QR_THREADS);
+  double* Aarg = A;
+  long Narg = N;
+  int c0arg = c0;
+  double *Varg = w.Vall, *Targ = w.Tall + k * B * B, *parg = w.part, *rarg = w.rowj;
+  unsigned* barg = w.bar;
+  void* args[] = {&Aarg, &Narg, &c0arg, &Varg, &Targ, &parg, &rarg, &barg};
+  PODSDF_CUDA(cudaLaunchCooperativeKernel((const void*)sbr_panel_qr_kernel, dim3(G), dim3(QR_THREADS), args, 0, st));
+  count_launch();
+  return 0;
+}
+
 static int sbr_stage1(double* A, long N, const SbrWs& w, cudaStream_t st) {
   static bool configured[64] = {};
   int dev = 0;
@@ -773,24 +856,14 @@ static int sbr_stage1(double* A, long N, const SbrWs& w, cudaStream_t st) {
     PODSDF_CUDA(cudaFuncSetAttribute(sbr_syr2k_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)USMEM));
     configured[dev & 63] = true;
   }
+  SbrStreams& ss = sbr_streams(dev);
+  if (!ss.ok) return fail(PODSDF_ERR_CUDA, "stream creation failed");
+  if (w.npanel > 0) PODSDF_TRY(sbr_launch_qr(A, N, 0, w, st));
   for (long k = 0; k < w.npanel; ++k) {
     const int c0 = (int)(k * B);
     const long r0 = c0 + B, n = N - r0;
     double* Vk = w.Vall + (long)c0 * N;
     double* Tk = w.Tall + k * B * B;
-    // 1a: panel QR (cooperative: one grid barrier per column)
-    PODSDF_CUDA(cudaMemsetAsync(w.bar, 0, sizeof(unsigned), st));     // barrier counter (the error flag stays)
-    {
-      const int G = (int)((n + QR_THREADS - 1) / QR_THREADS);
-      double* Aarg = A;
-      long Narg = N;
-      int c0arg = c0;
-      double *Varg = w.Vall, *Targ = Tk, *parg = w.part, *rarg = w.rowj;
-      unsigned* barg = w.bar;
-      void* args[] = {&Aarg, &Narg, &c0arg, &Varg, &Targ, &parg, &rarg, &barg};
-      PODSDF_CUDA(cudaLaunchCooperativeKernel((const void*)sbr_panel_qr_kernel, dim3(G), dim3(QR_THREADS), args, 0, st));
-      count_launch();
-    }
     // 1b: X = A22 V, split over K so that the grid fills the machine
     const int row_tiles = (int)((N + XR - 1) / XR - r0 / XR);        // absolute tiles that reach rows >= r0
     const int total_chunks = (int)((N + XKB - 1) / XKB - r0 / XKB);
@@ -804,10 +877,26 @@ static int sbr_stage1(double* A, long N, const SbrWs& w, cudaStream_t st) {
     const int wct = (int)((n + WR - 1) / WR);
     sbr_w1_kernel<<<wct, 256, 0, st>>>(w.Xp, nsplit, Vk, N, r0, w.X, w.Zp);
     sbr_w2_kernel<<<(int)((n + WR2 - 1) / WR2), 256, 0, st>>>(w.X, Vk, Tk, w.Zp, wct, N, r0, w.W);
-    // 1e: rank-2b update of the lower tiles
+    count_launch(3);
+    // 1e: rank-2b update of the lower tiles.  The first tile column (it contains the next panel) goes first; the
+    // next panel's QR -- a latency-bound chain of grid barriers on a few SMs -- then runs on the high-priority
+    // stream beside the rest of the update.
     const int side = (int)((N + UT - 1) / UT - r0 / UT);
-    sbr_syr2k_kernel<<<side * (side + 1) / 2, 256, USMEM, st>>>(A, N, r0, Vk, w.W);
-    count_launch(4);
+    const bool ahead = k + 1 < w.npanel;
+    if (ahead && side > 1) {
+      sbr_syr2k_kernel<<<side, 256, USMEM, st>>>(A, N, r0, Vk, w.W, 1);
+      PODSDF_CUDA(cudaEventRecord(ss.head, st));
+      PODSDF_CUDA(cudaStreamWaitEvent(ss.qr, ss.head, 0));
+      PODSDF_TRY(sbr_launch_qr(A, N, k + 1, w, ss.qr));
+      PODSDF_CUDA(cudaEventRecord(ss.qr_done, ss.qr));
+      sbr_syr2k_kernel<<<side * (side - 1) / 2, 256, USMEM, st>>>(A, N, r0, Vk, w.W, 2);
+      PODSDF_CUDA(cudaStreamWaitEvent(st, ss.qr_done, 0));
+      count_launch(2);
+    } else {
+      sbr_syr2k_kernel<<<side * (side + 1) / 2, 256, USMEM, st>>>(A, N, r0, Vk, w.W, 0);
+      count_launch();
+      if (ahead) PODSDF_TRY(sbr_launch_qr(A, N, k + 1, w, st));
+    }
   }
   sbr_extract_band_kernel<<<ceil_div(N * LDB, 256L), 256, 0, st>>>(A, N, w.Bb);
   count_launch();
@@ -886,19 +975,21 @@ int sbr_back_transform(const double* ws, long N, double* Z, int nvec, cudaStream
   int dev = 0, max_smem = 0;
   PODSDF_CUDA(cudaGetDevice(&dev));
   PODSDF_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  const size_t fixed = 48 * 1024;                            // static shared memory of the kernel, generous
-  if (2 * one + fixed <= (size_t)max_smem) {
-    auto k = sbr_back_kernel<2>;
-    PODSDF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * one)));
-    k<<<(nvec + 1) / 2, BT_THREADS, 2 * one, st>>>(w.V2, w.TAU2, w.ntask_max, w.Vall, w.Tall, w.npanel, N, Z, nvec);
-  } else if (one + fixed <= (size_t)max_smem) {
-    auto k = sbr_back_kernel<1>;
-    PODSDF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)one));
-    k<<<nvec, BT_THREADS, one, st>>>(w.V2, w.TAU2, w.ntask_max, w.Vall, w.Tall, w.npanel, N, Z, nvec);
-  } else {
+  const size_t fixed = 48 * 1024;                            // static shared memory of the kernels, generous
+  if (one + fixed > (size_t)max_smem)
     return fail(PODSDF_ERR_UNSUPPORTED, "back-transformation: one eigenvector does not fit shared memory");
+  PODSDF_CUDA(cudaFuncSetAttribute(sbr_back_q2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)one));
+  sbr_back_q2_kernel<<<nvec, Q2_THREADS, one, st>>>(w.V2, w.TAU2, w.ntask_max, N, Z);
+  if (2 * one + fixed <= (size_t)max_smem) {
+    auto k = sbr_back_q1_kernel<2>;
+    PODSDF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * one)));
+    k<<<(nvec + 1) / 2, BT_THREADS, 2 * one, st>>>(w.Vall, w.Tall, w.npanel, N, Z, nvec);
+  } else {
+    auto k = sbr_back_q1_kernel<1>;
+    PODSDF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)one));
+    k<<<nvec, BT_THREADS, one, st>>>(w.Vall, w.Tall, w.npanel, N, Z, nvec);
   }
-  count_launch();
+  count_launch(2);
   PODSDF_CUDA(cudaGetLastError());
   return 0;
 }

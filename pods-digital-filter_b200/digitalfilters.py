@@ -340,6 +340,52 @@ def generate(nsteps, jma, kma, lnx, lny, lnz, nfx, nfy, nfz, fac_mean=None, rota
     return p.generate_seeded(seed, t0, nsteps, out)
 
 
+def _device_pipeline_available():
+    """The device-resident DF -> PODFS path needs PyTorch for its device buffers (plumbing only)."""
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def _main_device_pipeline(i_d, options, nsteps, jma, kma, lnx, lny, lnz, nfx, nfy, nfz, fac_mean, rotation, slabs, dt):
+    """DF:1403-1500 on the device (pipeline.df_to_podfs); fills the same i_d fields POD() publishes, except that
+    i_d.temporal_modes holds the nm kept modes (ns, nm) instead of all ns of them."""
+    import torch
+    try:
+        from . import pipeline
+    except ImportError:
+        import pipeline
+    p = _plan(jma, kma, nfx, nfy, nfz, _taps(nfx, lnx), _taps(nfy, lny), _taps(nfz, lnz))
+    p.set_impl(_capi.IMPL_AUTO)
+    if fac_mean is None:
+        p.set_coefficients(None, 0)
+    else:
+        p.set_coefficients(*_lund.pack(fac_mean[0], fac_mean[1], jma, kma))
+    p.set_rotation(None if rotation is None or np.array_equal(rotation, np.eye(3)) else rotation)
+    dev = torch.device("cuda", DEVICE)
+    slabs_dev = None
+    if slabs is not None:
+        slabs_dev = torch.from_numpy(np.ascontiguousarray(slabs[:nsteps + 2 * nfx])).to(dev)
+    print("\n==============================================================")
+    print("Calculating POD modes on the device ...")
+    res = pipeline.df_to_podfs(p, nsteps, options.nm, dt, options.et, seed=options.seed, slabs=slabs_dev,
+                               device_index=DEVICE)
+    energy, nm = res["energy"], res["nm"]
+    nv = pod._count_valid(energy, nsteps, 1.0e-15)
+    print("      Number of valid POD modes with positive energies = ", nv)
+    i_d.mean_field = res["mean"].cpu().numpy()
+    i_d.temporal_modes = res["T"]
+    i_d.spatial_modes = res["Phi"].cpu().numpy()
+    i_d.nm = nm
+    i_d.energy = energy
+    i_d.c128 = res["c128"]
+    pod.write_eigenvalues(nv, nsteps, energy, "PODFS/" + "POD.eigenvalues.dat")
+    print("\nCode completed.")
+    print("==============================================================\n")
+
+
 # ------------------------------------------------------------------------------------- CLI
 # (flags, dest, type, default, help) -- the reference's option table DF:1143-1237, names verbatim
 _OPTIONS = [
@@ -378,6 +424,9 @@ _OPTIONS = [
      "numpy: draw the random field from np.random in the reference's order and inject it (bit-compatible "
      "with a seeded reference run); philox: generate it on the GPU (fast path)"),
     (("--seed",), "seed", "int", 0, "seed of the philox stream"),
+    (("--pipeline",), "pipeline", "string", "device",
+     "device: planes stay in GPU memory from generation to the POD modes (default when not verbose); "
+     "host: every step goes through host arrays like the reference"),
 ]
 
 
@@ -461,28 +510,41 @@ def main(argv=None):
     rotation = prof_rotation_matrix(nx, ny, nz) if profilefile == "none" else None    # DF:1476-1477
 
     print("Generating", nsteps, "inlets on the GPU")
-    if options.rng == "numpy":
-        slabs = reference_stream(nsteps, jma, kma, nfx, nfy, nfz)
-        planes = generate(nsteps, jma, kma, lnx, lny, lnz, nfx, nfy, nfz, fac_mean, rotation, slabs=slabs)
-    elif options.rng == "philox":
-        planes = generate(nsteps, jma, kma, lnx, lny, lnz, nfx, nfy, nfz, fac_mean, rotation, seed=options.seed)
-    else:
+    if options.rng not in ("numpy", "philox"):
         raise Exception("--rng must be numpy or philox")
-    A = planes.reshape(nsteps, 3 * num_points).T       # (3P, ns) view of the device-native layout
-
-    if options.verbose:                                  # DF:1479-1481
-        for i in range(nsteps):
-            i_d.time = i * dt
-            pod.save_plane(A[:, i], i_d)
-    nmw = options.nm if options.verbose else 0
+    slabs = reference_stream(nsteps, jma, kma, nfx, nfy, nfz) if options.rng == "numpy" else None
     i_d.verbose = options.verbose
+    if not options.verbose and options.pipeline != "host" and _device_pipeline_available():
+        # DF:1403-1500 without a host round trip: the planes stay in HBM in the generator's layout [t][c][p] (the
+        # snapshot matrix transposed), mean removal, Gram matrix, leading eigenpairs and projection run on them in
+        # place, and only the mean field, the nm modes and the energies come back (pipeline.df_to_podfs).  Verbose
+        # runs write every plane and every temporal mode, so they take the host path below.
+        _main_device_pipeline(i_d, options, nsteps, jma, kma, lnx, lny, lnz, nfx, nfy, nfz, fac_mean, rotation, slabs, dt)
+    else:
+        if slabs is not None:
+            planes = generate(nsteps, jma, kma, lnx, lny, lnz, nfx, nfy, nfz, fac_mean, rotation, slabs=slabs)
+        else:
+            planes = generate(nsteps, jma, kma, lnx, lny, lnz, nfx, nfy, nfz, fac_mean, rotation, seed=options.seed)
+        A = planes.reshape(nsteps, 3 * num_points).T       # (3P, ns) view of the device-native layout
 
-    mean_field = np.mean(A, 1)                           # DF:1492-1495
-    i_d.mean_field = mean_field
-    planes -= mean_field[None, :].reshape(1, 3, jma, kma)
+        if options.verbose:                                  # DF:1479-1481
+            for i in range(nsteps):
+                i_d.time = i * dt
+                pod.save_plane(A[:, i], i_d)
+        nmw = options.nm if options.verbose else 0
 
-    pod.POD(A, nsteps, num_points, 3, "false", [], "PODFS/", "false", 1.0e-15, options.nm, nmw, "false", "false",
-            i_d.grid, mean_field, dt, "velocity", 1, nsteps, 1, 1, i_d)
+        # DF:1492-1495.  The reference reduces a C-contiguous (3P, ns) array, i.e. numpy's pairwise sum along the
+        # contiguous time axis; `planes` holds the transpose, so the same reduction order needs a contiguous copy
+        # of each row block (bit parity of mean_field with the reference).
+        mean_field = np.empty(3 * num_points)
+        blk = max(1, (1 << 24) // max(nsteps, 1))
+        for r0 in range(0, 3 * num_points, blk):
+            mean_field[r0:r0 + blk] = np.mean(np.ascontiguousarray(A[r0:r0 + blk]), 1)
+        i_d.mean_field = mean_field
+        planes -= mean_field[None, :].reshape(1, 3, jma, kma)
+
+        pod.POD(A, nsteps, num_points, 3, "false", [], "PODFS/", "false", 1.0e-15, options.nm, nmw, "false", "false",
+                i_d.grid, mean_field, dt, "velocity", 1, nsteps, 1, 1, i_d)
     pod.fourier_coefficients(i_d)
     pod.pod2prf(i_d)
     if options.hdf5:

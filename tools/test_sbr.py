@@ -36,7 +36,7 @@ def band_dense(band, N, b=32):
 
 
 def main():
-    sizes = [int(a) for a in sys.argv[1:]] or [300, 515, 1000, 2049]
+    sizes = [int(a) for a in sys.argv[1:] if not a.startswith("--")] or [300, 515, 1000, 2049]
     rs = np.random.RandomState(5)
     out = []
     for N in sizes:
@@ -57,7 +57,7 @@ def main():
                            top_resid=float(np.abs(R).max() / nrm), top_orth=float(np.abs(V @ V.T - np.eye(nm)).max()))
             out.append(rec)
             print(json.dumps(rec), flush=True)
-    if "--big" in sys.argv or not sys.argv[1:]:
+    if "--big" in sys.argv:
         N = 10000
         C = sym_matrix(N, rs, "gram")
         for rep in range(2):
