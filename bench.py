@@ -178,6 +178,10 @@ class ClockSampler(object):
                 "power_w_median": float(np.median(watts)) if watts else None}
 
 
+def us_per_plane_fmt(x):
+    return float("%.4f" % x)
+
+
 def cfg3_lund(pkg):
     c = CFG3
     df = pkg.digitalfilters
@@ -258,6 +262,195 @@ def run_reference(args, rank):
     _emit(line)
 
 
+
+# --------------------------------------------------------------------------------------------------
+CFG1 = dict(J=64, K=64, nf=10, ln=5.0, ns=1000, nm=20, et=0.9, profile="hyperbolic-tangent", U0=1.0, u_dash=0.02, res=0.1)
+
+
+def run_cfg1(args, pkg, torch, dev, local_rank, cpu_too=True):
+    """BASELINE config 1 IN FULL (64 x 64 x 3, 1000 steps, half-width 10, ln = 5, built tanh profile, 20 modes, et = 0.9):
+    `digitalfilters.main()`'s compute -- DF:1403-1510 without the file writers -- through the device-resident pipeline,
+    results (mean, 20 modes, energies, Fourier coefficients) copied to the host inside the timed region; next to the
+    oracle port of the reference on the host cores, faithful (per-point Python loops) and vectorised, with the BLAS
+    thread count at all cores and at 1."""
+    capi, df, pipeline = pkg._capi, pkg.digitalfilters, pkg.pipeline
+    c = CFG1
+    J, K, nf, ln, ns, nm = c["J"], c["K"], c["nf"], c["ln"], c["ns"], c["nm"]
+    U, uu, vv, ww, uw = df.build_profile(c["profile"], "top-hat", c["U0"], c["u_dash"], K)
+    dt = c["res"] / np.mean(U[U != 0])
+    taps = df._taps(nf, ln)
+
+    def ours(seed):
+        plan = capi.DfPlan(J, K, nf, nf, nf, taps, taps, taps, device=local_rank)
+        plan.set_coefficients(*pkg._lund.pack(*pkg._lund.lund_1d(U, uu, vv, ww, uw, J, K), J, K))   # H2D of the inputs
+        res = pipeline.df_to_podfs(plan, ns, nm, dt, c["et"], seed=seed, device_index=local_rank)
+        out = dict(mean=res["mean"].cpu().numpy(), Phi=res["Phi"].cpu().numpy(), energy=res["energy"], T=res["T"],
+                   c_count=res["c_count"], route=res.get("route"))
+        plan.close()
+        return out
+
+    ours(1)                                                      # warm-up (workspaces, cuSOLVER handle if route 0)
+    torch.cuda.synchronize(dev)
+    reps = 5
+    t0 = time.perf_counter()
+    for r in range(reps):
+        o = ours(2 + r)
+    torch.cuda.synchronize(dev)
+    wall = (time.perf_counter() - t0) / reps
+    d2h = o["mean"].nbytes + o["Phi"].nbytes + 8 * ns
+    out = {"workload": "cfg1 in full: 64x64x3 planes, 1000 steps, nf=10, ln=5, adapt1d + identity rotation, PODFS 20 modes, et=0.9",
+           "ours": {"wall_s": wall, "planes_per_s": ns / wall, "snapshots_per_s": ns / wall, "reps": reps,
+                    "api": "DfPlan + pipeline.df_to_podfs (what digitalfilters.main() runs when not verbose), results on the host",
+                    "h2d_bytes": 5 * J * K * 8, "d2h_bytes": int(d2h), "modes_kept": int(len(o["c_count"])),
+                    "fourier_coefficients_kept": int(np.sum(o["c_count"]))}}
+    if cpu_too:
+        from oracle import df_oracle as dfo
+        from oracle import pod_oracle as podo
+        import multiprocessing
+        try:
+            from threadpoolctl import threadpool_limits
+        except Exception:
+            threadpool_limits = None
+        rs = np.random.RandomState(0)
+        X = rs.uniform(-dfo.SQRT3, dfo.SQRT3, (3, ns + 2 * nf, J + 2 * nf, K + 2 * nf))
+        lund = ("1d", U, uu, vv, ww, uw)
+        cpu = {"host_cores": multiprocessing.cpu_count()}
+        A = None
+        for name, loops in (("faithful", True), ("vectorised", False)):
+            t0 = time.perf_counter()
+            A = dfo.generate(X, ns, J, K, ln, ln, ln, nf, nf, nf, lund, rotate=(1.0, 0.0, 0.0), loops=loops)
+            cpu["df_%s_s" % name] = time.perf_counter() - t0
+        for label, limit in (("all", None), ("1", 1)):
+            ctx = threadpool_limits(limits=limit) if (threadpool_limits and limit) else None
+            if ctx is not None:
+                ctx.__enter__()
+            try:
+                t0 = time.perf_counter()
+                mean, A0 = dfo.remove_mean(np.array(A))
+                r = podo.pod(A0, ns, J * K, 3, "false", [], 1.0e-15, nm)
+                t1 = time.perf_counter()
+                podo.fourier_coefficients(r["temporal_modes"], ns, r["nm"], dt, c["et"], direct=True)
+                t2 = time.perf_counter()
+            finally:
+                if ctx is not None:
+                    ctx.__exit__(None, None, None)
+            cpu["pod_blas_threads_%s_s" % label] = {"mean_gram_eig_project": t1 - t0, "fourier_python_loop": t2 - t1}
+        for name in ("faithful", "vectorised"):
+            tot = cpu["df_%s_s" % name] + sum(cpu["pod_blas_threads_all_s"].values())
+            cpu["%s_total_s" % name] = tot
+            cpu["%s_planes_per_s" % name] = ns / tot
+        cpu["kind"] = "port"
+        cpu["note"] = ("oracle port of DF:1403-1510 (scipy direct convolutions; faithful = the reference's per-point Python "
+                       "loops, vectorised = same arithmetic in numpy), POD via numpy BLAS/LAPACK, Fourier fit = the reference's "
+                       "O(ns^2) Python DFT loop; the DF loop is single-threaded either way, BLAS threads only touch the POD part")
+        out["cpu"] = cpu
+    return out
+
+
+def run_multi_gpu(args, pkg, torch, dist, dev, local_rank, rank, world, barrier, max_over_ranks):
+    """Driver-visible multi-GPU evidence (N > 1): (a) parity on a small case -- generated time shards equal the
+    single-GPU run bit for bit, the injected-mode halo received over NCCL equals the neighbour's slabs bit for bit,
+    the row-sharded Gram matrix after the all-reduce equals the one-GPU Gram matrix; (b) the two collectives of the
+    path timed at config-3 size: the filter-width halo exchange and the DF -> PODFS all-to-all re-shard."""
+    capi, df, pipeline = pkg._capi, pkg.digitalfilters, pkg.pipeline
+    out = {}
+    # ---- (a) parity, 64 x 48 plane, nf = 4, 16 steps per rank
+    J, K, nf, ln = 64, 48, 4, 2.0
+    ns = 16 * world
+    taps = df._taps(nf, ln)
+    plan = capi.DfPlan(J, K, nf, nf, nf, taps, taps, taps, device=local_rank)
+    U, uu, vv, ww, uw = df.build_profile("hyperbolic-tangent", "top-hat", 1.0, 0.05, K)
+    plan.set_coefficients(*pkg._lund.pack(*pkg._lund.lund_1d(U, uu, vv, ww, uw, J, K), J, K))
+    st = torch.cuda.current_stream(dev).cuda_stream
+    seed = 99
+    t0, t1 = pipeline.shard_range(ns, rank, world, 8)
+    whole = torch.empty((ns, 3, J, K), dtype=torch.float64, device=dev)
+    plan.generate_seeded_dev(seed, 0, ns, whole.data_ptr(), st)                       # the one-GPU run, on every rank
+    mine = torch.empty((t1 - t0, 3, J, K), dtype=torch.float64, device=dev)
+    plan.generate_seeded_dev(seed, t0, t1 - t0, mine.data_ptr(), st)
+    torch.cuda.synchronize(dev)
+    shard_ok = bool(torch.equal(mine, whole[t0:t1]))
+    Jp, Kp = J + 2 * nf, K + 2 * nf
+    nown = (t1 - t0) if rank < world - 1 else (t1 - t0) + 2 * nf                       # the last rank owns the tail slabs
+    own = torch.empty((nown, 3, Jp, Kp), dtype=torch.float64, device=dev)
+    plan.random_slabs_dev(seed, t0, nown, own.data_ptr(), st)
+    torch.cuda.synchronize(dev)
+    ext = pipeline.exchange_halo(own, 2 * nf, rank, world)
+    want = torch.empty((t1 - t0 + 2 * nf, 3, Jp, Kp), dtype=torch.float64, device=dev)
+    plan.random_slabs_dev(seed, t0, t1 - t0 + 2 * nf, want.data_ptr(), st)
+    torch.cuda.synchronize(dev)
+    halo_ok = bool(torch.equal(ext, want))
+    inj = torch.empty((t1 - t0, 3, J, K), dtype=torch.float64, device=dev)
+    plan.generate_injected_dev(ext.data_ptr(), ext.shape[0], inj.data_ptr(), st)
+    torch.cuda.synchronize(dev)
+    inj_err = float((inj - whole[t0:t1]).abs().max() / whole.abs().max())
+    # Gram: rows sharded, one all-reduce
+    M = 3 * J * K
+    a_full = whole.view(ns, M)
+    L = capi.lib()
+    C1 = torch.empty((ns, ns), dtype=torch.float64, device=dev)
+    capi.check(L.podsdf_gram_dev(local_rank, a_full.data_ptr(), M, ns, 1, None, 0, 1.0 / ns, C1.data_ptr(), st))
+    m0, m1 = pipeline.shard_range(M, rank, world)
+    a_rows = a_full[:, m0:m1].contiguous()
+    Cp = torch.empty((ns, ns), dtype=torch.float64, device=dev)
+    capi.check(L.podsdf_gram_dev(local_rank, a_rows.data_ptr(), m1 - m0, ns, 1, None, 0, 1.0 / ns, Cp.data_ptr(), st))
+    pipeline.allreduce_gram(Cp)
+    torch.cuda.synchronize(dev)
+    gram_err = float((Cp - C1).abs().max() / C1.abs().max())
+    # re-shard parity: all-to-all of the time shards gives every rank its rows of the one-GPU matrix
+    a_loc, rows = pipeline.reshard_time_to_rows(mine.view(t1 - t0, M))
+    torch.cuda.synchronize(dev)
+    resh_ok = bool(torch.equal(a_loc, a_full[:, rows[0]:rows[1]]))
+    flags = torch.tensor([float(shard_ok), float(halo_ok), float(resh_ok), -inj_err, -gram_err], dtype=torch.float64, device=dev)
+    dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+    out["parity"] = {"case": "64x48x3, nf=4, %d steps, %d ranks" % (ns, world),
+                     "generated_shards_bitexact": bool(flags[0] > 0.5), "halo_exchange_bitexact": bool(flags[1] > 0.5),
+                     "reshard_all_to_all_bitexact": bool(flags[2] > 0.5),
+                     "injected_vs_one_gpu_max_rel": float(-flags[3]), "gram_allreduce_vs_one_gpu_max_rel": float(-flags[4])}
+    plan.close()
+    del whole, mine, own, ext, want, inj, C1, Cp, a_rows, a_loc
+    torch.cuda.empty_cache()
+    # ---- (b) collectives at config-3 size (512^2 x 3, nf = 10, 2500 planes per GPU)
+    c = CFG3
+    J, K, nf = c["J"], c["K"], c["nf"]
+    Jp, Kp = J + 2 * nf, K + 2 * nf
+    halo = torch.randn((2 * nf + 1, 3, Jp, Kp), dtype=torch.float64, device=dev)     # >= 2 nfx slabs: what a neighbour needs
+    for it in range(3):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ext = pipeline.exchange_halo(halo, 2 * nf, rank, world)
+        e1.record()
+        barrier()
+        halo_ms = max_over_ranks(e0.elapsed_time(e1))
+        del ext
+    hb = 2 * nf * 3 * Jp * Kp * 8
+    out["halo_exchange"] = {"ms": halo_ms, "bytes_per_edge": hb, "gbs_per_edge": hb / (halo_ms * 1e-3) / 1e9,
+                            "what": "2 nfx = 20 raw random slabs of 3 x 532 x 532 doubles from the right neighbour "
+                                    "(NCCL send/recv + concatenation), injected mode only"}
+    del halo
+    n_loc = min(args.df_planes, 2500)
+    M = 3 * J * K
+    planes = torch.empty((n_loc, M), dtype=torch.float64, device=dev)
+    planes.normal_()
+    for it in range(2):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        a_loc, rows = pipeline.reshard_time_to_rows(planes)
+        e1.record()
+        barrier()
+        resh_ms = max_over_ranks(e0.elapsed_time(e1))
+        del a_loc
+    nbytes = n_loc * M * 8
+    out["reshard_all_to_all"] = {"ms": resh_ms, "bytes_per_gpu": nbytes, "gbs_per_gpu": nbytes / (resh_ms * 1e-3) / 1e9,
+                                 "sent_off_gpu_gbs": nbytes * (world - 1) / world / (resh_ms * 1e-3) / 1e9,
+                                 "what": "time-sharded planes [t_local][row] -> row shards [t][rows_local]: pack, one NCCL "
+                                         "all-to-all, concatenate (pipeline.reshard_time_to_rows), %d planes per GPU" % n_loc}
+    del planes
+    torch.cuda.empty_cache()
+    return out
+
 # --------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -280,6 +473,8 @@ def main():
     ap.add_argument("--no-pod", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cfg1", action="store_true", help="skip the config-1 leg (64x64x3, 1000 steps, 20 modes, in full)")
+    ap.add_argument("--no-multi", action="store_true", help="skip the multi-GPU parity / collective timing leg (N > 1)")
     ap.add_argument("--impl-kernels", type=int, default=0, help="0 auto, 1 generic, 2 tuned")
     args = ap.parse_args()
 
@@ -412,6 +607,20 @@ def main():
                                "algorithmic_bytes_per_plane": b_time},
     }
 
+    # ---- whole step against SURVEY 8(d): max(algorithmic bytes / HBM peak, flops / FP64 peak) / measured time
+    us_plane = 1e3 * ms_per_step / n_planes
+    b_step = 24.0 * J * K if args.rng == "philox" else b_plane
+    step_roofline = {
+        "us_per_plane": us_per_plane_fmt(us_plane),
+        "algorithmic_bytes_per_plane": b_step, "algorithmic_flops_per_plane": fl_total,
+        "hbm_floor_us": b_step / hbm_peak / 1e3, "fp64_floor_us": fl_total / FP64_DFMA_PEAK_TFLOPS / 1e6,
+        "frac": max(b_step / hbm_peak / 1e3, fl_total / FP64_DFMA_PEAK_TFLOPS / 1e6) / us_plane,
+        "bound": "fp64" if fl_total / FP64_DFMA_PEAK_TFLOPS / 1e6 > b_step / hbm_peak / 1e3 else "hbm",
+        "note": "generated mode writes each plane once (24 J K bytes); the time-filtered intermediate T1 makes one round "
+                "trip through HBM (6.95 MB/plane written + read at nf=10) that is not algorithmic -- DESIGN.md section 3 "
+                "shows why it cannot stay on chip",
+    }
+
     # ---- e2e: public host API (pinned host output, D2H inside the timed region)
     e2e = None
     if not args.no_e2e:
@@ -442,6 +651,13 @@ def main():
         pod = run_pod(args, pkg, torch, dist, dev, local_rank, rank, world, barrier, max_over_ranks)
     launches_all = capi.launch_count() - launches0
 
+    multi = None
+    if world > 1 and not args.no_multi:
+        multi = run_multi_gpu(args, pkg, torch, dist, dev, local_rank, rank, world, barrier, max_over_ranks)
+    cfg1 = None
+    if rank == 0 and world == 1 and not args.no_cfg1:
+        cfg1 = run_cfg1(args, pkg, torch, dev, local_rank, cpu_too=not args.no_cpu)
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         v, dt, tm = cpu_df_baseline(2, loops=True)
@@ -457,13 +673,15 @@ def main():
             "metric": "df_planes_per_s", "value": value, "unit": "planes/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "cfg3 round-jet inlet 512x512x3, nf=%d, ln=%g, adapt2d Lund + rotation: %d-plane time shard per GPU "
+            "config": {"workload": "cfg3 round-jet inlet 512x512x3, nf=%d, ln=%g, adapt2d Lund transform (default plane normal: the "
+                                   "rotation is the identity and is skipped, DF:1476-1477): %d-plane time shard per GPU "
                                    "(config 3's 20000 steps at 8 GPUs)" % (nf, ln, n_planes),
                        "rng": args.rng, "planes_per_step_per_gpu": n_planes, "parallelism": "time-sharded x%d" % world,
                        "l2": "every step writes %.1f GB per GPU (>> 126 MB L2); no flush needed" % (n_planes * 3 * J * K * 8 / 1e9),
                        "kernels": "tuned" if (info["tuned_time"] and info["tuned_plane"]) else "generic",
                        "planes_per_pass": info["chunk"]},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_timed,
+            "roofline": roofline, "step_roofline": step_roofline, "cpu_baseline": cpu, "e2e": e2e, "cfg1": cfg1,
+            "multi_gpu": multi, "gpu_launches": launches_timed,
             "gpu_launches_total": launches_all, "clocks": clocks, "sustained": sustained, "pod": pod,
         }
         _emit(line)

@@ -23,6 +23,7 @@
 #include "sbr_kernels.cuh"
 
 #include <cfloat>
+#include <cstdlib>
 
 namespace podsdf {
 
@@ -222,7 +223,7 @@ constexpr int XATILE = (XR * XPA0 > XKB * XPA1) ? XR * XPA0 : XKB * XPA1;
 constexpr int XVTILE = B * XPV;
 constexpr size_t XSMEM = (size_t)XST * (XATILE + XVTILE) * sizeof(double);
 
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(256, 2)
 sbr_symm_kernel(const double* __restrict__ A, const long N, const long r0, const double* __restrict__ V,
                 double* __restrict__ Xp, const int chunks_per_split) {
   extern __shared__ double smem[];
@@ -529,10 +530,18 @@ sbr_chase_kernel(double* __restrict__ Bb, const long N, double* __restrict__ V2,
   unsigned* err = bar + 1;
   unsigned* prog = bar + 2;
   const long nsweep = N - 2;
+#ifdef PODSDF_CHASE_PROFILE
+  long long pc[5] = {0, 0, 0, 0, 0}, ptasks = 0;
+#define PCLK(n) { const long long t_ = clock64(); pc[n] += t_ - plast; plast = t_; }
+  long long plast = clock64();
+#else
+#define PCLK(n)
+#endif
   for (long i = blockIdx.x; i < nsweep; i += gridDim.x) {
     const int nt = (int)((N - 1 - i + B - 1) / B);
     double v = 0.0, tau = 0.0;                       // reflector of the current task (lane = row inside J_k)
     for (int k = 0; k < nt; ++k) {
+      PCLK(4)
       // ---- dependency: sweep i-1 has finished task k+1
       if (i > 0) {
         int ok = 1;
@@ -549,6 +558,7 @@ sbr_chase_kernel(double* __restrict__ Bb, const long N, double* __restrict__ V2,
         ok = __shfl_sync(0xffffffffu, ok, 0);
         if (!ok) return;
       }
+      PCLK(0)
       const long j0 = i + 1 + (long)k * B;
       const int L = (int)min((long)B, N - j0);
       const int L2 = (int)max(0L, min((long)B, N - j0 - B));
@@ -568,6 +578,7 @@ sbr_chase_kernel(double* __restrict__ Bb, const long N, double* __restrict__ V2,
       sv[lane] = v;
       cpa_wait<0>();
       __syncwarp();
+      PCLK(1)
       // ---- D <- H D H, H = I - tau v v^T: p = tau D v, q = p - (tau/2)(p^T v) v, D -= v q^T + q v^T
       {
         double pp[4] = {0.0, 0.0, 0.0, 0.0};        // four independent chains: one warp has no other latency cover
@@ -614,6 +625,7 @@ sbr_chase_kernel(double* __restrict__ Bb, const long N, double* __restrict__ V2,
         sB[0][B + lane] = (lane == 0) ? beta2 : 0.0;       // exactly (beta, 0, ..., 0)
         __syncwarp();
       }
+      PCLK(2)
       // ---- write back the entries of this task: column c, d in [0, len_c)
 #pragma unroll
       for (int c = 0; c < B; ++c) {
@@ -630,6 +642,189 @@ sbr_chase_kernel(double* __restrict__ Bb, const long N, double* __restrict__ V2,
       __syncwarp();
       if (lane == 0) st_release_u32(prog + i, (k + 1 == nt) ? 0x7fffffffu : (unsigned)(k + 1));
       __syncwarp();
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stage 2, pipelined inside a CTA.  The single-warp kernel above pays a global-memory hand-off (fence, release,
+// acquire poll, L2 copies) on every task and the pipeline advances two tasks per sweep: 2 N hand-offs on the
+// critical path.  Here a CTA runs CG consecutive sweeps, one warp each, and the band columns stream through them
+// in SHARED memory: warp 0 copies the columns of its task in from L2, every warp works on them in place one after
+// the other (warp w starts task k when warp w-1 has finished task k+1: a shared-memory flag), and the last warp
+// copies them back out.  Only the hand-off between CTAs (bundles of CG sweeps) goes through global memory.
+//   ring of RC = (2 CG + 1) 32-column blocks: slot(c) = c mod RC, 64 doubles per column (the band layout itself).
+// ------------------------------------------------------------------------------------------------
+constexpr int CG = 6;                    // sweeps per CTA
+constexpr int RCB = 2 * CG + 1;          // ring capacity in blocks of B columns (one block of slack)
+constexpr int RC = RCB * B;              // ... in columns
+constexpr size_t CHASE_SMEM = (size_t)RC * LDB * sizeof(double);
+
+__device__ __forceinline__ int ring_slot(int s) { return s >= RC ? s - RC : s; }
+
+__global__ void __launch_bounds__(32 * CG, 1)
+sbr_chase_multi_kernel(double* __restrict__ Bb, const long N, double* __restrict__ V2, double* __restrict__ TAU2,
+                       const long ntask_max, unsigned* __restrict__ bar) {
+  extern __shared__ __align__(16) double ring[];          // [RC][LDB]
+  __shared__ double s_v[CG][B], s_q[CG][B];
+  __shared__ volatile int s_prog[CG];
+  __shared__ volatile int s_abort;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  unsigned* err = bar + 1;
+  unsigned* prog = bar + 2;
+  const long nsweep = N - 2;
+  double* sv = s_v[w];
+  double* sq = s_q[w];
+  if (threadIdx.x == 0) s_abort = 0;
+
+  for (long i0 = (long)blockIdx.x * CG; i0 < nsweep; i0 += (long)gridDim.x * CG) {
+    __syncthreads();                                 // the previous bundle has left the ring
+    if (lane == 0) s_prog[w] = 0;
+    __syncthreads();
+    const long i = i0 + w;                           // this warp's sweep
+    const int gv = (int)min((long)CG, nsweep - i0);  // valid sweeps of the bundle
+    if (w < gv) {
+      const int nt = (int)((N - 1 - i + B - 1) / B);
+      const bool first = (w == 0), last = (w == gv - 1);
+      double v = 0.0, tau = 0.0;
+      bool ok = true;
+      for (int k = 0; k < nt && ok; ++k) {
+        const long j0 = i + 1 + (long)k * B;
+        const int L = (int)min((long)B, N - j0);
+        const int L2 = (int)max(0L, min((long)B, N - j0 - B));
+        // ---- wait: predecessor sweep has finished task k+1; the ring has room (first warp only)
+        if (lane == 0) {
+          unsigned spins = 0;
+          if (first) {
+            if (i > 0) {
+              const unsigned need = (unsigned)(k + 2);
+              while (ld_acquire_u32(prog + i - 1) < need) {
+                if (++spins > (1u << 22)) {
+                  if ((spins & 0xFFFFu) == 0 && (ld_acquire_u32(err) != 0 || s_abort)) { ok = false; break; }
+                  if (spins > (1u << 27)) { atomicExch(err, 2u); ok = false; break; }
+                }
+              }
+            }
+            const int need_last = k - RCB + 1;       // columns leaving the slots this task overwrites
+            while (ok && need_last > 0 && s_prog[gv - 1] < need_last) {
+              if (++spins > (1u << 27) || s_abort) { atomicExch(err, 3u); ok = false; break; }
+            }
+          } else {
+            const int need = k + 2;
+            while (s_prog[w - 1] < need) {
+              if (++spins > (1u << 27) || s_abort) { atomicExch(err, 4u); ok = false; break; }
+            }
+          }
+          if (!ok) s_abort = 1;
+        }
+        ok = __shfl_sync(0xffffffffu, ok ? 1 : 0, 0) != 0;
+        if (!ok) break;
+        __threadfence_block();
+        const int a0 = (int)(j0 % RC);               // ring slot of column j0
+        if (first) {
+          // ---- copy the task's band columns in (and the sweep column i itself at task 0)
+#pragma unroll
+          for (int c = 0; c < B; ++c)
+            cpa16_cg(ring + (size_t)ring_slot(a0 + c) * LDB + 2 * lane, Bb + (j0 + c) * LDB + 2 * lane, c < L);
+          if (k == 0) cpa16_cg(ring + (size_t)(i % RC) * LDB + 2 * lane, Bb + i * LDB + 2 * lane, true);
+          cpa_commit();
+          cpa_wait<0>();
+          __syncwarp();
+        }
+        if (k == 0) {                                // reflector of column i; the column is final afterwards
+          double* col = ring + (size_t)(i % RC) * LDB;
+          const double x = (lane < L) ? col[1 + lane] : 0.0;
+          double beta;
+          warp_house(x, lane, v, tau, beta);
+          __syncwarp();
+          if (lane < L) col[1 + lane] = (lane == 0) ? beta : 0.0;
+          __syncwarp();
+          __stcg(reinterpret_cast<double2*>(Bb + i * LDB + 2 * lane), make_double2(col[2 * lane], col[2 * lane + 1]));
+        }
+        if (lane >= L) v = 0.0;
+        if (lane < L) V2[i * N + j0 + lane] = v;
+        if (lane == 0) TAU2[i * ntask_max + k] = tau;
+        sv[lane] = v;
+        __syncwarp();
+        // ---- D <- H D H
+        {
+          double pp[4] = {0.0, 0.0, 0.0, 0.0};
+          const int sl = ring_slot(a0 + lane);
+#pragma unroll
+          for (int c = 0; c < B; ++c) {
+            const int sc = ring_slot(a0 + c);
+            const int idx = (c <= lane) ? sc * LDB + lane - c : sl * LDB + c - lane;
+            pp[c & 3] = fma(ring[idx], sv[c], pp[c & 3]);
+          }
+          const double pl = tau * ((pp[0] + pp[1]) + (pp[2] + pp[3]));
+          const double kk = 0.5 * tau * warp_sum(pl * v);
+          const double ql = fma(-kk, v, pl);
+          sq[lane] = ql;
+          __syncwarp();
+#pragma unroll
+          for (int c = 0; c < B; ++c)
+            if (c <= lane) ring[ring_slot(a0 + c) * LDB + lane - c] -= fma(v, sq[c], ql * sv[c]);
+          __syncwarp();
+        }
+        double v2 = 0.0, tau2 = 0.0;
+        if (L2 > 0) {
+          double yy[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+          for (int c = 0; c < B; ++c) yy[c & 3] = fma(ring[ring_slot(a0 + c) * LDB + B - c + lane], sv[c], yy[c & 3]);
+          const double yl = tau * ((yy[0] + yy[1]) + (yy[2] + yy[3]));
+#pragma unroll
+          for (int c = 0; c < B; ++c) {
+            double* pe = ring + ring_slot(a0 + c) * LDB + B - c + lane;
+            *pe = fma(-yl, sv[c], *pe);
+          }
+          __syncwarp();
+          double beta2;
+          double* col0 = ring + (size_t)a0 * LDB;
+          warp_house(lane < L2 ? col0[B + lane] : 0.0, lane, v2, tau2, beta2);
+          if (lane >= L2) v2 = 0.0;
+          sq[lane] = v2;
+          __syncwarp();
+          double zz[4] = {0.0, 0.0, 0.0, 0.0};
+          const double* mycol = ring + (size_t)ring_slot(a0 + lane) * LDB + B - lane;
+#pragma unroll
+          for (int a2 = 0; a2 < B; ++a2) zz[a2 & 3] = fma(sq[a2], mycol[a2], zz[a2 & 3]);
+          const double zl = tau2 * ((zz[0] + zz[1]) + (zz[2] + zz[3]));
+          __syncwarp();
+          sq[lane] = zl;
+          __syncwarp();
+#pragma unroll
+          for (int c = 0; c < B; ++c) {
+            double* pe = ring + ring_slot(a0 + c) * LDB + B - c + lane;
+            *pe = fma(-v2, sq[c], *pe);
+          }
+          col0[B + lane] = (lane == 0) ? beta2 : 0.0;
+          __syncwarp();
+        }
+        v = v2;
+        tau = tau2;
+        if (last) {
+          // ---- the columns of this task leave the ring (every entry the bundle may have changed: d < B - c + L2)
+#pragma unroll
+          for (int c = 0; c < B; ++c) {
+            const int len = (c < L) ? ((L2 > 0) ? B - c + L2 : L - c) : 0;
+            const int d0 = 2 * lane;
+            const double* src = ring + (size_t)ring_slot(a0 + c) * LDB + d0;
+            double* dst = Bb + (j0 + c) * LDB + d0;
+            if (d0 + 1 < len) __stcg(reinterpret_cast<double2*>(dst), make_double2(src[0], src[1]));
+            else if (d0 < len) __stcg(dst, src[0]);
+          }
+          __threadfence();
+          __syncwarp();
+          if (lane == 0) st_release_u32(prog + i, (k + 1 == nt) ? 0x7fffffffu : (unsigned)(k + 1));
+        }
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0) s_prog[w] = (k + 1 == nt) ? 0x7fffffff : (k + 1);
+        __syncwarp();
+      }
+      if (!ok) {
+        if (lane == 0) s_prog[w] = 0x7fffffff;       // let the others run into their own time-outs / abort flag
+      }
     }
   }
 }
@@ -782,7 +977,7 @@ static SbrWs sbr_layout(double* ws, long N, size_t* total) {
   SbrWs w;
   w.npanel = sbr_npanel(N);
   w.ntask_max = (N + B - 1) / B + 1;
-  w.max_split = 8;
+  w.max_split = 16;
   w.max_qr_ctas = (int)((N + QR_THREADS - 1) / QR_THREADS);
   size_t off = 0;
   auto take = [&](size_t cnt) {
@@ -867,7 +1062,7 @@ static int sbr_stage1(double* A, long N, const SbrWs& w, cudaStream_t st) {
     // 1b: X = A22 V, split over K so that the grid fills the machine
     const int row_tiles = (int)((N + XR - 1) / XR - r0 / XR);        // absolute tiles that reach rows >= r0
     const int total_chunks = (int)((N + XKB - 1) / XKB - r0 / XKB);
-    int nsplit = (2 * 148 + row_tiles - 1) / row_tiles;
+    int nsplit = (4 * 148 + row_tiles - 1) / row_tiles;          // two CTAs per SM, two waves
     if (nsplit > w.max_split) nsplit = w.max_split;
     int cps = (total_chunks + nsplit - 1) / nsplit;
     cps = ((cps + 7) / 8) * 8;                               // whole 128-column blocks per split
@@ -910,20 +1105,33 @@ static int sbr_stage2(long N, const SbrWs& w, double* d, double* e, cudaStream_t
   PODSDF_CUDA(cudaMemsetAsync(w.bar + 2, 0, sizeof(unsigned) * (size_t)(N + 2), st));
   const long nsweep = N - 2;
   if (nsweep > 0) {
-    int dev = 0, sms = 148, per_sm = 1;
+    int dev = 0, sms = 148;
     PODSDF_CUDA(cudaGetDevice(&dev));
     PODSDF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    PODSDF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sbr_chase_kernel, 32, 0));
-    long G = (long)sms * (per_sm < 4 ? per_sm : 4);          // all chains co-resident (cooperative launch checks it)
-    const long useful = (N + 2 * B - 1) / (2 * B) + 8;       // sweeps that can be in flight at once
-    if (G > useful) G = useful;
-    if (G > nsweep) G = nsweep;
     double* Bb = w.Bb;
     long Narg = N, ntm = w.ntask_max;
     double *V2 = w.V2, *TAU2 = w.TAU2;
     unsigned* bar = w.bar;
     void* args[] = {&Bb, &Narg, &V2, &TAU2, &ntm, &bar};
-    PODSDF_CUDA(cudaLaunchCooperativeKernel((const void*)sbr_chase_kernel, dim3((unsigned)G), dim3(32), args, 0, st));
+    const char* variant = getenv("PODSDF_CHASE");               // "2": experimental CTA-pipelined kernel (A/B only)
+    if (!(variant && atoi(variant) == 2)) {
+      int per_sm = 1;
+      PODSDF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sbr_chase_kernel, 32, 0));
+      long G = (long)sms * (per_sm < 4 ? per_sm : 4);           // all chains co-resident (cooperative launch checks it)
+      const long useful = (N + 2 * B - 1) / (2 * B) + 8;        // sweeps that can be in flight at once
+      if (G > useful) G = useful;
+      if (G > nsweep) G = nsweep;
+      PODSDF_CUDA(cudaLaunchCooperativeKernel((const void*)sbr_chase_kernel, dim3((unsigned)G), dim3(32), args, 0, st));
+    } else {
+      PODSDF_CUDA(cudaFuncSetAttribute(sbr_chase_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHASE_SMEM));
+      long G = sms;                                             // one CTA per SM (the ring takes the shared memory)
+      const long useful = ((N + 2 * B - 1) / (2 * B) + 8 + CG - 1) / CG + 1;
+      const long bundles = (nsweep + CG - 1) / CG;
+      if (G > useful) G = useful;
+      if (G > bundles) G = bundles;
+      PODSDF_CUDA(cudaLaunchCooperativeKernel((const void*)sbr_chase_multi_kernel, dim3((unsigned)G), dim3(32 * CG), args,
+                                              CHASE_SMEM, st));
+    }
     count_launch();
   }
   sbr_band_to_tridiag_kernel<<<ceil_div(N, 256L), 256, 0, st>>>(w.Bb, N, d, e);

@@ -139,10 +139,12 @@ def pod_resident(A, M, N, layout, nm, dt, et, device_index=0, group=None, timers
     # all eigenvalues + the leading vectors only (rows 0.. of C, descending): PODFS never reads the other N - nm
     # eigenvectors (POD:1329-1333); nm < 0 ("keep every valid mode") needs them all
     n_vec = N if nm < 0 else min(int(nm), N)
+    route_val = 0                        # 1 = this library's own tridiagonal route, 0 = full library eigen-solver
     if n_vec < N:
         import ctypes
         route = ctypes.c_int(0)
         _capi.check(L.podsdf_eig_sym_top_dev(device_index, C.data_ptr(), N, n_vec, lam.data_ptr(), ctypes.byref(route), st))
+        route_val = int(route.value)
         lead = C[:n_vec].cpu().numpy()                   # one copy of the leading rows instead of one per mode
         vec = lambda j: lead[N - 1 - j]                  # ascending index j -> row of the descending list
     else:
@@ -171,7 +173,7 @@ def pod_resident(A, M, N, layout, nm, dt, et, device_index=0, group=None, timers
         names = ["mean", "gram", "eig", "select_project", "dft"]
         for i, name in enumerate(names):
             timers[name] = timers.get(name, 0.0) + marks[i].elapsed_time(marks[i + 1])
-    return dict(mean=mean, energy=energy, nm=nm, T=T, Phi=Phi, c128=c128, c_ind=c_ind, c_count=c_count)
+    return dict(mean=mean, energy=energy, nm=nm, T=T, Phi=Phi, c128=c128, c_ind=c_ind, c_count=c_count, route=route_val)
 
 
 # ----------------------------------------------------------------------------- DF -> PODFS
