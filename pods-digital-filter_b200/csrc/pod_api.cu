@@ -432,7 +432,7 @@ int podsdf_dft_modes_dev(int device, const double* a_dev, long N, long ld, int n
   DeviceGuard guard(device);
   cudaStream_t st = (cudaStream_t)stream;
   DevBuf tw;
-  PODSDF_CUDA(tw.alloc(sizeof(double) * 2 * (size_t)N));
+  PODSDF_CUDA(tw.alloc(sizeof(double) * dft_workspace_doubles(N, nm)));
   int rc = launch_dft(a_dev, N, ld, nm, tw.p, c_dev, st);
   cudaError_t e = cudaStreamSynchronize(st);  // twiddle table is freed on return
   if (!rc && e != cudaSuccess) rc = cuda_fail(e, "dft", __FILE__, __LINE__);

@@ -12,7 +12,9 @@ int launch_gram(const double* A, long M, long N, int layout, const double* w, lo
 // Phi[M][nm] = scale * (A . T[:, :nm]) . diag(dinv)
 int launch_project(const double* A, long M, long N, int layout, const double* T, long ldT, const double* dinv,
                    int nm, double scale, double* Phi, cudaStream_t st);
-// c[N][nm] complex128 = fftshift-ordered DFT of the first nm columns of a (N x ld); tw_ws: 2*N doubles
+// c[N][nm] complex128 = fftshift-ordered DFT of the first nm columns of a (N x ld); tw_ws: dft_workspace_doubles
+// (twiddle table + the intermediate of the two-factor transform)
+size_t dft_workspace_doubles(long N, int nm);
 int launch_dft(const double* a, long N, long ld, int nm, double* tw_ws, double* c, cudaStream_t st);
 int launch_mean_rows(double* A, long M, long N, int layout, double* mean, int subtract, cudaStream_t st);
 int launch_transpose(const double* in, double* out, long n, cudaStream_t st);

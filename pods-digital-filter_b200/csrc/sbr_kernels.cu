@@ -89,7 +89,7 @@ __device__ __forceinline__ bool grid_barrier(unsigned* counter, unsigned* err, u
 //   Partials go through part[phase & 1][cta][B]; every CTA sums them in the same order -> identical values.
 // Outputs: R (upper triangle) back into A, V rows c0 .. c0+B-1 of Vall (explicit ones / zeros), T (B x B, row-major).
 // ------------------------------------------------------------------------------------------------
-constexpr int QR_THREADS = 512;
+constexpr int QR_THREADS = 256;    // 8 warps: the row + the reduction tree need ~170 registers per thread
 
 __global__ void __launch_bounds__(QR_THREADS, 1)
 sbr_panel_qr_kernel(double* __restrict__ A, const long N, const int c0, double* __restrict__ Vall,
@@ -114,8 +114,16 @@ sbr_panel_qr_kernel(double* __restrict__ A, const long N, const int c0, double* 
     for (int e = tid; e < B * (B + 1); e += QR_THREADS) (&s_T[0][0])[e] = 0.0;
 
   unsigned phase = 0;
+#ifdef PODSDF_CHASE_PROFILE
+  long long qc[4] = {0, 0, 0, 0};
+  long long qlast = clock64();
+#define QCLK(n) { const long long t_ = clock64(); qc[n] += t_ - qlast; qlast = t_; }
+#else
+#define QCLK(n)
+#endif
 #pragma unroll 1
   for (int j = 0; j <= B; ++j) {
+    QCLK(3)
     // p[j] and p[j-1] without dynamic register indexing
     double pj = 0.0, pjm1 = 0.0;
 #pragma unroll
@@ -127,12 +135,31 @@ sbr_panel_qr_kernel(double* __restrict__ A, const long N, const int c0, double* 
     // slots i < j-1: V[r][i] v_{j-1}[r] over rows >= j-1 (T factor of the column finished in the previous step)
     const double fa = (j < B && active && row > j) ? pj : 0.0;
     const double fb = (j >= 1 && active) ? ((row > j - 1) ? pjm1 : (row == j - 1 ? 1.0 : 0.0)) : 0.0;
+    // 32 sums over the 32 lanes of a warp by recursive halving: 31 double shuffles per lane instead of 160 (the
+    // shuffle unit moves one warp per clock per SM: 16 warps x 320 SHFL was the whole phase, r02_sbr_profile.md).
+    // After the five rounds lane l holds the total of slot l.
+    {
+      double a[B / 2];
+      auto term = [&](int m) { return (m >= j) ? fa * p[m] : ((m < j - 1) ? fb * p[m] : 0.0); };
+      {                                            // first round straight from the products: 16 live values
+        const bool up = (lane & (B / 2)) != 0;
 #pragma unroll
-    for (int m = 0; m < B; ++m) {
-      double v = (m >= j) ? fa * p[m] : ((m < j - 1) ? fb * p[m] : 0.0);
+        for (int q = 0; q < B / 2; ++q) {
+          const double lo = term(q), hi = term(q + B / 2);
+          a[q] = (up ? hi : lo) + __shfl_xor_sync(0xffffffffu, up ? lo : hi, B / 2);
+        }
+      }
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (lane == 0) s_red[warp][m] = v;
+      for (int half = B / 4; half >= 1; half >>= 1) {
+        const bool up = (lane & half) != 0;
+#pragma unroll
+        for (int q = 0; q < half; ++q) {
+          const double send = up ? a[q] : a[q + half];
+          const double keep = up ? a[q + half] : a[q];
+          a[q] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+        }
+      }
+      s_red[warp][lane] = a[0];
     }
     __syncthreads();
     if (tid < B) {
@@ -145,22 +172,23 @@ sbr_panel_qr_kernel(double* __restrict__ A, const long N, const int c0, double* 
 #pragma unroll
       for (int m = 0; m < B; ++m) __stcg(rowj + (j & 1) * B + m, p[m]);
     }
+    QCLK(0)
     if (!grid_barrier(counter, err, ++phase)) return;
+    QCLK(1)
     // ---- phase B: everyone sums the partials in the same order
     {
-      // all threads fetch (L2: other CTAs' data) -- one round trip per QR_THREADS / B CTAs -- then B threads add
-      // them up in CTA order, the same order everywhere
+      // all threads fetch (L2: other CTAs' data) in one round trip, then B threads add the partial sums up -- in
+      // the same order in every CTA, so everybody derives identical reflectors
       double rj = 0.0, v = 0.0;
       if (tid < B && j < B) rj = __ldcg(rowj + (j & 1) * B + tid);
-      for (int g0 = 0; g0 < G; g0 += QR_THREADS / B) {
-        const int g2 = g0 + tid / B;
-        s_part[tid] = (g2 < G) ? __ldcg(part + ((long)(j & 1) * G + g2) * B + (tid % B)) : 0.0;
-        __syncthreads();
-        if (tid < B) {
-          const int cnt = min(QR_THREADS / B, G - g0);
-          for (int q = 0; q < cnt; ++q) v += s_part[q * B + tid];
-        }
-        __syncthreads();
+      double acc = 0.0;                              // thread (q, m) adds CTAs q, q + 8, ... : one round trip
+      for (int g2 = tid / B; g2 < G; g2 += QR_THREADS / B)
+        acc += __ldcg(part + ((long)(j & 1) * G + g2) * B + (tid % B));
+      s_part[tid] = acc;
+      __syncthreads();
+      if (tid < B) {
+#pragma unroll
+        for (int q = 0; q < QR_THREADS / B; ++q) v += s_part[q * B + tid];
       }
       if (tid < B) {
         s_S[tid] = v;
@@ -197,7 +225,13 @@ sbr_panel_qr_kernel(double* __restrict__ A, const long N, const int c0, double* 
       }
     }
     __syncthreads();
+    QCLK(2)
   }
+#ifdef PODSDF_CHASE_PROFILE
+  if (tid == 0 && cta == 0 && (c0 == 0 || c0 == 4992))
+    printf("qr c0 %d G %d: cycles per column: phaseA %lld, barrier %lld, phaseB %lld, loop %lld\n", c0, G, qc[0] / (B + 1),
+           qc[1] / (B + 1), qc[2] / (B + 1), qc[3] / (B + 1));
+#endif
   // ---- write back: R (rows < B, upper triangle incl. diagonal) into A; V (unit lower trapezoid) into Vall
   if (active) {
 #pragma unroll
@@ -637,11 +671,154 @@ sbr_chase_kernel(double* __restrict__ Bb, const long N, double* __restrict__ V2,
       }
       v = v2;
       tau = tau2;
-      // ---- publish progress (the stores above must be visible first)
-      __threadfence();
+      // ---- publish progress.  The warp barrier orders every lane's stores before lane 0's release store
+      // (cumulativity), so one fence -- the one inside st.release.gpu -- is enough: an explicit __threadfence()
+      // here cost another 1.5 us per task (profiles/r02_sbr_profile.md)
       __syncwarp();
       if (lane == 0) st_release_u32(prog + i, (k + 1 == nt) ? 0x7fffffffu : (unsigned)(k + 1));
       __syncwarp();
+      PCLK(3)
+#ifdef PODSDF_CHASE_PROFILE
+      ++ptasks;
+#endif
+    }
+  }
+#ifdef PODSDF_CHASE_PROFILE
+  if (lane == 0 && (blockIdx.x == 0 || blockIdx.x == 7 || blockIdx.x == gridDim.x - 1))
+    printf("chase cta %d: tasks %lld, cycles per task: wait %lld, load %lld, compute %lld, store+fence+publish %lld, loop %lld\n",
+           blockIdx.x, ptasks, pc[0] / ptasks, pc[1] / ptasks, pc[2] / ptasks, pc[3] / ptasks, pc[4] / ptasks);
+#endif
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stage 2, two warps per task.  A lone warp runs the ~2000 instructions of a task at IPC ~0.4, and the task time
+// IS the critical path (profiles/r02_sbr_profile.md: load 0.5 us, compute 2.7 us, store + release 3 us per task).
+// D <- H D H and the E chain (E <- E H, new reflector, E <- H' E) only share the incoming reflector and touch
+// disjoint band entries, so warp 1 takes D and warp 0 (the owner of the reflector chain) takes E; each warp
+// copies in half of the columns and writes back its own entries.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(64)
+sbr_chase2_kernel(double* __restrict__ Bb, const long N, double* __restrict__ V2, double* __restrict__ TAU2,
+                  const long ntask_max, unsigned* __restrict__ bar) {
+  __shared__ __align__(16) double sB[B][LDB];
+  __shared__ double sv[B], sqE[B], sqD[B];
+  __shared__ double s_tau;
+  __shared__ int s_ok;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned* err = bar + 1;
+  unsigned* prog = bar + 2;
+  const long nsweep = N - 2;
+  for (long i = blockIdx.x; i < nsweep; i += gridDim.x) {
+    const int nt = (int)((N - 1 - i + B - 1) / B);
+    double v = 0.0, tau = 0.0;                       // warp 0: reflector of the current task (lane = row inside J_k)
+    for (int k = 0; k < nt; ++k) {
+      // ---- dependency: sweep i-1 has finished task k+1
+      if (threadIdx.x == 0) {
+        int ok = 1;
+        if (i > 0) {
+          const unsigned need = (unsigned)(k + 2);
+          unsigned spins = 0;
+          while (ld_acquire_u32(prog + i - 1) < need) {
+            if (++spins > (1u << 22)) {
+              if ((spins & 0xFFFFu) == 0 && ld_acquire_u32(err) != 0) { ok = 0; break; }
+              if (spins > (1u << 27)) { atomicExch(err, 2u); ok = 0; break; }
+            }
+          }
+        }
+        s_ok = ok;
+      }
+      __syncthreads();
+      if (!s_ok) return;
+      const long j0 = i + 1 + (long)k * B;
+      const int L = (int)min((long)B, N - j0);
+      const int L2 = (int)max(0L, min((long)B, N - j0 - B));
+      // ---- fetch band columns j0 .. j0+L-1 (zero-filled beyond), half per warp
+#pragma unroll
+      for (int cc = 0; cc < B / 2; ++cc) {
+        const int c = warp * (B / 2) + cc;
+        cpa16_cg(&sB[c][2 * lane], Bb + (j0 + c) * LDB + 2 * lane, c < L);
+      }
+      cpa_commit();
+      if (warp == 0) {
+        if (k == 0) {                                // reflector of column i (overlaps the copies)
+          const double x = (lane < L) ? __ldcg(Bb + i * LDB + 1 + lane) : 0.0;
+          double beta;
+          warp_house(x, lane, v, tau, beta);
+          if (lane < L) __stcg(Bb + i * LDB + 1 + lane, lane == 0 ? beta : 0.0);
+        }
+        if (lane >= L) v = 0.0;
+        if (lane < L) V2[i * N + j0 + lane] = v;
+        if (lane == 0) {
+          TAU2[i * ntask_max + k] = tau;
+          s_tau = tau;
+        }
+        sv[lane] = v;
+      }
+      cpa_wait<0>();
+      __syncthreads();
+      if (warp == 1) {
+        // ---- D <- H D H, H = I - tau v v^T: p = tau D v, q = p - (tau/2)(p^T v) v, D -= v q^T + q v^T
+        const double tD = s_tau, vD = sv[lane];
+        double pp[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int c = 0; c < B; ++c) {
+          const int idx = (c <= lane) ? c * LDB + lane - c : lane * LDB + c - lane;
+          pp[c & 3] = fma((&sB[0][0])[idx], sv[c], pp[c & 3]);
+        }
+        const double pl = tD * ((pp[0] + pp[1]) + (pp[2] + pp[3]));
+        const double kk = 0.5 * tD * warp_sum(pl * vD);
+        const double ql = fma(-kk, vD, pl);
+        sqD[lane] = ql;
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < B; ++c)
+          if (c <= lane) sB[c][lane - c] -= fma(vD, sqD[c], ql * sv[c]);     // lower part: every entry once
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < B; ++c) {                // write back column c, d in [0, L - c)
+          const int len = L - c, d0 = 2 * lane;
+          double* dst = Bb + (j0 + c) * LDB + d0;
+          if (d0 + 1 < len) __stcg(reinterpret_cast<double2*>(dst), make_double2(sB[c][d0], sB[c][d0 + 1]));
+          else if (d0 < len) __stcg(dst, sB[c][d0]);
+        }
+      } else {
+        double v2 = 0.0, tau2 = 0.0;
+        if (L2 > 0) {
+          // ---- E <- E H (lane = row a of E)
+          double yy[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+          for (int c = 0; c < B; ++c) yy[c & 3] = fma(sB[c][B - c + lane], sv[c], yy[c & 3]);
+          const double yl = tau * ((yy[0] + yy[1]) + (yy[2] + yy[3]));
+#pragma unroll
+          for (int c = 0; c < B; ++c) sB[c][B - c + lane] = fma(-yl, sv[c], sB[c][B - c + lane]);
+          __syncwarp();
+          double beta2;
+          warp_house(lane < L2 ? sB[0][B + lane] : 0.0, lane, v2, tau2, beta2);
+          if (lane >= L2) v2 = 0.0;
+          sqE[lane] = v2;
+          __syncwarp();
+          // ---- E <- H2 E: z_c = tau2 v2^T E[:, c] (lane = column c), then lane = row a again
+          double zz[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+          for (int a2 = 0; a2 < B; ++a2) zz[a2 & 3] = fma(sqE[a2], sB[lane][B - lane + a2], zz[a2 & 3]);
+          const double zl = tau2 * ((zz[0] + zz[1]) + (zz[2] + zz[3]));
+          __syncwarp();
+          sqE[lane] = zl;
+          __syncwarp();
+#pragma unroll
+          for (int c = 0; c < B; ++c) sB[c][B - c + lane] = fma(-v2, sqE[c], sB[c][B - c + lane]);
+          sB[0][B + lane] = (lane == 0) ? beta2 : 0.0;       // exactly (beta, 0, ..., 0)
+          __syncwarp();
+#pragma unroll
+          for (int c = 0; c < B; ++c)                // write back column c, d = B - c + a
+            if (c < L && lane < L2) __stcg(Bb + (j0 + c) * LDB + B - c + lane, sB[c][B - c + lane]);
+        }
+        v = v2;
+        tau = tau2;
+      }
+      // ---- publish progress: the CTA barrier orders both warps' stores before thread 0's release store
+      __syncthreads();
+      if (threadIdx.x == 0) st_release_u32(prog + i, (k + 1 == nt) ? 0x7fffffffu : (unsigned)(k + 1));
     }
   }
 }
@@ -1113,15 +1290,20 @@ static int sbr_stage2(long N, const SbrWs& w, double* d, double* e, cudaStream_t
     double *V2 = w.V2, *TAU2 = w.TAU2;
     unsigned* bar = w.bar;
     void* args[] = {&Bb, &Narg, &V2, &TAU2, &ntm, &bar};
-    const char* variant = getenv("PODSDF_CHASE");               // "2": experimental CTA-pipelined kernel (A/B only)
-    if (!(variant && atoi(variant) == 2)) {
+    // PODSDF_CHASE (A/B only): "1" = one warp per task, "2" = experimental CTA-pipelined kernel; default: two warps per task
+    const char* variant = getenv("PODSDF_CHASE");
+    const int var = variant ? atoi(variant) : 0;
+    if (var != 2) {
+      const void* kern = (var == 1) ? (const void*)sbr_chase_kernel : (const void*)sbr_chase2_kernel;
+      const int threads = (var == 1) ? 32 : 64;
       int per_sm = 1;
-      PODSDF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sbr_chase_kernel, 32, 0));
+      if (var == 1) PODSDF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sbr_chase_kernel, 32, 0));
+      else PODSDF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sbr_chase2_kernel, 64, 0));
       long G = (long)sms * (per_sm < 4 ? per_sm : 4);           // all chains co-resident (cooperative launch checks it)
       const long useful = (N + 2 * B - 1) / (2 * B) + 8;        // sweeps that can be in flight at once
       if (G > useful) G = useful;
       if (G > nsweep) G = nsweep;
-      PODSDF_CUDA(cudaLaunchCooperativeKernel((const void*)sbr_chase_kernel, dim3((unsigned)G), dim3(32), args, 0, st));
+      PODSDF_CUDA(cudaLaunchCooperativeKernel(kern, dim3((unsigned)G), dim3(threads), args, 0, st));
     } else {
       PODSDF_CUDA(cudaFuncSetAttribute(sbr_chase_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHASE_SMEM));
       long G = sms;                                             // one CTA per SM (the ring takes the shared memory)
