@@ -141,6 +141,11 @@ PODSDF_API int podsdf_gram_host(int device, const double* A_host, long M, long N
                      long P, double scale, double* C_host);
 PODSDF_API int podsdf_gram_dev(int device, const double* A_dev, long M, long N, int layout, const double* w_dev,
                     long P, double scale, double* C_dev, void* stream);
+/* Packed upper triangle of the (exactly symmetric) Gram matrix for the cross-rank all-reduce: N (N + 1) / 2 doubles
+ * instead of N^2 (ref: the sum over spatial rows of POD:1455 split across ranks).  packed[i N - i (i - 1) / 2 + j - i] =
+ * C[i][j], j >= i; unpack writes both triangles. */
+PODSDF_API int podsdf_sym_pack_dev(int device, const double* C_dev, long N, double* packed_dev, void* stream);
+PODSDF_API int podsdf_sym_unpack_dev(int device, const double* packed_dev, long N, double* C_dev, void* stream);
 /* device time (ms) of the last Gram kernel on this thread */
 PODSDF_API int podsdf_gram_last_ms(double* ms);
 
@@ -156,7 +161,7 @@ PODSDF_API int podsdf_eig_sym_host(int device, const double* C_host, long N, dou
  * tridiagonal route ran -- all of it this library's kernels: two-stage reduction (dense -> band -> tridiagonal),
  * multisection / bisection, inverse iteration, back-transformation of the nm vectors, re-orthonormalisation --
  * 0 when the leading eigenvalues were not well separated (relative gap below 1e-7), a residual check failed or the
- * size is unusual (N < 256, N > 28000, 4 nm > N), and the full library solver of podsdf_eig_sym_* ran. */
+ * size is unusual (N < 256, N > 26000, 4 nm > N), and the full library solver of podsdf_eig_sym_* ran. */
 PODSDF_API int podsdf_eig_sym_top_dev(int device, double* C_dev_inout_V, long N, int nm, double* lambda_dev, int* path,
                            void* stream);
 PODSDF_API int podsdf_eig_sym_top_host(int device, const double* C_host, long N, int nm, double* lambda_host,
@@ -184,7 +189,19 @@ PODSDF_API int podsdf_dft_modes_host(int device, const double* a_host, long N, l
 PODSDF_API int podsdf_dft_modes_dev(int device, const double* a_dev, long N, long ld, int nm, double* c_dev,
                          void* stream);
 
-/* ref: the PODFS reconstruction of docs/usage/CFDCodeIntegration.rst:85-91 is a "next" row. */
+/* One- and two-point statistics of a three-component field held as a snapshot matrix (M = 3 P rows, N samples, either
+ * layout): what a-posteriori checks of the PODFS reconstruction U~(x,t) of docs/usage/CFDCodeIntegration.rst:85-91
+ * (the reference's plot-only y2, POD:1602-1612) and of the generated inlet itself compare -- the mean profile and
+ * Reynolds stresses the Lund transform prescribes (DF:143-178) and the two-point correlations the filter imposes
+ * (DF:73-89).  mean_dev[3][P]; stress_dev[6][P] = uu, vv, ww, uv, uw, vw (central moments over the N samples). */
+PODSDF_API int podsdf_field_moments_dev(int device, const double* F_dev, long P, long N, int layout, double* mean_dev,
+                             double* stress_dev, void* stream);
+/* cov_host[l] = < a'(t, j, k) a'(t + dt_l, j + dj_l, k + dk_l) > over all valid (t, j, k) of component comp (0..2) of
+ * the J x K plane; lags3_host[nl][3] = (dt, dj, dk) >= 0, nl <= 16; mean_dev (3 P doubles) is subtracted first (NULL:
+ * the field is already mean-free).  Synchronous (the result lands on the host). */
+PODSDF_API int podsdf_lag_covariance_dev(int device, const double* F_dev, long J, long K, long N, int layout,
+                              const double* mean_dev, int comp, const int* lags3_host, int nl, double* cov_host,
+                              void* stream);
 
 #ifdef __cplusplus
 }

@@ -56,11 +56,15 @@ SIGNATURES = {
     "podsdf_gram_host": [_i, _vp, _l, _l, _i, _vp, _l, _d, _vp],
     "podsdf_gram_dev": [_i, _vp, _l, _l, _i, _vp, _l, _d, _vp, _vp],
     "podsdf_gram_last_ms": [_vp],
+    "podsdf_sym_pack_dev": [_i, _vp, _l, _vp, _vp],
+    "podsdf_sym_unpack_dev": [_i, _vp, _l, _vp, _vp],
     "podsdf_eig_sym_host": [_i, _vp, _l, _vp, _vp],
     "podsdf_eig_sym_top_dev": [_i, _vp, _l, _i, _vp, ctypes.POINTER(_i), _vp],
     "podsdf_eig_sym_top_host": [_i, _vp, _l, _i, _vp, _vp, ctypes.POINTER(_i)],
     "podsdf_eig_sym_dev": [_i, _vp, _l, _vp, _vp],
     "podsdf_sym_tridiag_host": [_i, _vp, _l, _vp, _vp, _vp, _vp],
+    "podsdf_field_moments_dev": [_i, _vp, _l, _l, _i, _vp, _vp, _vp],
+    "podsdf_lag_covariance_dev": [_i, _vp, _l, _l, _l, _i, _vp, _i, _vp, _i, _vp, _vp],
     "podsdf_project_host": [_i, _vp, _l, _l, _i, _vp, _l, _vp, _i, _d, _vp],
     "podsdf_project_dev": [_i, _vp, _l, _l, _i, _vp, _l, _vp, _i, _d, _vp, _vp],
     "podsdf_dft_modes_host": [_i, _vp, _l, _l, _i, _vp],

@@ -114,134 +114,181 @@ tridiag_sect_kernel(const double* __restrict__ d, const double* __restrict__ e2,
   if (gl == 0) lam[k] = 0.5 * (lo + hi);
 }
 
-// Inverse iteration for the nm largest eigenvalues.  Thread j owns vector j (eigenvalue lam[N-1-j]); its seven
-// work arrays are separate [i][j] planes (consecutive threads touch consecutive doubles, and the compiler may
-// hoist the loads of an unrolled stretch above the serial recurrence because no plane is read after it is written
-// inside one sweep).  Z[j][i] (row-major nm x N) receives the unit eigenvector of T;
+// Inverse iteration for the nm largest eigenvalues.  CTA j owns vector j (eigenvalue lam[N-1-j]): LU of T - lambda I
+// with partial pivoting as in LAPACK dlagtf / dlagts, three solves, residual reported.  The recurrences are serial in i,
+// so ONE thread runs them -- out of shared memory: the CTA streams the operands of 512 steps in (coalesced), thread 0
+// walks the chunk at register / shared-memory latency, the CTA streams the results out.  (Round 1 ran one thread per
+// vector straight on global memory: 19 ms at N = 10^4, nm = 100; the arithmetic alone is ~1 ms.)
+// Work arrays: seven planes [vector][i].  Z[j][i] (row-major nm x N) receives the unit eigenvector of T;
 // resid[j] = |T z - lambda z|_inf / |T|.
-__global__ void __launch_bounds__(32)
+constexpr int IV_CH = 512, IV_THREADS = 128;
+
+__global__ void __launch_bounds__(IV_THREADS)
 tridiag_invit_kernel(const double* __restrict__ d, const double* __restrict__ e, const double* __restrict__ bounds,
                      const double* __restrict__ lam, const long N, const int nm, double* __restrict__ wP,
                      double* __restrict__ wQ, double* __restrict__ wR, double* __restrict__ wM, double* __restrict__ wS,
                      double* __restrict__ wX, double* __restrict__ wY, double* __restrict__ Z, double* __restrict__ resid) {
-  const int j = blockIdx.x * 32 + threadIdx.x;
+  __shared__ double si[4][IV_CH + 2];                // chunk inputs
+  __shared__ double so[5][IV_CH];                    // chunk outputs
+  __shared__ double s_red[IV_THREADS];
+  __shared__ double s_carry[4];                      // recurrence state between chunks (thread 0 only)
+  const int j = blockIdx.x, tid = threadIdx.x;
   if (j >= nm) return;
   const double tnorm = fmax(bounds[3], DBL_MIN);
   const double floor_p = DBL_EPSILON * tnorm;
   const double l = lam[N - 1 - j];
-  const long st = nm;                                    // stride between consecutive i of one plane
-  wP += j; wQ += j; wR += j; wM += j; wS += j; wX += j; wY += j;
-  // Every sweep below is a serial recurrence over i whose operands do not depend on the recurrence: they are
-  // fetched U steps at a time into registers first, so one memory latency is paid per U steps instead of per step.
-  constexpr int U = 8;
-  // ---- LU of (T - l I) with partial pivoting: row i of U = (P[i], Q[i], R[i]), multiplier M[i], swap flag S[i]
-  double p = __ldg(d) - l, q = (N > 1) ? __ldg(e) : 0.0;
-  for (long i0 = 0; i0 + 1 < N; i0 += U) {
-    double cc[U], aa[U], bb[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const long i = i0 + u;
-      const bool ok = i + 1 < N;
-      cc[u] = ok ? __ldg(e + i) : 0.0;                   // sub-diagonal entry of row i+1
-      aa[u] = ok ? __ldg(d + i + 1) - l : 0.0;
-      bb[u] = (i + 2 < N) ? __ldg(e + i + 1) : 0.0;
+  const long off = (long)j * N;
+  wP += off; wQ += off; wR += off; wM += off; wS += off; wX += off; wY += off;
+
+  // ---- LU of (T - l I): row i of U = (P[i], Q[i], R[i]), multiplier M[i], swap flag S[i]
+  if (tid == 0) {
+    s_carry[0] = d[0] - l;
+    s_carry[1] = (N > 1) ? e[0] : 0.0;
+  }
+  for (long i0 = 0; i0 + 1 < N; i0 += IV_CH) {
+    const int cnt = (int)min((long)IV_CH, N - 1 - i0);            // steps i0 .. i0+cnt-1 (each needs row i+1)
+    __syncthreads();
+    for (int t = tid; t < cnt + 1; t += IV_THREADS) {
+      const long i = i0 + t;
+      si[0][t] = (i < N - 1) ? e[i] : 0.0;                        // sub-diagonal entry of row i+1
+      si[1][t] = (i + 1 < N) ? d[i + 1] - l : 0.0;
+      si[2][t] = (i + 2 < N) ? e[i + 1] : 0.0;
     }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const long i = i0 + u;
-      if (i + 1 < N) {
-        const double c = cc[u], a1 = aa[u], b1 = bb[u];
+    __syncthreads();
+    if (tid == 0) {
+      double p = s_carry[0], q = s_carry[1];
+#pragma unroll 4
+      for (int t = 0; t < cnt; ++t) {
+        const double c = si[0][t], a1 = si[1][t], b1 = si[2][t];
         if (fabs(p) >= fabs(c)) {
           if (fabs(p) < floor_p) p = copysign(floor_p, p);
           const double m = c / p;
-          wP[i * st] = p; wQ[i * st] = q; wR[i * st] = 0.0; wM[i * st] = m; wS[i * st] = 0.0;
+          so[0][t] = p; so[1][t] = q; so[2][t] = 0.0; so[3][t] = m; so[4][t] = 0.0;
           p = a1 - m * q;
           q = b1;
         } else {
           const double m = p / c;
-          wP[i * st] = c; wQ[i * st] = a1; wR[i * st] = b1; wM[i * st] = m; wS[i * st] = 1.0;
+          so[0][t] = c; so[1][t] = a1; so[2][t] = b1; so[3][t] = m; so[4][t] = 1.0;
           p = q - m * a1;
           q = -m * b1;
         }
       }
+      s_carry[0] = p;
+      s_carry[1] = q;
+    }
+    __syncthreads();
+    for (int t = tid; t < cnt; t += IV_THREADS) {
+      const long i = i0 + t;
+      wP[i] = so[0][t]; wQ[i] = so[1][t]; wR[i] = so[2][t]; wM[i] = so[3][t]; wS[i] = so[4][t];
     }
   }
-  if (fabs(p) < floor_p) p = copysign(floor_p, p);
-  wP[(N - 1) * st] = p; wQ[(N - 1) * st] = 0.0; wR[(N - 1) * st] = 0.0;
+  __syncthreads();
+  if (tid == 0) {
+    double p = s_carry[0];
+    if (fabs(p) < floor_p) p = copysign(floor_p, p);
+    wP[N - 1] = p; wQ[N - 1] = 0.0; wR[N - 1] = 0.0;
+  }
   // ---- start vector: a fixed pseudo-random pattern per (i, j)
-  for (long i = 0; i < N; ++i) {
+  for (long i = tid; i < N; i += IV_THREADS) {
     unsigned h = (unsigned)(i * 2654435761u) ^ (unsigned)(j * 40503u + 12345u);
     h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
-    wX[i * st] = ((double)(h & 0xFFFFF) + 0.5) / 1048576.0 - 0.5;
+    wX[i] = ((double)(h & 0xFFFFF) + 0.5) / 1048576.0 - 0.5;
   }
+  __syncthreads();
   for (int iter = 0; iter < 3; ++iter) {
-    // forward sweep X -> Y: apply the row operations to the right-hand side (y carried in a register)
-    double y = wX[0];
-    for (long i0 = 0; i0 + 1 < N; i0 += U) {
-      double xs[U], ss[U], ms[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const long i = i0 + u;
-        const bool ok = i + 1 < N;
-        xs[u] = ok ? wX[(i + 1) * st] : 0.0;
-        ss[u] = ok ? wS[i * st] : 0.0;
-        ms[u] = ok ? wM[i * st] : 0.0;
+    // ---- forward sweep X -> Y: apply the row operations to the right-hand side (y carried between chunks)
+    if (tid == 0) s_carry[0] = wX[0];
+    for (long i0 = 0; i0 + 1 < N; i0 += IV_CH) {
+      const int cnt = (int)min((long)IV_CH, N - 1 - i0);
+      __syncthreads();
+      for (int t = tid; t < cnt; t += IV_THREADS) {
+        const long i = i0 + t;
+        si[0][t] = wX[i + 1];
+        si[1][t] = wS[i];
+        si[2][t] = wM[i];
       }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const long i = i0 + u;
-        if (i + 1 < N) {
-          double y1 = xs[u];
-          if (ss[u] != 0.0) { const double t = y; y = y1; y1 = t; }
-          y1 -= ms[u] * y;
-          wY[i * st] = y;
+      __syncthreads();
+      if (tid == 0) {
+        double y = s_carry[0];
+#pragma unroll 4
+        for (int t = 0; t < cnt; ++t) {
+          double y1 = si[0][t];
+          if (si[1][t] != 0.0) { const double tmp = y; y = y1; y1 = tmp; }
+          y1 -= si[2][t] * y;
+          so[0][t] = y;
           y = y1;
         }
+        s_carry[0] = y;
       }
+      __syncthreads();
+      for (int t = tid; t < cnt; t += IV_THREADS) wY[i0 + t] = so[0][t];
     }
-    wY[(N - 1) * st] = y;
-    // back substitution Y -> X with two super-diagonals
-    double x1 = 0.0, x2 = 0.0, big = 0.0;
-    for (long i0 = N - 1; i0 >= 0; i0 -= U) {
-      double ys[U], qs[U], rs[U], ps[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const long i = i0 - u;
-        const bool ok = i >= 0;
-        ys[u] = ok ? wY[i * st] : 0.0;
-        qs[u] = ok ? wQ[i * st] : 0.0;
-        rs[u] = ok ? wR[i * st] : 0.0;
-        ps[u] = ok ? wP[i * st] : 1.0;
+    __syncthreads();
+    if (tid == 0) {
+      wY[N - 1] = s_carry[0];
+      s_carry[0] = 0.0;   // x1
+      s_carry[1] = 0.0;   // x2
+      s_carry[2] = 0.0;   // big
+    }
+    // ---- back substitution Y -> X with two super-diagonals (descending chunks)
+    for (long hi = N; hi > 0; hi -= IV_CH) {
+      const long lo = max(0L, hi - IV_CH);
+      const int cnt = (int)(hi - lo);
+      __syncthreads();
+      for (int t = tid; t < cnt; t += IV_THREADS) {
+        const long i = lo + t;
+        si[0][t] = wY[i];
+        si[1][t] = wQ[i];
+        si[2][t] = wR[i];
+        si[3][t] = wP[i];
       }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const long i = i0 - u;
-        if (i >= 0) {
-          const double x0 = (ys[u] - qs[u] * x1 - rs[u] * x2) / ps[u];
-          wX[i * st] = x0;
+      __syncthreads();
+      if (tid == 0) {
+        double x1 = s_carry[0], x2 = s_carry[1], big = s_carry[2];
+#pragma unroll 4
+        for (int t = cnt - 1; t >= 0; --t) {
+          const double x0 = (si[0][t] - si[1][t] * x1 - si[2][t] * x2) / si[3][t];
+          so[0][t] = x0;
           big = fmax(big, fabs(x0));
           x2 = x1;
           x1 = x0;
         }
+        s_carry[0] = x1; s_carry[1] = x2; s_carry[2] = big;
       }
+      __syncthreads();
+      for (int t = tid; t < cnt; t += IV_THREADS) wX[lo + t] = so[0][t];
     }
-    const double s = 1.0 / fmax(big, DBL_MIN);
-    for (long i = 0; i < N; ++i) wX[i * st] *= s;
+    __syncthreads();
+    const double sc = 1.0 / fmax(s_carry[2], DBL_MIN);
+    for (long i = tid; i < N; i += IV_THREADS) wX[i] *= sc;
+    __syncthreads();
   }
   // ---- unit 2-norm, residual, write the row of Z
   double ss = 0.0;
-  for (long i = 0; i < N; ++i) ss = fma(wX[i * st], wX[i * st], ss);
-  const double s = 1.0 / sqrt(ss);
-  double r = 0.0, xm = 0.0, x0 = wX[0] * s;
-  for (long i = 0; i < N; ++i) {
-    const double xp = (i + 1 < N) ? wX[(i + 1) * st] * s : 0.0;
+  for (long i = tid; i < N; i += IV_THREADS) ss = fma(wX[i], wX[i], ss);
+  s_red[tid] = ss;
+  __syncthreads();
+  for (int st = IV_THREADS / 2; st > 0; st >>= 1) {
+    if (tid < st) s_red[tid] += s_red[tid + st];
+    __syncthreads();
+  }
+  const double sn = 1.0 / sqrt(s_red[0]);
+  __syncthreads();
+  double r = 0.0;
+  for (long i = tid; i < N; i += IV_THREADS) {
+    const double x0 = wX[i] * sn;
+    const double xm = (i > 0) ? wX[i - 1] * sn : 0.0, xp = (i + 1 < N) ? wX[i + 1] * sn : 0.0;
     const double t = ((i > 0) ? __ldg(e + i - 1) * xm : 0.0) + (__ldg(d + i) - l) * x0 + ((i + 1 < N) ? __ldg(e + i) * xp : 0.0);
     r = fmax(r, fabs(t));
     Z[(long)j * N + i] = x0;
-    xm = x0;
-    x0 = xp;
   }
-  resid[j] = r / tnorm;
+  s_red[tid] = r;
+  __syncthreads();
+  for (int st = IV_THREADS / 2; st > 0; st >>= 1) {
+    if (tid < st) s_red[tid] = fmax(s_red[tid], s_red[tid + st]);
+    __syncthreads();
+  }
+  if (tid == 0) resid[j] = s_red[0] / tnorm;
 }
 
 // S[a][b] = <Z_a, Z_b>
@@ -341,7 +388,7 @@ size_t tridiag_invit_workspace_doubles(long N, int nm) { return (size_t)7 * N * 
 int launch_tridiag_invit(const double* d, const double* e, const double* bounds, const double* lam, long N, int nm,
                          double* ws, double* Z, double* resid, cudaStream_t st) {
   const size_t pl = (size_t)N * nm;
-  tridiag_invit_kernel<<<(unsigned)ceil_div(nm, 32), 32, 0, st>>>(d, e, bounds, lam, N, nm, ws, ws + pl, ws + 2 * pl, ws + 3 * pl,
+  tridiag_invit_kernel<<<(unsigned)nm, IV_THREADS, 0, st>>>(d, e, bounds, lam, N, nm, ws, ws + pl, ws + 2 * pl, ws + 3 * pl,
                                                                   ws + 4 * pl, ws + 5 * pl, ws + 6 * pl, Z, resid);
   count_launch();
   PODSDF_CUDA(cudaGetLastError());

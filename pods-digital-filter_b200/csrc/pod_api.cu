@@ -151,7 +151,7 @@ int eig_top_inplace(int device, double* C_dev, long N, int nm, double* lambda_de
   if (nm < 1 || nm > N) return fail(PODSDF_ERR_INVALID, "nm must be in 1..N");
   std::lock_guard<std::recursive_mutex> lk(g_solver_mu);
   const char* force = getenv("PODSDF_EIG_ROUTE");
-  const bool eligible = N >= 256 && N <= 28000 && nm <= 512 && 4L * nm <= N && !(force && atoi(force) == 0);
+  const bool eligible = N >= 256 && N <= 26000 && nm <= 512 && 4L * nm <= N && !(force && atoi(force) == 0);
   // scratch: [C copy | Z nm*N | d | e | e2 | bounds 8 | resid nm | S nm*nm | flag | invit | sbr workspace]
   const size_t nn = (size_t)N * N, zn = (size_t)nm * N;
   const size_t invit = eligible ? tridiag_invit_workspace_doubles(N, nm) : 0;
@@ -395,6 +395,45 @@ int podsdf_sym_tridiag_host(int device, const double* C_host, long N, double* d_
   }
   PODSDF_CUDA(cudaMemcpy(d_host, de.p, sizeof(double) * (size_t)N, cudaMemcpyDeviceToHost));
   PODSDF_CUDA(cudaMemcpy(e_host, de.p + N, sizeof(double) * (size_t)(N - 1), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int podsdf_sym_pack_dev(int device, const double* C_dev, long N, double* packed_dev, void* stream) {
+  if (!C_dev || !packed_dev || N < 1 || N > 65535) return fail(PODSDF_ERR_INVALID, "bad argument");
+  PODSDF_TRY(check_device(device));
+  DeviceGuard guard(device);
+  return launch_sym_pack(C_dev, N, packed_dev, (cudaStream_t)stream);
+}
+
+int podsdf_sym_unpack_dev(int device, const double* packed_dev, long N, double* C_dev, void* stream) {
+  if (!C_dev || !packed_dev || N < 1 || N > 65535) return fail(PODSDF_ERR_INVALID, "bad argument");
+  PODSDF_TRY(check_device(device));
+  DeviceGuard guard(device);
+  return launch_sym_unpack(packed_dev, N, C_dev, (cudaStream_t)stream);
+}
+
+int podsdf_field_moments_dev(int device, const double* F_dev, long P, long N, int layout, double* mean_dev,
+                             double* stress_dev, void* stream) {
+  if (!F_dev || !mean_dev || !stress_dev || P < 1 || N < 1 || (layout != 0 && layout != 1))
+    return fail(PODSDF_ERR_INVALID, "bad argument");
+  PODSDF_TRY(check_device(device));
+  DeviceGuard guard(device);
+  return launch_field_moments(F_dev, P, N, layout, mean_dev, stress_dev, (cudaStream_t)stream);
+}
+
+int podsdf_lag_covariance_dev(int device, const double* F_dev, long J, long K, long N, int layout, const double* mean_dev,
+                              int comp, const int* lags3_host, int nl, double* cov_host, void* stream) {
+  if (!F_dev || !lags3_host || !cov_host || J < 1 || K < 1 || N < 1 || comp < 0 || comp > 2 || (layout != 0 && layout != 1))
+    return fail(PODSDF_ERR_INVALID, "bad argument");
+  PODSDF_TRY(check_device(device));
+  DeviceGuard guard(device);
+  DevBuf ws;
+  PODSDF_CUDA(ws.alloc(sizeof(double) * lag_covariance_workspace_doubles()));
+  double* out = ws.p + lag_covariance_workspace_doubles() - lag_covariance_max();
+  cudaStream_t st = (cudaStream_t)stream;
+  PODSDF_TRY(launch_lag_covariance(F_dev, J, K, N, layout, mean_dev, comp, lags3_host, nl, ws.p, out, st));
+  PODSDF_CUDA(cudaMemcpyAsync(cov_host, out, sizeof(double) * nl, cudaMemcpyDeviceToHost, st));
+  PODSDF_CUDA(cudaStreamSynchronize(st));
   return 0;
 }
 

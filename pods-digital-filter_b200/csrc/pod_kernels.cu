@@ -14,6 +14,8 @@
 // every fragment load of a half-warp hit 16 distinct 8-byte banks.
 #include "pod_kernels.cuh"
 
+#include <algorithm>
+
 namespace podsdf {
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, const double a, const double b) {
@@ -545,6 +547,172 @@ int launch_mean_rows(double* A, long M, long N, int layout, double* mean, int su
     mean_rows_l0_kernel<<<ceil_div(M, 8), 256, 0, st>>>(A, M, N, mean, subtract);
   else
     mean_rows_l1_kernel<<<ceil_div(M, 256), 256, 0, st>>>(A, M, N, mean, subtract);
+  count_launch();
+  PODSDF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// One- and two-point statistics of a three-component field given as a snapshot matrix (a-posteriori
+// checks of the PODFS reconstruction, docs/usage/CFDCodeIntegration.rst:85-91; the same moments the Lund transform
+// prescribes, digitalfilters.py:143-178).
+//   moments: mean[c][p] and the six second central moments uu, vv, ww, uv, uw, vw per point, accumulated about
+//            the first sample (no cancellation between U ~ 1 and u' ~ 0.02).
+//   lag covariance: <a'(t, j, k) a'(t + dt, j + dj, k + dk)> over all valid (t, j, k) of one component.
+// ------------------------------------------------------------------------------------------------
+template <int LAYOUT>
+__global__ void __launch_bounds__(128)
+field_moments_kernel(const double* __restrict__ F, const long P, const long N, double* __restrict__ mean,
+                     double* __restrict__ stress) {
+  // LAYOUT 1 (f[t][c*P + p]): thread = point, consecutive threads read consecutive doubles
+  // LAYOUT 0 (F[c*P + p][t]): warp = point, lanes stride over time
+  const int lane = threadIdx.x & 31;
+  const long p = (LAYOUT == 1) ? blockIdx.x * 128L + threadIdx.x : blockIdx.x * 4L + (threadIdx.x >> 5);
+  if (p >= P) return;
+  auto at = [&](int c, long t) { return (LAYOUT == 1) ? F[t * 3 * P + c * P + p] : F[(c * P + p) * N + t]; };
+  const double k0 = at(0, 0), k1 = at(1, 0), k2 = at(2, 0);
+  double s[3] = {0, 0, 0}, q[6] = {0, 0, 0, 0, 0, 0};
+  for (long t = (LAYOUT == 1) ? 0 : lane; t < N; t += (LAYOUT == 1) ? 1 : 32) {
+    const double a = at(0, t) - k0, b = at(1, t) - k1, c = at(2, t) - k2;
+    s[0] += a; s[1] += b; s[2] += c;
+    q[0] = fma(a, a, q[0]); q[1] = fma(b, b, q[1]); q[2] = fma(c, c, q[2]);
+    q[3] = fma(a, b, q[3]); q[4] = fma(a, c, q[4]); q[5] = fma(b, c, q[5]);
+  }
+  if (LAYOUT == 0) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) s[i] += __shfl_xor_sync(0xffffffffu, s[i], o);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) q[i] += __shfl_xor_sync(0xffffffffu, q[i], o);
+    }
+    if (lane != 0) return;
+  }
+  const double inv = 1.0 / (double)N;
+  const double m0 = s[0] * inv, m1 = s[1] * inv, m2 = s[2] * inv;
+  mean[p] = k0 + m0; mean[P + p] = k1 + m1; mean[2 * P + p] = k2 + m2;
+  stress[p] = q[0] * inv - m0 * m0;
+  stress[P + p] = q[1] * inv - m1 * m1;
+  stress[2 * P + p] = q[2] * inv - m2 * m2;
+  stress[3 * P + p] = q[3] * inv - m0 * m1;
+  stress[4 * P + p] = q[4] * inv - m0 * m2;
+  stress[5 * P + p] = q[5] * inv - m1 * m2;
+}
+
+int launch_field_moments(const double* F, long P, long N, int layout, double* mean, double* stress, cudaStream_t st) {
+  if (layout == 1) field_moments_kernel<1><<<ceil_div(P, 128L), 128, 0, st>>>(F, P, N, mean, stress);
+  else field_moments_kernel<0><<<ceil_div(P, 4L), 128, 0, st>>>(F, P, N, mean, stress);
+  count_launch();
+  PODSDF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+constexpr int LAGC_MAX = 16;
+struct LagList {
+  int dt[LAGC_MAX], dj[LAGC_MAX], dk[LAGC_MAX];
+  int n;
+};
+
+// partial[block][lag] = sum over this block's (t, j, k) of a'(t,j,k) a'(t+dt, j+dj, k+dk); counts are analytic
+template <int LAYOUT>
+__global__ void __launch_bounds__(256)
+lag_covariance_kernel(const double* __restrict__ F, const double* __restrict__ mean, const long J, const long K,
+                      const long N, const int comp, const LagList lags, double* __restrict__ partial) {
+  __shared__ double red[256];
+  const long P = J * K;
+  const long total = N * P;
+  double acc[LAGC_MAX];
+#pragma unroll
+  for (int l = 0; l < LAGC_MAX; ++l) acc[l] = 0.0;
+  auto val = [&](long t, long p) {
+    const double m = mean ? mean[comp * P + p] : 0.0;
+    return ((LAYOUT == 1) ? F[t * 3 * P + comp * P + p] : F[(comp * P + p) * N + t]) - m;
+  };
+  for (long e = blockIdx.x * 256L + threadIdx.x; e < total; e += (long)gridDim.x * 256) {
+    const long t = (LAYOUT == 1) ? e / P : e % N;          // the contiguous index varies fastest across threads
+    const long p = (LAYOUT == 1) ? e % P : e / N;
+    const long j = p / K, k = p % K;
+    const double a = val(t, p);
+#pragma unroll
+    for (int l = 0; l < LAGC_MAX; ++l) {
+      if (l < lags.n) {
+        const long t2 = t + lags.dt[l], j2 = j + lags.dj[l], k2 = k + lags.dk[l];
+        if (t2 < N && j2 < J && k2 < K) acc[l] = fma(a, val(t2, j2 * K + k2), acc[l]);
+      }
+    }
+  }
+  for (int l = 0; l < lags.n; ++l) {
+    red[threadIdx.x] = acc[l];
+    __syncthreads();
+    for (int s2 = 128; s2 > 0; s2 >>= 1) {
+      if ((int)threadIdx.x < s2) red[threadIdx.x] += red[threadIdx.x + s2];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[(long)blockIdx.x * LAGC_MAX + l] = red[0];
+    __syncthreads();
+  }
+}
+
+__global__ void lag_covariance_final_kernel(const double* __restrict__ partial, const int nblocks, const LagList lags,
+                                            const long J, const long K, const long N, double* __restrict__ out) {
+  const int l = threadIdx.x;
+  if (l >= lags.n) return;
+  double sacc = 0.0;
+  for (int b = 0; b < nblocks; ++b) sacc += partial[(long)b * LAGC_MAX + l];       // fixed order
+  const double cnt = (double)(N - lags.dt[l]) * (double)(J - lags.dj[l]) * (double)(K - lags.dk[l]);
+  out[l] = cnt > 0.0 ? sacc / cnt : 0.0;
+}
+
+int lag_covariance_max() { return LAGC_MAX; }
+size_t lag_covariance_workspace_doubles() { return (size_t)1184 * LAGC_MAX + LAGC_MAX; }
+
+int launch_lag_covariance(const double* F, long J, long K, long N, int layout, const double* mean, int comp,
+                          const int* lags3, int nl, double* ws, double* out_dev, cudaStream_t st) {
+  if (nl < 1 || nl > LAGC_MAX) return fail(PODSDF_ERR_INVALID, "1..16 lags per call");
+  LagList ll;
+  ll.n = nl;
+  for (int l = 0; l < LAGC_MAX; ++l) {
+    ll.dt[l] = l < nl ? lags3[3 * l] : 0;
+    ll.dj[l] = l < nl ? lags3[3 * l + 1] : 0;
+    ll.dk[l] = l < nl ? lags3[3 * l + 2] : 0;
+    if (ll.dt[l] < 0 || ll.dj[l] < 0 || ll.dk[l] < 0) return fail(PODSDF_ERR_INVALID, "lags must be non-negative");
+  }
+  const long total = N * J * K;
+  int nblocks = (int)std::min<long>(1184, ceil_div(total, 256L));    // 148 SMs x 8
+  if (layout == 1) lag_covariance_kernel<1><<<nblocks, 256, 0, st>>>(F, mean, J, K, N, comp, ll, ws);
+  else lag_covariance_kernel<0><<<nblocks, 256, 0, st>>>(F, mean, J, K, N, comp, ll, ws);
+  lag_covariance_final_kernel<<<1, 32, 0, st>>>(ws, nblocks, ll, J, K, N, out_dev);
+  count_launch(2);
+  PODSDF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// Packed upper triangle of a symmetric N x N matrix (row-major rows i, columns j >= i): the all-reduce of the
+// per-rank Gram matrices moves N (N + 1) / 2 doubles instead of N^2.
+__global__ void __launch_bounds__(256)
+sym_pack_kernel(const double* __restrict__ C, const long N, double* __restrict__ packed, const int unpack,
+                double* __restrict__ Cout) {
+  const long i = blockIdx.y;
+  const long j = i + blockIdx.x * 256L + threadIdx.x;
+  if (j >= N) return;
+  const long off = i * N - i * (i - 1) / 2 + (j - i);     // rows 0..i-1 hold N, N-1, ..., N-i+1 entries
+  if (!unpack) {
+    packed[off] = C[i * N + j];
+  } else {
+    const double v = packed[off];
+    Cout[i * N + j] = v;
+    Cout[j * N + i] = v;
+  }
+}
+
+int launch_sym_pack(const double* C, long N, double* packed, cudaStream_t st) {
+  sym_pack_kernel<<<dim3((unsigned)ceil_div(N, 256L), (unsigned)N), 256, 0, st>>>(C, N, packed, 0, nullptr);
+  count_launch();
+  PODSDF_CUDA(cudaGetLastError());
+  return 0;
+}
+int launch_sym_unpack(const double* packed, long N, double* C, cudaStream_t st) {
+  sym_pack_kernel<<<dim3((unsigned)ceil_div(N, 256L), (unsigned)N), 256, 0, st>>>(nullptr, N, const_cast<double*>(packed), 1, C);
   count_launch();
   PODSDF_CUDA(cudaGetLastError());
   return 0;

@@ -377,19 +377,43 @@ sbr_w1_kernel(const double* __restrict__ Xp, const int nsplit, const double* __r
   }
 }
 
-// Stage 1d: Z = sum Zp;  S = T^T Z T;  W = X T - 1/2 V S   (every CTA recomputes the 32 x 32 products)
+// Stage 1d: Z = sum Zp;  S = T^T Z T  (one CTA: 1024 threads, one entry each; the partials are read coalesced)
+__global__ void __launch_bounds__(B * B)
+sbr_s_kernel(const double* __restrict__ T, const double* __restrict__ Zp, const int nz, double* __restrict__ S) {
+  __shared__ double sT[B][B + 1], sZ[B][B + 1], sU[B][B + 1];
+  const int e = threadIdx.x, a = e / B, c = e % B;
+  double z0 = 0.0, z1 = 0.0, z2 = 0.0, z3 = 0.0;       // four independent streams of loads, fixed order
+  int g2 = 0;
+  for (; g2 + 3 < nz; g2 += 4) {
+    z0 += Zp[(long)g2 * B * B + e];
+    z1 += Zp[(long)(g2 + 1) * B * B + e];
+    z2 += Zp[(long)(g2 + 2) * B * B + e];
+    z3 += Zp[(long)(g2 + 3) * B * B + e];
+  }
+  for (; g2 < nz; ++g2) z0 += Zp[(long)g2 * B * B + e];
+  sZ[a][c] = (z0 + z1) + (z2 + z3);
+  sT[a][c] = T[e];
+  __syncthreads();
+  double acc = 0.0;                                    // U = Z T (T upper triangular)
+  for (int l = 0; l <= c; ++l) acc = fma(sZ[a][l], sT[l][c], acc);
+  sU[a][c] = acc;
+  __syncthreads();
+  acc = 0.0;                                           // S = T^T U
+  for (int l = 0; l <= a; ++l) acc = fma(sT[l][a], sU[l][c], acc);
+  S[e] = acc;
+}
+
+// Stage 1d': W = X T - 1/2 V S
 __global__ void __launch_bounds__(256)
 sbr_w2_kernel(const double* __restrict__ X, const double* __restrict__ V, const double* __restrict__ T,
-              const double* __restrict__ Zp, const int nz, const long N, const long r0, double* __restrict__ W) {
-  __shared__ double sT[B][B + 1], sZ[B][B + 1], sU[B][B + 1];      // sZ: Z, later S
+              const double* __restrict__ S, const long N, const long r0, double* __restrict__ W) {
+  __shared__ double sT[B][B + 1], sS[B][B + 1];
   __shared__ double sV[B][WR2 + 1], sX[B][WR2 + 1];
   const long n = N - r0;
   const long row0 = (long)blockIdx.x * WR2;
   const int tid = threadIdx.x;
   for (int e = tid; e < B * B; e += 256) {
-    double z = 0.0;
-    for (int g2 = 0; g2 < nz; ++g2) z += Zp[(long)g2 * B * B + e];
-    sZ[e / B][e % B] = z;
+    sS[e / B][e % B] = S[e];
     sT[e / B][e % B] = T[e];
   }
   for (int e = tid; e < B * WR2; e += 256) {
@@ -399,20 +423,6 @@ sbr_w2_kernel(const double* __restrict__ X, const double* __restrict__ V, const 
     sV[m][r] = ok ? V[(long)m * N + r0 + row0 + r] : 0.0;
   }
   __syncthreads();
-  for (int e = tid; e < B * B; e += 256) {                    // U = Z T
-    const int a = e / B, c = e % B;
-    double acc = 0.0;
-    for (int l = 0; l <= c; ++l) acc = fma(sZ[a][l], sT[l][c], acc);     // T upper triangular
-    sU[a][c] = acc;
-  }
-  __syncthreads();
-  for (int e = tid; e < B * B; e += 256) {                    // S = T^T U  (into sZ)
-    const int a = e / B, c = e % B;
-    double acc = 0.0;
-    for (int l = 0; l <= a; ++l) acc = fma(sT[l][a], sU[l][c], acc);
-    sZ[a][c] = acc;
-  }
-  __syncthreads();
   for (int e = tid; e < B * WR2; e += 256) {
     const int m = e / WR2, r = e % WR2;
     if (row0 + r < n) {
@@ -420,7 +430,7 @@ sbr_w2_kernel(const double* __restrict__ X, const double* __restrict__ V, const 
       for (int l = 0; l <= m; ++l) acc = fma(sX[l][r], sT[l][m], acc);
       double acc2 = 0.0;
 #pragma unroll 8
-      for (int l = 0; l < B; ++l) acc2 = fma(sV[l][r], sZ[l][m], acc2);
+      for (int l = 0; l < B; ++l) acc2 = fma(sV[l][r], sS[l][m], acc2);
       W[(long)m * N + r0 + row0 + r] = fma(-0.5, acc2, acc);
     }
   }
@@ -1022,34 +1032,108 @@ sbr_band_to_tridiag_kernel(const double* __restrict__ Bb, const long N, double* 
 constexpr int BT_THREADS = 512;
 constexpr int Q2_THREADS = 1024;
 
-// Q2: one eigenvector per CTA (the work per sweep is a handful of 32-element reflectors: latency, not throughput)
+// Q2: one eigenvector per CTA, held in shared memory.  The reflectors of one sweep act on disjoint 32-element
+// ranges, so each is applied by ONE THREAD (32 multiply-adds for the dot product, 32 for the update, no shuffles:
+// with a warp per reflector the shuffle unit -- one warp-instruction per clock and SM -- was the bottleneck,
+// profiles/r02_sbr_profile.md).  Both arrays are stored with one pad per 32 entries: the threads of a warp work
+// on ranges 32 entries apart, i.e. 33 words apart, conflict-free for every sweep offset.  The reflectors of sweep
+// i-1 are fetched (coalesced) into registers while sweep i is applied and parked in shared memory afterwards.
+template <int MAXPF>
 __global__ void __launch_bounds__(Q2_THREADS, 1)
 sbr_back_q2_kernel(const double* __restrict__ V2, const double* __restrict__ TAU2, const long ntask_max, const long N,
                    double* __restrict__ Z) {
-  extern __shared__ double zs[];                     // [N]
+  extern __shared__ double smem_q2[];
+  const long NP = N + N / 32 + 2;                    // padded length
+  double* zs = smem_q2;                              // z[e] at zs[e + e/32]
+  double* vs = smem_q2 + NP;                         // reflector entry for row e at vs[e + e/32]
+  const int tid = threadIdx.x;
+  double* z = Z + (long)blockIdx.x * N;
+  for (long r = tid; r < N; r += Q2_THREADS) zs[r + (r >> 5)] = z[r];
+  double pf[MAXPF];
+  auto fetch = [&](long i) {                         // entries i+1 .. N-1 of row i of V2, coalesced
+#pragma unroll
+    for (int q = 0; q < MAXPF; ++q) {
+      const long e = i + 1 + tid + (long)q * Q2_THREADS;
+      pf[q] = (e < N) ? __ldg(V2 + i * N + e) : 0.0;
+    }
+  };
+  auto park = [&](long i) {
+#pragma unroll
+    for (int q = 0; q < MAXPF; ++q) {
+      const long e = i + 1 + tid + (long)q * Q2_THREADS;
+      if (e < N) vs[e + (e >> 5)] = pf[q];
+    }
+  };
+  if (N >= 3) {
+    fetch(N - 3);
+    park(N - 3);
+  }
+  __syncthreads();
+  for (long i = N - 3; i >= 0; --i) {
+    if (i > 0) fetch(i - 1);
+    const int nt = (int)((N - 1 - i + B - 1) / B);
+    for (int k = tid; k < nt; k += Q2_THREADS) {     // one reflector per thread
+      const long e0 = i + 1 + (long)k * B;
+      const int len = (int)min((long)B, N - e0);
+      const double tau = __ldg(TAU2 + i * ntask_max + k);
+      double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
+#pragma unroll 8
+      for (int j = 0; j < B; j += 4) {
+        const long ea = e0 + j;
+        if (j + 3 < len) {
+          d0 = fma(vs[ea + (ea >> 5)], zs[ea + (ea >> 5)], d0);
+          d1 = fma(vs[ea + 1 + ((ea + 1) >> 5)], zs[ea + 1 + ((ea + 1) >> 5)], d1);
+          d2 = fma(vs[ea + 2 + ((ea + 2) >> 5)], zs[ea + 2 + ((ea + 2) >> 5)], d2);
+          d3 = fma(vs[ea + 3 + ((ea + 3) >> 5)], zs[ea + 3 + ((ea + 3) >> 5)], d3);
+        } else {
+          for (int jj = j; jj < len; ++jj) {
+            const long eb = e0 + jj;
+            d0 = fma(vs[eb + (eb >> 5)], zs[eb + (eb >> 5)], d0);
+          }
+        }
+      }
+      const double s = -tau * ((d0 + d1) + (d2 + d3));
+#pragma unroll 8
+      for (int j = 0; j < B; ++j) {
+        if (j < len) {
+          const long eb = e0 + j;
+          zs[eb + (eb >> 5)] = fma(s, vs[eb + (eb >> 5)], zs[eb + (eb >> 5)]);
+        }
+      }
+    }
+    __syncthreads();                                 // sweep i applied; its reflectors are no longer needed
+    if (i > 0) park(i - 1);
+    __syncthreads();
+  }
+  for (long r = tid; r < N; r += Q2_THREADS) z[r] = zs[r + (r >> 5)];
+}
+
+// Q2 for vectors too long for the layout above (two padded arrays): only z in shared memory, one warp per reflector
+__global__ void __launch_bounds__(Q2_THREADS, 1)
+sbr_back_q2_long_kernel(const double* __restrict__ V2, const double* __restrict__ TAU2, const long ntask_max,
+                        const long N, double* __restrict__ Z) {
+  extern __shared__ double smem_q2[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NW = Q2_THREADS / 32;
   double* z = Z + (long)blockIdx.x * N;
-  for (long r = tid; r < N; r += Q2_THREADS) zs[r] = z[r];
+  for (long r = tid; r < N; r += Q2_THREADS) smem_q2[r] = z[r];
   __syncthreads();
   for (long i = N - 3; i >= 0; --i) {
     const int nt = (int)((N - 1 - i + B - 1) / B);
-    const double* vrow = V2 + i * N + i + 1;
-    const double* trow = TAU2 + i * ntask_max;
-    double* zz = zs + i + 1;
+    double* zz = smem_q2 + i + 1;
 #pragma unroll 2
     for (int k = warp; k < nt; k += NW) {
       const long o = (long)k * B + lane;
       const bool in = i + 1 + o < N;
-      const double v = in ? __ldg(vrow + o) : 0.0;
-      const double tau = __ldg(trow + k);
+      const double v = in ? __ldg(V2 + i * N + i + 1 + o) : 0.0;
+      const double tau = __ldg(TAU2 + i * ntask_max + k);
       const double x = in ? zz[o] : 0.0;
       const double dot = warp_sum(v * x);
       if (in) zz[o] = fma(-tau * dot, v, x);
     }
     __syncthreads();
   }
-  for (long r = tid; r < N; r += Q2_THREADS) z[r] = zs[r];
+  for (long r = tid; r < N; r += Q2_THREADS) z[r] = smem_q2[r];
 }
 
 // Q1: NV eigenvectors per CTA share every read of the panel reflectors
@@ -1138,7 +1222,7 @@ sbr_back_q1_kernel(const double* __restrict__ Vall, const double* __restrict__ T
 // workspace layout
 // ------------------------------------------------------------------------------------------------
 struct SbrWs {
-  double *Vall, *Tall, *W, *X, *Xp, *Zp, *part, *rowj, *Bb, *V2, *TAU2;
+  double *Vall, *Tall, *W, *X, *Xp, *Zp, *S, *part, *rowj, *Bb, *V2, *TAU2;
   unsigned* bar;      // [0] barrier counter, [1] error flag, [2..] sweep progress (N)
   long npanel, ntask_max;
   int max_split, max_qr_ctas;
@@ -1168,6 +1252,7 @@ static SbrWs sbr_layout(double* ws, long N, size_t* total) {
   w.X = take((size_t)B * N);
   w.Xp = take((size_t)w.max_split * B * N);
   w.Zp = take((size_t)((N + WR - 1) / WR) * B * B);
+  w.S = take((size_t)B * B);
   w.part = take((size_t)2 * w.max_qr_ctas * B);
   w.rowj = take((size_t)2 * B);
   w.Bb = take((size_t)N * LDB);
@@ -1248,8 +1333,9 @@ static int sbr_stage1(double* A, long N, const SbrWs& w, cudaStream_t st) {
     // 1c / 1d: W
     const int wct = (int)((n + WR - 1) / WR);
     sbr_w1_kernel<<<wct, 256, 0, st>>>(w.Xp, nsplit, Vk, N, r0, w.X, w.Zp);
-    sbr_w2_kernel<<<(int)((n + WR2 - 1) / WR2), 256, 0, st>>>(w.X, Vk, Tk, w.Zp, wct, N, r0, w.W);
-    count_launch(3);
+    sbr_s_kernel<<<1, B * B, 0, st>>>(Tk, w.Zp, wct, w.S);
+    sbr_w2_kernel<<<(int)((n + WR2 - 1) / WR2), 256, 0, st>>>(w.X, Vk, Tk, w.S, N, r0, w.W);
+    count_launch(4);
     // 1e: rank-2b update of the lower tiles.  The first tile column (it contains the next panel) goes first; the
     // next panel's QR -- a latency-bound chain of grid barriers on a few SMs -- then runs on the high-priority
     // stream beside the rest of the update.
@@ -1365,11 +1451,28 @@ int sbr_back_transform(const double* ws, long N, double* Z, int nvec, cudaStream
   int dev = 0, max_smem = 0;
   PODSDF_CUDA(cudaGetDevice(&dev));
   PODSDF_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  const size_t fixed = 48 * 1024;                            // static shared memory of the kernels, generous
+  const size_t fixed = 20 * 1024;                            // static shared memory of the Q1 kernels (17.6 KB at NV = 2)
   if (one + fixed > (size_t)max_smem)
     return fail(PODSDF_ERR_UNSUPPORTED, "back-transformation: one eigenvector does not fit shared memory");
-  PODSDF_CUDA(cudaFuncSetAttribute(sbr_back_q2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)one));
-  sbr_back_q2_kernel<<<nvec, Q2_THREADS, one, st>>>(w.V2, w.TAU2, w.ntask_max, N, Z);
+  {
+    const long pfs = (N + Q2_THREADS - 1) / Q2_THREADS;          // prefetched entries per thread and sweep
+    const size_t q2_smem = sizeof(double) * 2 * (size_t)(N + N / 32 + 2);
+#define PODSDF_Q2(M)                                                                                         \
+  do {                                                                                                       \
+    auto k = sbr_back_q2_kernel<M>;                                                                          \
+    PODSDF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)q2_smem));         \
+    k<<<nvec, Q2_THREADS, q2_smem, st>>>(w.V2, w.TAU2, w.ntask_max, N, Z);                                   \
+  } while (0)
+    if (q2_smem + 2048 > (size_t)max_smem || pfs > 14) {
+      if (one + 2048 > (size_t)max_smem)
+        return fail(PODSDF_ERR_UNSUPPORTED, "back-transformation: one eigenvector does not fit shared memory");
+      PODSDF_CUDA(cudaFuncSetAttribute(sbr_back_q2_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)one));
+      sbr_back_q2_long_kernel<<<nvec, Q2_THREADS, one, st>>>(w.V2, w.TAU2, w.ntask_max, N, Z);
+    } else if (pfs <= 4) PODSDF_Q2(4);
+    else if (pfs <= 10) PODSDF_Q2(10);
+    else PODSDF_Q2(14);
+#undef PODSDF_Q2
+  }
   if (2 * one + fixed <= (size_t)max_smem) {
     auto k = sbr_back_q1_kernel<2>;
     PODSDF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * one)));

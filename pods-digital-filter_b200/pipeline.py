@@ -86,11 +86,25 @@ class DfShard(object):
 
 
 # ------------------------------------------------------------------------------------ POD
-def allreduce_gram(C, group=None):
-    """Sum of the per-rank N x N partial Gram matrices (float64) on every rank."""
+def allreduce_gram(C, group=None, device_index=None):
+    """Sum of the per-rank N x N partial Gram matrices (float64) on every rank.  On GPUs the exactly symmetric partials
+    travel as their packed upper triangle -- N (N + 1) / 2 doubles instead of N^2 -- through
+    podsdf_sym_pack_dev / _unpack_dev; CPU tensors (gloo unit tests) are reduced in full."""
+    import torch
     import torch.distributed as dist
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.all_reduce(C, op=dist.ReduceOp.SUM, group=group)
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
+        return C
+    if C.is_cuda and C.dim() == 2 and C.shape[0] == C.shape[1] and C.is_contiguous() and C.shape[0] <= 65535:
+        N = C.shape[0]
+        L = _capi.lib()
+        di = C.device.index if device_index is None else device_index
+        st = torch.cuda.current_stream(C.device).cuda_stream
+        packed = torch.empty(N * (N + 1) // 2, dtype=torch.float64, device=C.device)
+        _capi.check(L.podsdf_sym_pack_dev(di, C.data_ptr(), N, packed.data_ptr(), st))
+        dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
+        _capi.check(L.podsdf_sym_unpack_dev(di, packed.data_ptr(), N, C.data_ptr(), st))
+        return C
+    dist.all_reduce(C, op=dist.ReduceOp.SUM, group=group)
     return C
 
 
@@ -281,3 +295,67 @@ def reconstruct_field(Phi, mean, y2, device_index=0):
                                      Nt, 1.0, U.data_ptr(), st))
     U += mean[:, None]
     return U
+
+
+# ------------------------------------------------------------- one- / two-point statistics
+def field_moments(F, P, N, layout, device_index=0):
+    """mean (3, P) and central second moments (6, P) = uu, vv, ww, uv, uw, vw of a three-component field held on the
+    device as a snapshot matrix (layout 0: rows-by-time, 1: time-by-rows).  CUDA tensors back."""
+    import torch
+    L = _capi.lib()
+    dev = F.device
+    mean = torch.empty((3, P), dtype=torch.float64, device=dev)
+    stress = torch.empty((6, P), dtype=torch.float64, device=dev)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    _capi.check(L.podsdf_field_moments_dev(device_index, F.data_ptr(), P, N, layout, mean.data_ptr(), stress.data_ptr(), st))
+    return mean, stress
+
+
+def lag_covariance(F, J, K, N, layout, comp, lags, mean=None, device_index=0):
+    """< a'(t,j,k) a'(t+dt,j+dj,k+dk) > of component `comp` for every (dt, dj, dk) in `lags` (any number; sent in groups
+    of 16).  `mean` (3, J*K) CUDA tensor or None for a mean-free field.  Returns a numpy vector."""
+    import ctypes
+    import torch
+    L = _capi.lib()
+    lags = np.ascontiguousarray(np.asarray(lags, dtype=np.int32).reshape(-1, 3))
+    out = np.empty(lags.shape[0])
+    st = torch.cuda.current_stream(F.device).cuda_stream
+    for a in range(0, lags.shape[0], 16):
+        blk = np.ascontiguousarray(lags[a:a + 16])
+        res = np.empty(blk.shape[0])
+        _capi.check(L.podsdf_lag_covariance_dev(device_index, F.data_ptr(), J, K, N, layout,
+                                                None if mean is None else mean.data_ptr(), int(comp),
+                                                blk.ctypes.data_as(ctypes.c_void_p), blk.shape[0],
+                                                res.ctypes.data_as(ctypes.c_void_p), st))
+        out[a:a + blk.shape[0]] = res
+    return out
+
+
+def reconstruction_statistics(res, planes, J, K, dt, lags=None, device_index=0):
+    """A-posteriori check of a PODFS compression on the device: rebuild the inlet the CFD solver would
+    see, U~(x, t_j) = mean + sum_i Phi_i(x) a~_i(t_j) with a~_i the truncated Fourier series (docs/usage/
+    CFDCodeIntegration.rst:85-91; the reference's y2, POD:1602-1612), and compare with the generated planes:
+    relative error energy, mean profile, the six Reynolds stresses per point, and two-point covariances of u along
+    time, j and k.  `res` = pod_resident's dict, `planes` (N, 3 J K) the MEAN-REMOVED snapshots on the device in the
+    generator's layout.  Every field-sized operation runs on the device (projection kernel, statistics kernels)."""
+    import torch
+    N = planes.shape[0]
+    P = J * K
+    c64 = res["c128"].astype(np.complex64)
+    y2 = temporal_reconstruction(c64, res["c_ind"], res["c_count"], N * dt, np.arange(N) * dt)      # (N, nm)
+    U = reconstruct_field(res["Phi"], torch.zeros_like(res["mean"]), y2, device_index)              # (3P, N) fluctuation
+    diff = planes.t() - U
+    err = float((diff * diff).sum() / (planes * planes).sum())
+    # error energy the truncation to nm modes alone would leave (exact temporal modes): 1 - sum_{i<nm} lambda_i / sum lambda
+    lam = np.asarray(res["energy"], dtype=np.float64)
+    trunc = float(1.0 - lam[:res["nm"]].sum() / lam[lam > 0].sum())
+    m_ref, s_ref = field_moments(planes, P, N, _capi.LAYOUT_TIME_BY_ROWS, device_index)
+    m_rec, s_rec = field_moments(U, P, N, _capi.LAYOUT_ROWS_BY_TIME, device_index)
+    if lags is None:
+        lags = [(0, 0, 0)] + [(r, 0, 0) for r in (1, 2, 4, 8)] + [(0, r, 0) for r in (1, 2, 4)] + [(0, 0, r) for r in (1, 2, 4)]
+    lags = [tuple(int(v) for v in l) for l in lags if l[0] < N and l[1] < J and l[2] < K]
+    c_ref = lag_covariance(planes, J, K, N, _capi.LAYOUT_TIME_BY_ROWS, 0, lags, None, device_index)
+    c_rec = lag_covariance(U, J, K, N, _capi.LAYOUT_ROWS_BY_TIME, 0, lags, None, device_index)
+    return dict(error_energy=err, truncation_energy=trunc, mean_generated=m_ref, mean_reconstructed=m_rec,
+                stress_generated=s_ref, stress_reconstructed=s_rec, lags=lags, cov_generated=c_ref, cov_reconstructed=c_rec,
+                field=U)

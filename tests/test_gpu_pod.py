@@ -314,3 +314,50 @@ def test_leading_eigenpairs(P, N, nm, kind):
                          np.abs(np.diff(np.r_[np.inf, top]))) / ref[-1]
         dots = np.abs(np.sum(V * full, axis=1))
         assert (1.0 - dots < 1e-12 / np.maximum(gap, 1e-12) ** 2 + 1e-13).all()
+
+
+def test_field_statistics_kernels_and_reconstruction_check(P):
+    """one- and two-point statistics on the device.  (a) the moment and lag-covariance kernels against
+    numpy on a random three-component field, both layouts; (b) `pipeline.reconstruction_statistics` on a generated inlet:
+    with every Fourier coefficient kept (et = 1) the reconstruction error equals the energy of the discarded POD modes,
+    and the Reynolds stresses / two-point covariances of the reconstruction approach those of the generated field."""
+    torch = pytest.importorskip("torch")
+    pipeline, capi = P.pipeline, P._capi
+    rs = np.random.RandomState(11)
+    J, K, N = 7, 9, 40
+    Pn = J * K
+    F = rs.standard_normal((N, 3 * Pn)) * rs.uniform(0.5, 2.0, (1, 3 * Pn)) + rs.uniform(-3, 3, (1, 3 * Pn))
+    F[:, Pn:2 * Pn] += 0.5 * F[:, :Pn]
+    Fd = torch.from_numpy(F).cuda()
+    Ft = torch.from_numpy(np.ascontiguousarray(F.T)).cuda()
+    m = F.mean(0).reshape(3, Pn)
+    a = F.reshape(N, 3, Pn) - m[None]
+    want = np.stack([(a[:, x] * a[:, y]).mean(0) for x, y in ((0, 0), (1, 1), (2, 2), (0, 1), (0, 2), (1, 2))])
+    lags = [(0, 0, 0), (1, 0, 0), (3, 0, 0), (0, 1, 0), (0, 2, 0), (0, 0, 1), (0, 0, 4), (2, 1, 3)] + [(5, 0, 0)] * 10
+    for layout, T in ((1, Fd), (0, Ft)):
+        mean, stress = pipeline.field_moments(T, Pn, N, layout)
+        assert np.abs(mean.cpu().numpy() - m).max() < 1e-13
+        assert np.abs(stress.cpu().numpy() - want).max() < 1e-12
+        for comp in (0, 2):
+            got = pipeline.lag_covariance(T, J, K, N, layout, comp, lags, mean)
+            f = a[:, comp].reshape(N, J, K)
+            ref = [np.mean(f[:N - dt, :J - dj, :K - dk] * f[dt:, dj:, dk:]) for dt, dj, dk in lags]
+            assert np.abs(got - np.array(ref)).max() < 1e-13
+    # (b) a generated inlet through PODFS and back
+    df = P.digitalfilters
+    J = K = 32
+    nf, ln, ns, nm = 4, 2.0, 160, 24
+    U, uu, vv, ww, uw = df.build_profile("hyperbolic-tangent", "top-hat", 1.0, 0.05, K)
+    plan = df._plan(J, K, nf, nf, nf, df._taps(nf, ln), df._taps(nf, ln), df._taps(nf, ln))
+    plan.set_impl(0)
+    plan.set_coefficients(*P._lund.pack(*P._lund.lund_1d(U, uu, vv, ww, uw, J, K), J, K))
+    plan.set_rotation(None)
+    res = pipeline.df_to_podfs(plan, ns, nm, 0.01, 1.0, seed=5)
+    st = pipeline.reconstruction_statistics(res, res["planes"].view(ns, -1), J, K, 0.01)
+    assert abs(st["error_energy"] - st["truncation_energy"]) < 1e-6 * max(st["truncation_energy"], 1e-12) + 1e-9
+    assert 0.0 < st["error_energy"] < 0.9
+    sg, sr = st["stress_generated"].cpu().numpy(), st["stress_reconstructed"].cpu().numpy()
+    assert np.all(sr[:3].sum(1) <= sg[:3].sum(1) * (1 + 1e-12))            # a truncation only removes energy
+    assert np.abs(st["mean_reconstructed"].cpu().numpy()).max() < 1e-12    # fluctuation field: zero mean
+    # covariances: reconstruction variance = generated variance minus the discarded energy (per unit volume)
+    assert abs((st["cov_generated"][0] - st["cov_reconstructed"][0])) <= st["cov_generated"][0]
