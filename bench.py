@@ -384,6 +384,10 @@ def run_multi_gpu(args, pkg, torch, dist, dev, local_rank, rank, world, barrier,
     plan.generate_injected_dev(ext.data_ptr(), ext.shape[0], inj.data_ptr(), st)
     torch.cuda.synchronize(dev)
     inj_err = float((inj - whole[t0:t1]).abs().max() / whole.abs().max())
+    ovl = torch.empty((t1 - t0, 3, J, K), dtype=torch.float64, device=dev)       # halo hidden behind the interior steps
+    pipeline.generate_injected_sharded(plan, own, ovl, rank, world)
+    torch.cuda.synchronize(dev)
+    ovl_ok = bool(torch.equal(ovl, inj))
     # Gram: rows sharded, one all-reduce
     M = 3 * J * K
     a_full = whole.view(ns, M)
@@ -401,14 +405,16 @@ def run_multi_gpu(args, pkg, torch, dist, dev, local_rank, rank, world, barrier,
     a_loc, rows = pipeline.reshard_time_to_rows(mine.view(t1 - t0, M))
     torch.cuda.synchronize(dev)
     resh_ok = bool(torch.equal(a_loc, a_full[:, rows[0]:rows[1]]))
-    flags = torch.tensor([float(shard_ok), float(halo_ok), float(resh_ok), -inj_err, -gram_err], dtype=torch.float64, device=dev)
+    flags = torch.tensor([float(shard_ok), float(halo_ok), float(resh_ok), -inj_err, -gram_err, float(ovl_ok)],
+                         dtype=torch.float64, device=dev)
     dist.all_reduce(flags, op=dist.ReduceOp.MIN)
     out["parity"] = {"case": "64x48x3, nf=4, %d steps, %d ranks" % (ns, world),
                      "generated_shards_bitexact": bool(flags[0] > 0.5), "halo_exchange_bitexact": bool(flags[1] > 0.5),
                      "reshard_all_to_all_bitexact": bool(flags[2] > 0.5),
+                     "overlapped_halo_equals_blocking_bitexact": bool(flags[5] > 0.5),
                      "injected_vs_one_gpu_max_rel": float(-flags[3]), "gram_allreduce_vs_one_gpu_max_rel": float(-flags[4])}
     plan.close()
-    del whole, mine, own, ext, want, inj, C1, Cp, a_rows, a_loc
+    del whole, mine, own, ext, want, inj, ovl, C1, Cp, a_rows, a_loc
     torch.cuda.empty_cache()
     # ---- (b) collectives at config-3 size (512^2 x 3, nf = 10, 2500 planes per GPU)
     c = CFG3

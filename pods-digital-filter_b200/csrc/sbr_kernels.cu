@@ -22,8 +22,12 @@
 // matrices are k-major: V[m*N + r] is entry (r, m).  tools/proto_sbr.py is the numpy model of every step below.
 #include "sbr_kernels.cuh"
 
+#include <cooperative_groups.h>
+
 #include <cfloat>
 #include <cstdlib>
+
+namespace cg = cooperative_groups;
 
 namespace podsdf {
 
@@ -1016,6 +1020,230 @@ sbr_chase_multi_kernel(double* __restrict__ Bb, const long N, double* __restrict
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Stage 2 across a thread-block cluster.  The hand-off between consecutive sweeps is what the critical path is made
+// of (2 N hand-offs; through global memory each costs a release fence over 16 KB of stores, an acquire poll and an L2
+// copy: ~3 us).  Here CC consecutive sweeps run on the CC CTAs of a cluster -- one SM each, so they do not compete
+// for issue slots like the warps of sbr_chase_multi_kernel -- and a sweep hands the band columns of a finished task
+// to the next sweep by writing them straight into that CTA's shared memory (DSMEM) and bumping a counter there with
+// a cluster-scope release; the consumer polls its OWN shared memory.  Only the first sweep of a cluster reads from
+// global memory and only the last one writes back and publishes progress for the next cluster.
+//   every CTA: ring of RB 32-column blocks, slot(c) = c mod (32 RB), 64 doubles per column (the band layout);
+//   s_in   (written by the predecessor): tasks of sweep i-1 whose columns have arrived;
+//   s_credit (written by the successor): tasks of sweep i+1 finished -- the predecessor may run RB - 1 tasks ahead.
+// ------------------------------------------------------------------------------------------------
+constexpr int CC = 8;                    // sweeps (CTAs) per cluster: the portable maximum
+constexpr int RB = 6;                    // ring capacity in blocks of B columns
+constexpr int RCOLS = RB * B;
+constexpr size_t CLUSTER_CHASE_SMEM = (size_t)RCOLS * LDB * sizeof(double);
+
+__device__ __forceinline__ unsigned ld_acquire_cluster_u32(const volatile unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.cluster.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_cluster_u32(unsigned* p, unsigned v) {
+  asm volatile("st.release.cluster.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int rslot(int s2) { return s2 >= RCOLS ? s2 - RCOLS : s2; }
+
+__global__ void __cluster_dims__(CC, 1, 1) __launch_bounds__(64)
+sbr_chase_cluster_kernel(double* __restrict__ Bb, const long N, double* __restrict__ V2, double* __restrict__ TAU2,
+                         const long ntask_max, unsigned* __restrict__ bar) {
+  extern __shared__ __align__(16) double ring[];          // [RCOLS][LDB]
+  __shared__ double sv[B], sqE[B], sqD[B];
+  __shared__ double s_tau;
+  __shared__ int s_ok;
+  __shared__ unsigned s_in, s_credit;
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned r = cluster.block_rank();
+  const long ncl = gridDim.x / CC, cl = blockIdx.x / CC;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned* err = bar + 1;
+  unsigned* prog = bar + 2;
+  const long nsweep = N - 2;
+  double* ring_next = (r + 1 < CC) ? cluster.map_shared_rank(ring, r + 1) : nullptr;
+  unsigned* in_next = (r + 1 < CC) ? cluster.map_shared_rank(&s_in, r + 1) : nullptr;
+  unsigned* credit_prev = (r > 0) ? cluster.map_shared_rank(&s_credit, r - 1) : nullptr;
+
+  for (long i0 = cl * CC; i0 < nsweep; i0 += ncl * CC) {
+    if (threadIdx.x == 0) {
+      s_in = 0;
+      s_credit = 0;
+      s_ok = 1;
+    }
+    cluster.sync();                                  // flags reset; the previous bundle has left every ring
+    const long i = i0 + r;
+    const bool valid = i < nsweep;
+    const bool first = (r == 0);
+    const bool last = valid && (r == CC - 1 || i + 1 >= nsweep);
+    if (valid) {
+      const int nt = (int)((N - 1 - i + B - 1) / B);
+      double v = 0.0, tau = 0.0;                     // warp 0: reflector of the current task
+      for (int k = 0; k < nt; ++k) {
+        // ---- wait for the input columns (and for room in the successor's ring)
+        if (threadIdx.x == 0) {
+          int ok = 1;
+          unsigned spins = 0;
+          if (first) {
+            if (i > 0) {
+              const unsigned need = (unsigned)(k + 2);
+              while (ld_acquire_u32(prog + i - 1) < need) {
+                if (++spins > (1u << 22)) {
+                  if ((spins & 0xFFFFu) == 0 && ld_acquire_u32(err) != 0) { ok = 0; break; }
+                  if (spins > (1u << 27)) { atomicExch(err, 2u); ok = 0; break; }
+                }
+              }
+            }
+          } else {
+            const unsigned need = (unsigned)(k + 2);
+            while (ld_acquire_cluster_u32(&s_in) < need) {
+              if (++spins > (1u << 22)) {
+                if ((spins & 0xFFFFu) == 0 && ld_acquire_u32(err) != 0) { ok = 0; break; }
+                if (spins > (1u << 28)) { atomicExch(err, 5u); ok = 0; break; }
+              }
+            }
+          }
+          if (ok && !last && k >= RB - 1) {
+            const unsigned need = (unsigned)(k - (RB - 1) + 1);
+            while (ld_acquire_cluster_u32(&s_credit) < need) {
+              if (++spins > (1u << 22)) {
+                if ((spins & 0xFFFFu) == 0 && ld_acquire_u32(err) != 0) { ok = 0; break; }
+                if (spins > (1u << 28)) { atomicExch(err, 6u); ok = 0; break; }
+              }
+            }
+          }
+          s_ok = ok;
+        }
+        __syncthreads();
+        if (!s_ok) break;
+        const long j0 = i + 1 + (long)k * B;
+        const int L = (int)min((long)B, N - j0);
+        const int L2 = (int)max(0L, min((long)B, N - j0 - B));
+        const int a0 = (int)(j0 % RCOLS);
+        if (first) {                                 // copy the task's band columns in from L2, half per warp
+#pragma unroll
+          for (int cc = 0; cc < B / 2; ++cc) {
+            const int c = warp * (B / 2) + cc;
+            cpa16_cg(ring + (size_t)rslot(a0 + c) * LDB + 2 * lane, Bb + (j0 + c) * LDB + 2 * lane, c < L);
+          }
+          if (k == 0 && warp == 0) cpa16_cg(ring + (size_t)(i % RCOLS) * LDB + 2 * lane, Bb + i * LDB + 2 * lane, true);
+          cpa_commit();
+          cpa_wait<0>();
+          __syncthreads();
+        }
+        if (warp == 0) {
+          if (k == 0) {                              // reflector of column i; the column is final afterwards
+            double* col = ring + (size_t)(i % RCOLS) * LDB;
+            const double x = (lane < L) ? col[1 + lane] : 0.0;
+            double beta;
+            warp_house(x, lane, v, tau, beta);
+            __syncwarp();
+            if (lane < L) col[1 + lane] = (lane == 0) ? beta : 0.0;
+            __syncwarp();
+            __stcg(reinterpret_cast<double2*>(Bb + i * LDB + 2 * lane), make_double2(col[2 * lane], col[2 * lane + 1]));
+          }
+          if (lane >= L) v = 0.0;
+          if (lane < L) V2[i * N + j0 + lane] = v;
+          if (lane == 0) {
+            TAU2[i * ntask_max + k] = tau;
+            s_tau = tau;
+          }
+          sv[lane] = v;
+        }
+        __syncthreads();
+        if (warp == 1) {
+          // ---- D <- H D H
+          const double tD = s_tau, vD = sv[lane];
+          const int sl = rslot(a0 + lane);
+          double pp[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+          for (int c = 0; c < B; ++c) {
+            const int sc = rslot(a0 + c);
+            const int idx = (c <= lane) ? sc * LDB + lane - c : sl * LDB + c - lane;
+            pp[c & 3] = fma(ring[idx], sv[c], pp[c & 3]);
+          }
+          const double pl = tD * ((pp[0] + pp[1]) + (pp[2] + pp[3]));
+          const double kk = 0.5 * tD * warp_sum(pl * vD);
+          const double ql = fma(-kk, vD, pl);
+          sqD[lane] = ql;
+          __syncwarp();
+#pragma unroll
+          for (int c = 0; c < B; ++c)
+            if (c <= lane) ring[rslot(a0 + c) * LDB + lane - c] -= fma(vD, sqD[c], ql * sv[c]);
+        } else {
+          double v2 = 0.0, tau2 = 0.0;
+          if (L2 > 0) {
+            double yy[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+            for (int c = 0; c < B; ++c) yy[c & 3] = fma(ring[rslot(a0 + c) * LDB + B - c + lane], sv[c], yy[c & 3]);
+            const double yl = tau * ((yy[0] + yy[1]) + (yy[2] + yy[3]));
+#pragma unroll
+            for (int c = 0; c < B; ++c) {
+              double* pe = ring + rslot(a0 + c) * LDB + B - c + lane;
+              *pe = fma(-yl, sv[c], *pe);
+            }
+            __syncwarp();
+            double beta2;
+            double* col0 = ring + (size_t)a0 * LDB;
+            warp_house(lane < L2 ? col0[B + lane] : 0.0, lane, v2, tau2, beta2);
+            if (lane >= L2) v2 = 0.0;
+            sqE[lane] = v2;
+            __syncwarp();
+            double zz[4] = {0.0, 0.0, 0.0, 0.0};
+            const double* mycol = ring + (size_t)rslot(a0 + lane) * LDB + B - lane;
+#pragma unroll
+            for (int a2 = 0; a2 < B; ++a2) zz[a2 & 3] = fma(sqE[a2], mycol[a2], zz[a2 & 3]);
+            const double zl = tau2 * ((zz[0] + zz[1]) + (zz[2] + zz[3]));
+            __syncwarp();
+            sqE[lane] = zl;
+            __syncwarp();
+#pragma unroll
+            for (int c = 0; c < B; ++c) {
+              double* pe = ring + rslot(a0 + c) * LDB + B - c + lane;
+              *pe = fma(-v2, sqE[c], *pe);
+            }
+            col0[B + lane] = (lane == 0) ? beta2 : 0.0;
+          }
+          v = v2;
+          tau = tau2;
+        }
+        __syncthreads();                             // both blocks of the task are final in the ring
+        if (last) {
+          // ---- back to global memory: column c, d in [0, len_c); then publish for the next cluster
+#pragma unroll
+          for (int cc = 0; cc < B / 2; ++cc) {
+            const int c = warp * (B / 2) + cc;
+            const int len = (c < L) ? ((L2 > 0) ? B - c + L2 : L - c) : 0;
+            const int d0 = 2 * lane;
+            const double* src = ring + (size_t)rslot(a0 + c) * LDB + d0;
+            double* dst = Bb + (j0 + c) * LDB + d0;
+            if (d0 + 1 < len) __stcg(reinterpret_cast<double2*>(dst), make_double2(src[0], src[1]));
+            else if (d0 < len) __stcg(dst, src[0]);
+          }
+          __syncthreads();
+          if (threadIdx.x == 0) st_release_u32(prog + i, (k + 1 == nt) ? 0x7fffffffu : (unsigned)(k + 1));
+        } else {
+          // ---- hand the columns of this task to the next sweep: whole columns into its ring (DSMEM)
+#pragma unroll
+          for (int cc = 0; cc < B / 2; ++cc) {
+            const int c = warp * (B / 2) + cc;
+            if (c < L) {
+              const size_t o = (size_t)rslot(a0 + c) * LDB + 2 * lane;
+              *reinterpret_cast<double2*>(ring_next + o) = *reinterpret_cast<const double2*>(ring + o);
+            }
+          }
+          __syncthreads();
+          if (threadIdx.x == 0) st_release_cluster_u32(in_next, (k + 1 == nt) ? 0x7fffffffu : (unsigned)(k + 1));
+        }
+        if (!first && threadIdx.x == 0) st_release_cluster_u32(credit_prev, (unsigned)(k + 1));
+      }
+      if (!first && threadIdx.x == 0) st_release_cluster_u32(credit_prev, 0x7fffffffu);
+    }
+  }
+  cluster.sync();                                    // nobody leaves while a peer may still write into its ring
+}
+
 __global__ void __launch_bounds__(256)
 sbr_band_to_tridiag_kernel(const double* __restrict__ Bb, const long N, double* __restrict__ d, double* __restrict__ e) {
   const long c = blockIdx.x * 256L + threadIdx.x;
@@ -1033,71 +1261,75 @@ constexpr int BT_THREADS = 512;
 constexpr int Q2_THREADS = 1024;
 
 // Q2: one eigenvector per CTA, held in shared memory.  The reflectors of one sweep act on disjoint 32-element
-// ranges, so each is applied by ONE THREAD (32 multiply-adds for the dot product, 32 for the update, no shuffles:
-// with a warp per reflector the shuffle unit -- one warp-instruction per clock and SM -- was the bottleneck,
-// profiles/r02_sbr_profile.md).  Both arrays are stored with one pad per 32 entries: the threads of a warp work
-// on ranges 32 entries apart, i.e. 33 words apart, conflict-free for every sweep offset.  The reflectors of sweep
-// i-1 are fetched (coalesced) into registers while sweep i is applied and parked in shared memory afterwards.
+// ranges; EIGHT threads share one reflector (4 entries each, 3 shuffle rounds).  A warp per reflector was bound by
+// the shuffle unit (one warp-instruction per clock and SM: 36 ms at N = 10^4, 100 vectors), a thread per reflector
+// by the latency of 64 dependent shared-memory operations on too few warps (42 ms) -- profiles/r02_sbr_profile.md.
+// z and the current reflector row live in shared memory with 8 pads per 32 entries (neighbouring reflectors of a
+// half-warp land in different banks for every sweep offset); the row of sweep i-1 and its taus are fetched
+// (coalesced) into registers while sweep i is applied and parked in shared memory afterwards.
+__device__ __forceinline__ long q2_idx(long e) { return e + ((e >> 5) << 3); }
+
 template <int MAXPF>
 __global__ void __launch_bounds__(Q2_THREADS, 1)
 sbr_back_q2_kernel(const double* __restrict__ V2, const double* __restrict__ TAU2, const long ntask_max, const long N,
                    double* __restrict__ Z) {
   extern __shared__ double smem_q2[];
-  const long NP = N + N / 32 + 2;                    // padded length
-  double* zs = smem_q2;                              // z[e] at zs[e + e/32]
-  double* vs = smem_q2 + NP;                         // reflector entry for row e at vs[e + e/32]
+  const long NP = q2_idx(N) + 16;                    // padded length
+  double* zs = smem_q2;
+  double* vs = smem_q2 + NP;
+  double* ts = smem_q2 + 2 * NP;                     // taus of the current sweep (ntask_max)
   const int tid = threadIdx.x;
   double* z = Z + (long)blockIdx.x * N;
-  for (long r = tid; r < N; r += Q2_THREADS) zs[r + (r >> 5)] = z[r];
-  double pf[MAXPF];
-  auto fetch = [&](long i) {                         // entries i+1 .. N-1 of row i of V2, coalesced
+  for (long r = tid; r < N; r += Q2_THREADS) zs[q2_idx(r)] = z[r];
+  double pf[MAXPF], ptau = 0.0;
+  auto fetch = [&](long i) {                         // entries i+1 .. N-1 of row i of V2 and the sweep's taus
 #pragma unroll
     for (int q = 0; q < MAXPF; ++q) {
       const long e = i + 1 + tid + (long)q * Q2_THREADS;
       pf[q] = (e < N) ? __ldg(V2 + i * N + e) : 0.0;
     }
+    const int nt = (int)((N - 1 - i + B - 1) / B);
+    ptau = (tid < nt) ? __ldg(TAU2 + i * ntask_max + tid) : 0.0;
   };
   auto park = [&](long i) {
 #pragma unroll
     for (int q = 0; q < MAXPF; ++q) {
       const long e = i + 1 + tid + (long)q * Q2_THREADS;
-      if (e < N) vs[e + (e >> 5)] = pf[q];
+      if (e < N) vs[q2_idx(e)] = pf[q];
     }
+    if (tid < ntask_max) ts[tid] = ptau;
   };
   if (N >= 3) {
     fetch(N - 3);
     park(N - 3);
   }
   __syncthreads();
+  const int sub = tid & 7;
   for (long i = N - 3; i >= 0; --i) {
     if (i > 0) fetch(i - 1);
     const int nt = (int)((N - 1 - i + B - 1) / B);
-    for (int k = tid; k < nt; k += Q2_THREADS) {     // one reflector per thread
-      const long e0 = i + 1 + (long)k * B;
-      const int len = (int)min((long)B, N - e0);
-      const double tau = __ldg(TAU2 + i * ntask_max + k);
-      double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
-#pragma unroll 8
-      for (int j = 0; j < B; j += 4) {
-        const long ea = e0 + j;
-        if (j + 3 < len) {
-          d0 = fma(vs[ea + (ea >> 5)], zs[ea + (ea >> 5)], d0);
-          d1 = fma(vs[ea + 1 + ((ea + 1) >> 5)], zs[ea + 1 + ((ea + 1) >> 5)], d1);
-          d2 = fma(vs[ea + 2 + ((ea + 2) >> 5)], zs[ea + 2 + ((ea + 2) >> 5)], d2);
-          d3 = fma(vs[ea + 3 + ((ea + 3) >> 5)], zs[ea + 3 + ((ea + 3) >> 5)], d3);
-        } else {
-          for (int jj = j; jj < len; ++jj) {
-            const long eb = e0 + jj;
-            d0 = fma(vs[eb + (eb >> 5)], zs[eb + (eb >> 5)], d0);
-          }
-        }
+    for (int k0 = 0; k0 < nt; k0 += Q2_THREADS / 8) {        // CTA-uniform trip count
+      const int k = k0 + (tid >> 3);
+      const long e0 = i + 1 + (long)k * B + sub;             // this thread's entries: e0, e0+8, e0+16, e0+24
+      const bool on = k < nt;
+      double vv[4], zz[4], dot = 0.0;
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const long e = e0 + 8 * jj;
+        const bool in = on && e < N;
+        vv[jj] = in ? vs[q2_idx(e)] : 0.0;
+        zz[jj] = in ? zs[q2_idx(e)] : 0.0;
+        dot = fma(vv[jj], zz[jj], dot);
       }
-      const double s = -tau * ((d0 + d1) + (d2 + d3));
-#pragma unroll 8
-      for (int j = 0; j < B; ++j) {
-        if (j < len) {
-          const long eb = e0 + j;
-          zs[eb + (eb >> 5)] = fma(s, vs[eb + (eb >> 5)], zs[eb + (eb >> 5)]);
+      dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+      dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+      dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+      if (on) {
+        const double sfac = -ts[k] * dot;
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const long e = e0 + 8 * jj;
+          if (e < N) zs[q2_idx(e)] = fma(sfac, vv[jj], zz[jj]);
         }
       }
     }
@@ -1105,7 +1337,7 @@ sbr_back_q2_kernel(const double* __restrict__ V2, const double* __restrict__ TAU
     if (i > 0) park(i - 1);
     __syncthreads();
   }
-  for (long r = tid; r < N; r += Q2_THREADS) z[r] = zs[r + (r >> 5)];
+  for (long r = tid; r < N; r += Q2_THREADS) z[r] = zs[q2_idx(r)];
 }
 
 // Q2 for vectors too long for the layout above (two padded arrays): only z in shared memory, one warp per reflector
@@ -1379,7 +1611,36 @@ static int sbr_stage2(long N, const SbrWs& w, double* d, double* e, cudaStream_t
     // PODSDF_CHASE (A/B only): "1" = one warp per task, "2" = experimental CTA-pipelined kernel; default: two warps per task
     const char* variant = getenv("PODSDF_CHASE");
     const int var = variant ? atoi(variant) : 0;
-    if (var != 2) {
+    bool done = false;
+    if (var == 3) {                                             // cluster / DSMEM hand-offs
+      PODSDF_CUDA(cudaFuncSetAttribute(sbr_chase_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)CLUSTER_CHASE_SMEM));
+      cudaLaunchConfig_t cfg = {};
+      cfg.blockDim = dim3(64);
+      cfg.dynamicSmemBytes = CLUSTER_CHASE_SMEM;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeCooperative;
+      attr[0].val.cooperative = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      cfg.gridDim = dim3(CC);
+      int nclus = 0;
+      cudaError_t ce = cudaOccupancyMaxActiveClusters(&nclus, sbr_chase_cluster_kernel, &cfg);
+      if (ce == cudaSuccess && nclus > 0) {
+        long G = nclus;
+        const long useful = ((N + 2 * B - 1) / (2 * B) + 8 + CC - 1) / CC + 1;
+        const long bundles = (nsweep + CC - 1) / CC;
+        if (G > useful) G = useful;
+        if (G > bundles) G = bundles;
+        cfg.gridDim = dim3((unsigned)(G * CC));
+        ce = cudaLaunchKernelEx(&cfg, sbr_chase_cluster_kernel, Bb, Narg, V2, TAU2, ntm, bar);
+      }
+      if (ce == cudaSuccess) done = true;
+      else cudaGetLastError();                                  // fall through to the two-warp kernel
+    }
+    if (done) {
+    } else if (var != 2) {
       const void* kern = (var == 1) ? (const void*)sbr_chase_kernel : (const void*)sbr_chase2_kernel;
       const int threads = (var == 1) ? 32 : 64;
       int per_sm = 1;
@@ -1456,14 +1717,14 @@ int sbr_back_transform(const double* ws, long N, double* Z, int nvec, cudaStream
     return fail(PODSDF_ERR_UNSUPPORTED, "back-transformation: one eigenvector does not fit shared memory");
   {
     const long pfs = (N + Q2_THREADS - 1) / Q2_THREADS;          // prefetched entries per thread and sweep
-    const size_t q2_smem = sizeof(double) * 2 * (size_t)(N + N / 32 + 2);
+    const size_t q2_smem = sizeof(double) * (2 * (size_t)(N + 8 * (N / 32) + 16) + (size_t)w.ntask_max);
 #define PODSDF_Q2(M)                                                                                         \
   do {                                                                                                       \
     auto k = sbr_back_q2_kernel<M>;                                                                          \
     PODSDF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)q2_smem));         \
     k<<<nvec, Q2_THREADS, q2_smem, st>>>(w.V2, w.TAU2, w.ntask_max, N, Z);                                   \
   } while (0)
-    if (q2_smem + 2048 > (size_t)max_smem || pfs > 14) {
+    if (q2_smem + 2048 > (size_t)max_smem || pfs > 14 || w.ntask_max > Q2_THREADS) {
       if (one + 2048 > (size_t)max_smem)
         return fail(PODSDF_ERR_UNSUPPORTED, "back-transformation: one eigenvector does not fit shared memory");
       PODSDF_CUDA(cudaFuncSetAttribute(sbr_back_q2_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)one));

@@ -85,6 +85,48 @@ class DfShard(object):
         return self.out[:n_slabs - 2 * self.plan.nfx]
 
 
+def generate_injected_sharded(plan, own, out, rank=None, world=None, group=None, stream=None):
+    """Injected mode on a time shard with the halo exchange HIDDEN behind the interior steps: `own`
+    (n_own, 3, Jp, Kp) holds this rank's slabs [t0_r, t1_r) (the last rank also owns the 2 nfx tail slabs).  The
+    steps whose windows lie inside `own` start at once; meanwhile the first 2 nfx slabs go to the left neighbour and
+    the right neighbour's arrive (NCCL send/recv on its own stream); the last 24 steps (a multiple of 8 >= 2 nfx, so
+    tile anchors -- and therefore bits -- match the one-GPU run) follow on the received halo.  `out` (n_steps, 3, J, K)
+    with n_steps = t1_r - t0_r is filled; returns it."""
+    import torch
+    import torch.distributed as dist
+    rank = dist.get_rank(group) if rank is None else rank
+    world = dist.get_world_size(group) if world is None else world
+    st = torch.cuda.current_stream(own.device) if stream is None else stream
+    halo = 2 * plan.nfx
+    n_steps = out.shape[0]
+    if world == 1 or rank == world - 1:                  # nothing to receive: the shard owns its whole window
+        ops = []
+        if world > 1 and rank > 0:
+            ops.append(dist.P2POp(dist.isend, own[:halo].contiguous(), rank - 1, group))
+        reqs = dist.batch_isend_irecv(ops) if ops else []
+        plan.generate_injected_dev(own.data_ptr(), n_steps + halo, out.data_ptr(), st.cuda_stream)
+        for r in reqs:
+            r.wait()
+        return out
+    tail = ((halo + 7) // 8) * 8
+    if n_steps < tail + 8 or own.shape[0] != n_steps:
+        ext = exchange_halo(own, halo, rank, world, group)
+        plan.generate_injected_dev(ext.data_ptr(), ext.shape[0], out.data_ptr(), st.cuda_stream)
+        return out
+    recv = torch.empty((halo,) + tuple(own.shape[1:]), dtype=own.dtype, device=own.device)
+    ops = [dist.P2POp(dist.irecv, recv, rank + 1, group)]
+    if rank > 0:
+        ops.append(dist.P2POp(dist.isend, own[:halo].contiguous(), rank - 1, group))
+    reqs = dist.batch_isend_irecv(ops)
+    n_in = n_steps - tail                                 # interior steps: windows end at slab n_in + halo - 1 < n_steps
+    plan.generate_injected_dev(own.data_ptr(), n_in + halo, out.data_ptr(), st.cuda_stream)
+    for r in reqs:
+        r.wait()
+    last = torch.cat([own[n_in:], recv], dim=0)          # slabs n_in .. n_steps + halo - 1
+    plan.generate_injected_dev(last.data_ptr(), last.shape[0], out[n_in:].data_ptr(), st.cuda_stream)
+    return out
+
+
 # ------------------------------------------------------------------------------------ POD
 def allreduce_gram(C, group=None, device_index=None):
     """Sum of the per-rank N x N partial Gram matrices (float64) on every rank.  On GPUs the exactly symmetric partials
