@@ -12,9 +12,9 @@
 //                                                orientations, split over K
 //              W = X T - 1/2 V (T^T V^T X T)     two small kernels
 //              A22 -= V W^T + W V^T              FP64 tensor-core MMA rank-2b update, lower tiles + full diagonal tiles
-//   stage 2  band -> tridiagonal by bulge chasing (Murata-Horikoshi / Lang): sweep i = chain of b x b tasks, one warp
-//            per sweep, sweeps pipelined two tasks apart through progress counters in global memory (persistent
-//            cooperative kernel)
+//   stage 2  band -> tridiagonal by bulge chasing (Murata-Horikoshi / Lang): sweep i = chain of b x b tasks, one CTA
+//            (two warps: diagonal block / sub-diagonal block) per sweep, sweeps pipelined two tasks apart through
+//            progress counters in global memory (persistent cooperative kernel)
 //   back     eigenvectors of T -> eigenvectors of C: stage-2 reflectors (reverse order), then the block reflectors of
 //            stage 1, one CTA per vector with the vector in shared memory
 //
@@ -22,12 +22,8 @@
 // matrices are k-major: V[m*N + r] is entry (r, m).  tools/proto_sbr.py is the numpy model of every step below.
 #include "sbr_kernels.cuh"
 
-#include <cooperative_groups.h>
-
 #include <cfloat>
 #include <cstdlib>
-
-namespace cg = cooperative_groups;
 
 namespace podsdf {
 
@@ -837,413 +833,6 @@ sbr_chase2_kernel(double* __restrict__ Bb, const long N, double* __restrict__ V2
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// Stage 2, pipelined inside a CTA.  The single-warp kernel above pays a global-memory hand-off (fence, release,
-// acquire poll, L2 copies) on every task and the pipeline advances two tasks per sweep: 2 N hand-offs on the
-// critical path.  Here a CTA runs CG consecutive sweeps, one warp each, and the band columns stream through them
-// in SHARED memory: warp 0 copies the columns of its task in from L2, every warp works on them in place one after
-// the other (warp w starts task k when warp w-1 has finished task k+1: a shared-memory flag), and the last warp
-// copies them back out.  Only the hand-off between CTAs (bundles of CG sweeps) goes through global memory.
-//   ring of RC = (2 CG + 1) 32-column blocks: slot(c) = c mod RC, 64 doubles per column (the band layout itself).
-// ------------------------------------------------------------------------------------------------
-constexpr int CG = 6;                    // sweeps per CTA
-constexpr int RCB = 2 * CG + 1;          // ring capacity in blocks of B columns (one block of slack)
-constexpr int RC = RCB * B;              // ... in columns
-constexpr size_t CHASE_SMEM = (size_t)RC * LDB * sizeof(double);
-
-__device__ __forceinline__ int ring_slot(int s) { return s >= RC ? s - RC : s; }
-
-__global__ void __launch_bounds__(32 * CG, 1)
-sbr_chase_multi_kernel(double* __restrict__ Bb, const long N, double* __restrict__ V2, double* __restrict__ TAU2,
-                       const long ntask_max, unsigned* __restrict__ bar) {
-  extern __shared__ __align__(16) double ring[];          // [RC][LDB]
-  __shared__ double s_v[CG][B], s_q[CG][B];
-  __shared__ volatile int s_prog[CG];
-  __shared__ volatile int s_abort;
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  unsigned* err = bar + 1;
-  unsigned* prog = bar + 2;
-  const long nsweep = N - 2;
-  double* sv = s_v[w];
-  double* sq = s_q[w];
-  if (threadIdx.x == 0) s_abort = 0;
-
-  for (long i0 = (long)blockIdx.x * CG; i0 < nsweep; i0 += (long)gridDim.x * CG) {
-    __syncthreads();                                 // the previous bundle has left the ring
-    if (lane == 0) s_prog[w] = 0;
-    __syncthreads();
-    const long i = i0 + w;                           // this warp's sweep
-    const int gv = (int)min((long)CG, nsweep - i0);  // valid sweeps of the bundle
-    if (w < gv) {
-      const int nt = (int)((N - 1 - i + B - 1) / B);
-      const bool first = (w == 0), last = (w == gv - 1);
-      double v = 0.0, tau = 0.0;
-      bool ok = true;
-      for (int k = 0; k < nt && ok; ++k) {
-        const long j0 = i + 1 + (long)k * B;
-        const int L = (int)min((long)B, N - j0);
-        const int L2 = (int)max(0L, min((long)B, N - j0 - B));
-        // ---- wait: predecessor sweep has finished task k+1; the ring has room (first warp only)
-        if (lane == 0) {
-          unsigned spins = 0;
-          if (first) {
-            if (i > 0) {
-              const unsigned need = (unsigned)(k + 2);
-              while (ld_acquire_u32(prog + i - 1) < need) {
-                if (++spins > (1u << 22)) {
-                  if ((spins & 0xFFFFu) == 0 && (ld_acquire_u32(err) != 0 || s_abort)) { ok = false; break; }
-                  if (spins > (1u << 27)) { atomicExch(err, 2u); ok = false; break; }
-                }
-              }
-            }
-            const int need_last = k - RCB + 1;       // columns leaving the slots this task overwrites
-            while (ok && need_last > 0 && s_prog[gv - 1] < need_last) {
-              if (++spins > (1u << 27) || s_abort) { atomicExch(err, 3u); ok = false; break; }
-            }
-          } else {
-            const int need = k + 2;
-            while (s_prog[w - 1] < need) {
-              if (++spins > (1u << 27) || s_abort) { atomicExch(err, 4u); ok = false; break; }
-            }
-          }
-          if (!ok) s_abort = 1;
-        }
-        ok = __shfl_sync(0xffffffffu, ok ? 1 : 0, 0) != 0;
-        if (!ok) break;
-        __threadfence_block();
-        const int a0 = (int)(j0 % RC);               // ring slot of column j0
-        if (first) {
-          // ---- copy the task's band columns in (and the sweep column i itself at task 0)
-#pragma unroll
-          for (int c = 0; c < B; ++c)
-            cpa16_cg(ring + (size_t)ring_slot(a0 + c) * LDB + 2 * lane, Bb + (j0 + c) * LDB + 2 * lane, c < L);
-          if (k == 0) cpa16_cg(ring + (size_t)(i % RC) * LDB + 2 * lane, Bb + i * LDB + 2 * lane, true);
-          cpa_commit();
-          cpa_wait<0>();
-          __syncwarp();
-        }
-        if (k == 0) {                                // reflector of column i; the column is final afterwards
-          double* col = ring + (size_t)(i % RC) * LDB;
-          const double x = (lane < L) ? col[1 + lane] : 0.0;
-          double beta;
-          warp_house(x, lane, v, tau, beta);
-          __syncwarp();
-          if (lane < L) col[1 + lane] = (lane == 0) ? beta : 0.0;
-          __syncwarp();
-          __stcg(reinterpret_cast<double2*>(Bb + i * LDB + 2 * lane), make_double2(col[2 * lane], col[2 * lane + 1]));
-        }
-        if (lane >= L) v = 0.0;
-        if (lane < L) V2[i * N + j0 + lane] = v;
-        if (lane == 0) TAU2[i * ntask_max + k] = tau;
-        sv[lane] = v;
-        __syncwarp();
-        // ---- D <- H D H
-        {
-          double pp[4] = {0.0, 0.0, 0.0, 0.0};
-          const int sl = ring_slot(a0 + lane);
-#pragma unroll
-          for (int c = 0; c < B; ++c) {
-            const int sc = ring_slot(a0 + c);
-            const int idx = (c <= lane) ? sc * LDB + lane - c : sl * LDB + c - lane;
-            pp[c & 3] = fma(ring[idx], sv[c], pp[c & 3]);
-          }
-          const double pl = tau * ((pp[0] + pp[1]) + (pp[2] + pp[3]));
-          const double kk = 0.5 * tau * warp_sum(pl * v);
-          const double ql = fma(-kk, v, pl);
-          sq[lane] = ql;
-          __syncwarp();
-#pragma unroll
-          for (int c = 0; c < B; ++c)
-            if (c <= lane) ring[ring_slot(a0 + c) * LDB + lane - c] -= fma(v, sq[c], ql * sv[c]);
-          __syncwarp();
-        }
-        double v2 = 0.0, tau2 = 0.0;
-        if (L2 > 0) {
-          double yy[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-          for (int c = 0; c < B; ++c) yy[c & 3] = fma(ring[ring_slot(a0 + c) * LDB + B - c + lane], sv[c], yy[c & 3]);
-          const double yl = tau * ((yy[0] + yy[1]) + (yy[2] + yy[3]));
-#pragma unroll
-          for (int c = 0; c < B; ++c) {
-            double* pe = ring + ring_slot(a0 + c) * LDB + B - c + lane;
-            *pe = fma(-yl, sv[c], *pe);
-          }
-          __syncwarp();
-          double beta2;
-          double* col0 = ring + (size_t)a0 * LDB;
-          warp_house(lane < L2 ? col0[B + lane] : 0.0, lane, v2, tau2, beta2);
-          if (lane >= L2) v2 = 0.0;
-          sq[lane] = v2;
-          __syncwarp();
-          double zz[4] = {0.0, 0.0, 0.0, 0.0};
-          const double* mycol = ring + (size_t)ring_slot(a0 + lane) * LDB + B - lane;
-#pragma unroll
-          for (int a2 = 0; a2 < B; ++a2) zz[a2 & 3] = fma(sq[a2], mycol[a2], zz[a2 & 3]);
-          const double zl = tau2 * ((zz[0] + zz[1]) + (zz[2] + zz[3]));
-          __syncwarp();
-          sq[lane] = zl;
-          __syncwarp();
-#pragma unroll
-          for (int c = 0; c < B; ++c) {
-            double* pe = ring + ring_slot(a0 + c) * LDB + B - c + lane;
-            *pe = fma(-v2, sq[c], *pe);
-          }
-          col0[B + lane] = (lane == 0) ? beta2 : 0.0;
-          __syncwarp();
-        }
-        v = v2;
-        tau = tau2;
-        if (last) {
-          // ---- the columns of this task leave the ring (every entry the bundle may have changed: d < B - c + L2)
-#pragma unroll
-          for (int c = 0; c < B; ++c) {
-            const int len = (c < L) ? ((L2 > 0) ? B - c + L2 : L - c) : 0;
-            const int d0 = 2 * lane;
-            const double* src = ring + (size_t)ring_slot(a0 + c) * LDB + d0;
-            double* dst = Bb + (j0 + c) * LDB + d0;
-            if (d0 + 1 < len) __stcg(reinterpret_cast<double2*>(dst), make_double2(src[0], src[1]));
-            else if (d0 < len) __stcg(dst, src[0]);
-          }
-          __threadfence();
-          __syncwarp();
-          if (lane == 0) st_release_u32(prog + i, (k + 1 == nt) ? 0x7fffffffu : (unsigned)(k + 1));
-        }
-        __threadfence_block();
-        __syncwarp();
-        if (lane == 0) s_prog[w] = (k + 1 == nt) ? 0x7fffffff : (k + 1);
-        __syncwarp();
-      }
-      if (!ok) {
-        if (lane == 0) s_prog[w] = 0x7fffffff;       // let the others run into their own time-outs / abort flag
-      }
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Stage 2 across a thread-block cluster.  The hand-off between consecutive sweeps is what the critical path is made
-// of (2 N hand-offs; through global memory each costs a release fence over 16 KB of stores, an acquire poll and an L2
-// copy: ~3 us).  Here CC consecutive sweeps run on the CC CTAs of a cluster -- one SM each, so they do not compete
-// for issue slots like the warps of sbr_chase_multi_kernel -- and a sweep hands the band columns of a finished task
-// to the next sweep by writing them straight into that CTA's shared memory (DSMEM) and bumping a counter there with
-// a cluster-scope release; the consumer polls its OWN shared memory.  Only the first sweep of a cluster reads from
-// global memory and only the last one writes back and publishes progress for the next cluster.
-//   every CTA: ring of RB 32-column blocks, slot(c) = c mod (32 RB), 64 doubles per column (the band layout);
-//   s_in   (written by the predecessor): tasks of sweep i-1 whose columns have arrived;
-//   s_credit (written by the successor): tasks of sweep i+1 finished -- the predecessor may run RB - 1 tasks ahead.
-// ------------------------------------------------------------------------------------------------
-constexpr int CC = 8;                    // sweeps (CTAs) per cluster: the portable maximum
-constexpr int RB = 6;                    // ring capacity in blocks of B columns
-constexpr int RCOLS = RB * B;
-constexpr size_t CLUSTER_CHASE_SMEM = (size_t)RCOLS * LDB * sizeof(double);
-
-__device__ __forceinline__ unsigned ld_acquire_cluster_u32(const volatile unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.cluster.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_cluster_u32(unsigned* p, unsigned v) {
-  asm volatile("st.release.cluster.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ int rslot(int s2) { return s2 >= RCOLS ? s2 - RCOLS : s2; }
-
-__global__ void __cluster_dims__(CC, 1, 1) __launch_bounds__(64)
-sbr_chase_cluster_kernel(double* __restrict__ Bb, const long N, double* __restrict__ V2, double* __restrict__ TAU2,
-                         const long ntask_max, unsigned* __restrict__ bar) {
-  extern __shared__ __align__(16) double ring[];          // [RCOLS][LDB]
-  __shared__ double sv[B], sqE[B], sqD[B];
-  __shared__ double s_tau;
-  __shared__ int s_ok;
-  __shared__ unsigned s_in, s_credit;
-  cg::cluster_group cluster = cg::this_cluster();
-  const unsigned r = cluster.block_rank();
-  const long ncl = gridDim.x / CC, cl = blockIdx.x / CC;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  unsigned* err = bar + 1;
-  unsigned* prog = bar + 2;
-  const long nsweep = N - 2;
-  double* ring_next = (r + 1 < CC) ? cluster.map_shared_rank(ring, r + 1) : nullptr;
-  unsigned* in_next = (r + 1 < CC) ? cluster.map_shared_rank(&s_in, r + 1) : nullptr;
-  unsigned* credit_prev = (r > 0) ? cluster.map_shared_rank(&s_credit, r - 1) : nullptr;
-
-  for (long i0 = cl * CC; i0 < nsweep; i0 += ncl * CC) {
-    if (threadIdx.x == 0) {
-      s_in = 0;
-      s_credit = 0;
-      s_ok = 1;
-    }
-    cluster.sync();                                  // flags reset; the previous bundle has left every ring
-    const long i = i0 + r;
-    const bool valid = i < nsweep;
-    const bool first = (r == 0);
-    const bool last = valid && (r == CC - 1 || i + 1 >= nsweep);
-    if (valid) {
-      const int nt = (int)((N - 1 - i + B - 1) / B);
-      double v = 0.0, tau = 0.0;                     // warp 0: reflector of the current task
-      for (int k = 0; k < nt; ++k) {
-        // ---- wait for the input columns (and for room in the successor's ring)
-        if (threadIdx.x == 0) {
-          int ok = 1;
-          unsigned spins = 0;
-          if (first) {
-            if (i > 0) {
-              const unsigned need = (unsigned)(k + 2);
-              while (ld_acquire_u32(prog + i - 1) < need) {
-                if (++spins > (1u << 22)) {
-                  if ((spins & 0xFFFFu) == 0 && ld_acquire_u32(err) != 0) { ok = 0; break; }
-                  if (spins > (1u << 27)) { atomicExch(err, 2u); ok = 0; break; }
-                }
-              }
-            }
-          } else {
-            const unsigned need = (unsigned)(k + 2);
-            while (ld_acquire_cluster_u32(&s_in) < need) {
-              if (++spins > (1u << 22)) {
-                if ((spins & 0xFFFFu) == 0 && ld_acquire_u32(err) != 0) { ok = 0; break; }
-                if (spins > (1u << 28)) { atomicExch(err, 5u); ok = 0; break; }
-              }
-            }
-          }
-          if (ok && !last && k >= RB - 1) {
-            const unsigned need = (unsigned)(k - (RB - 1) + 1);
-            while (ld_acquire_cluster_u32(&s_credit) < need) {
-              if (++spins > (1u << 22)) {
-                if ((spins & 0xFFFFu) == 0 && ld_acquire_u32(err) != 0) { ok = 0; break; }
-                if (spins > (1u << 28)) { atomicExch(err, 6u); ok = 0; break; }
-              }
-            }
-          }
-          s_ok = ok;
-        }
-        __syncthreads();
-        if (!s_ok) break;
-        const long j0 = i + 1 + (long)k * B;
-        const int L = (int)min((long)B, N - j0);
-        const int L2 = (int)max(0L, min((long)B, N - j0 - B));
-        const int a0 = (int)(j0 % RCOLS);
-        if (first) {                                 // copy the task's band columns in from L2, half per warp
-#pragma unroll
-          for (int cc = 0; cc < B / 2; ++cc) {
-            const int c = warp * (B / 2) + cc;
-            cpa16_cg(ring + (size_t)rslot(a0 + c) * LDB + 2 * lane, Bb + (j0 + c) * LDB + 2 * lane, c < L);
-          }
-          if (k == 0 && warp == 0) cpa16_cg(ring + (size_t)(i % RCOLS) * LDB + 2 * lane, Bb + i * LDB + 2 * lane, true);
-          cpa_commit();
-          cpa_wait<0>();
-          __syncthreads();
-        }
-        if (warp == 0) {
-          if (k == 0) {                              // reflector of column i; the column is final afterwards
-            double* col = ring + (size_t)(i % RCOLS) * LDB;
-            const double x = (lane < L) ? col[1 + lane] : 0.0;
-            double beta;
-            warp_house(x, lane, v, tau, beta);
-            __syncwarp();
-            if (lane < L) col[1 + lane] = (lane == 0) ? beta : 0.0;
-            __syncwarp();
-            __stcg(reinterpret_cast<double2*>(Bb + i * LDB + 2 * lane), make_double2(col[2 * lane], col[2 * lane + 1]));
-          }
-          if (lane >= L) v = 0.0;
-          if (lane < L) V2[i * N + j0 + lane] = v;
-          if (lane == 0) {
-            TAU2[i * ntask_max + k] = tau;
-            s_tau = tau;
-          }
-          sv[lane] = v;
-        }
-        __syncthreads();
-        if (warp == 1) {
-          // ---- D <- H D H
-          const double tD = s_tau, vD = sv[lane];
-          const int sl = rslot(a0 + lane);
-          double pp[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-          for (int c = 0; c < B; ++c) {
-            const int sc = rslot(a0 + c);
-            const int idx = (c <= lane) ? sc * LDB + lane - c : sl * LDB + c - lane;
-            pp[c & 3] = fma(ring[idx], sv[c], pp[c & 3]);
-          }
-          const double pl = tD * ((pp[0] + pp[1]) + (pp[2] + pp[3]));
-          const double kk = 0.5 * tD * warp_sum(pl * vD);
-          const double ql = fma(-kk, vD, pl);
-          sqD[lane] = ql;
-          __syncwarp();
-#pragma unroll
-          for (int c = 0; c < B; ++c)
-            if (c <= lane) ring[rslot(a0 + c) * LDB + lane - c] -= fma(vD, sqD[c], ql * sv[c]);
-        } else {
-          double v2 = 0.0, tau2 = 0.0;
-          if (L2 > 0) {
-            double yy[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-            for (int c = 0; c < B; ++c) yy[c & 3] = fma(ring[rslot(a0 + c) * LDB + B - c + lane], sv[c], yy[c & 3]);
-            const double yl = tau * ((yy[0] + yy[1]) + (yy[2] + yy[3]));
-#pragma unroll
-            for (int c = 0; c < B; ++c) {
-              double* pe = ring + rslot(a0 + c) * LDB + B - c + lane;
-              *pe = fma(-yl, sv[c], *pe);
-            }
-            __syncwarp();
-            double beta2;
-            double* col0 = ring + (size_t)a0 * LDB;
-            warp_house(lane < L2 ? col0[B + lane] : 0.0, lane, v2, tau2, beta2);
-            if (lane >= L2) v2 = 0.0;
-            sqE[lane] = v2;
-            __syncwarp();
-            double zz[4] = {0.0, 0.0, 0.0, 0.0};
-            const double* mycol = ring + (size_t)rslot(a0 + lane) * LDB + B - lane;
-#pragma unroll
-            for (int a2 = 0; a2 < B; ++a2) zz[a2 & 3] = fma(sqE[a2], mycol[a2], zz[a2 & 3]);
-            const double zl = tau2 * ((zz[0] + zz[1]) + (zz[2] + zz[3]));
-            __syncwarp();
-            sqE[lane] = zl;
-            __syncwarp();
-#pragma unroll
-            for (int c = 0; c < B; ++c) {
-              double* pe = ring + rslot(a0 + c) * LDB + B - c + lane;
-              *pe = fma(-v2, sqE[c], *pe);
-            }
-            col0[B + lane] = (lane == 0) ? beta2 : 0.0;
-          }
-          v = v2;
-          tau = tau2;
-        }
-        __syncthreads();                             // both blocks of the task are final in the ring
-        if (last) {
-          // ---- back to global memory: column c, d in [0, len_c); then publish for the next cluster
-#pragma unroll
-          for (int cc = 0; cc < B / 2; ++cc) {
-            const int c = warp * (B / 2) + cc;
-            const int len = (c < L) ? ((L2 > 0) ? B - c + L2 : L - c) : 0;
-            const int d0 = 2 * lane;
-            const double* src = ring + (size_t)rslot(a0 + c) * LDB + d0;
-            double* dst = Bb + (j0 + c) * LDB + d0;
-            if (d0 + 1 < len) __stcg(reinterpret_cast<double2*>(dst), make_double2(src[0], src[1]));
-            else if (d0 < len) __stcg(dst, src[0]);
-          }
-          __syncthreads();
-          if (threadIdx.x == 0) st_release_u32(prog + i, (k + 1 == nt) ? 0x7fffffffu : (unsigned)(k + 1));
-        } else {
-          // ---- hand the columns of this task to the next sweep: whole columns into its ring (DSMEM)
-#pragma unroll
-          for (int cc = 0; cc < B / 2; ++cc) {
-            const int c = warp * (B / 2) + cc;
-            if (c < L) {
-              const size_t o = (size_t)rslot(a0 + c) * LDB + 2 * lane;
-              *reinterpret_cast<double2*>(ring_next + o) = *reinterpret_cast<const double2*>(ring + o);
-            }
-          }
-          __syncthreads();
-          if (threadIdx.x == 0) st_release_cluster_u32(in_next, (k + 1 == nt) ? 0x7fffffffu : (unsigned)(k + 1));
-        }
-        if (!first && threadIdx.x == 0) st_release_cluster_u32(credit_prev, (unsigned)(k + 1));
-      }
-      if (!first && threadIdx.x == 0) st_release_cluster_u32(credit_prev, 0x7fffffffu);
-    }
-  }
-  cluster.sync();                                    // nobody leaves while a peer may still write into its ring
-}
-
 __global__ void __launch_bounds__(256)
 sbr_band_to_tridiag_kernel(const double* __restrict__ Bb, const long N, double* __restrict__ d, double* __restrict__ e) {
   const long c = blockIdx.x * 256L + threadIdx.x;
@@ -1608,59 +1197,19 @@ static int sbr_stage2(long N, const SbrWs& w, double* d, double* e, cudaStream_t
     double *V2 = w.V2, *TAU2 = w.TAU2;
     unsigned* bar = w.bar;
     void* args[] = {&Bb, &Narg, &V2, &TAU2, &ntm, &bar};
-    // PODSDF_CHASE (A/B only): "1" = one warp per task, "2" = experimental CTA-pipelined kernel; default: two warps per task
+    // PODSDF_CHASE=1 (A/B only): one warp per task; default: two warps per task
     const char* variant = getenv("PODSDF_CHASE");
     const int var = variant ? atoi(variant) : 0;
-    bool done = false;
-    if (var == 3) {                                             // cluster / DSMEM hand-offs
-      PODSDF_CUDA(cudaFuncSetAttribute(sbr_chase_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)CLUSTER_CHASE_SMEM));
-      cudaLaunchConfig_t cfg = {};
-      cfg.blockDim = dim3(64);
-      cfg.dynamicSmemBytes = CLUSTER_CHASE_SMEM;
-      cfg.stream = st;
-      cudaLaunchAttribute attr[1];
-      attr[0].id = cudaLaunchAttributeCooperative;
-      attr[0].val.cooperative = 1;
-      cfg.attrs = attr;
-      cfg.numAttrs = 1;
-      cfg.gridDim = dim3(CC);
-      int nclus = 0;
-      cudaError_t ce = cudaOccupancyMaxActiveClusters(&nclus, sbr_chase_cluster_kernel, &cfg);
-      if (ce == cudaSuccess && nclus > 0) {
-        long G = nclus;
-        const long useful = ((N + 2 * B - 1) / (2 * B) + 8 + CC - 1) / CC + 1;
-        const long bundles = (nsweep + CC - 1) / CC;
-        if (G > useful) G = useful;
-        if (G > bundles) G = bundles;
-        cfg.gridDim = dim3((unsigned)(G * CC));
-        ce = cudaLaunchKernelEx(&cfg, sbr_chase_cluster_kernel, Bb, Narg, V2, TAU2, ntm, bar);
-      }
-      if (ce == cudaSuccess) done = true;
-      else cudaGetLastError();                                  // fall through to the two-warp kernel
-    }
-    if (done) {
-    } else if (var != 2) {
-      const void* kern = (var == 1) ? (const void*)sbr_chase_kernel : (const void*)sbr_chase2_kernel;
-      const int threads = (var == 1) ? 32 : 64;
-      int per_sm = 1;
-      if (var == 1) PODSDF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sbr_chase_kernel, 32, 0));
-      else PODSDF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sbr_chase2_kernel, 64, 0));
-      long G = (long)sms * (per_sm < 4 ? per_sm : 4);           // all chains co-resident (cooperative launch checks it)
-      const long useful = (N + 2 * B - 1) / (2 * B) + 8;        // sweeps that can be in flight at once
-      if (G > useful) G = useful;
-      if (G > nsweep) G = nsweep;
-      PODSDF_CUDA(cudaLaunchCooperativeKernel(kern, dim3((unsigned)G), dim3(threads), args, 0, st));
-    } else {
-      PODSDF_CUDA(cudaFuncSetAttribute(sbr_chase_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHASE_SMEM));
-      long G = sms;                                             // one CTA per SM (the ring takes the shared memory)
-      const long useful = ((N + 2 * B - 1) / (2 * B) + 8 + CG - 1) / CG + 1;
-      const long bundles = (nsweep + CG - 1) / CG;
-      if (G > useful) G = useful;
-      if (G > bundles) G = bundles;
-      PODSDF_CUDA(cudaLaunchCooperativeKernel((const void*)sbr_chase_multi_kernel, dim3((unsigned)G), dim3(32 * CG), args,
-                                              CHASE_SMEM, st));
-    }
+    const void* kern = (var == 1) ? (const void*)sbr_chase_kernel : (const void*)sbr_chase2_kernel;
+    const int threads = (var == 1) ? 32 : 64;
+    int per_sm = 1;
+    if (var == 1) PODSDF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sbr_chase_kernel, 32, 0));
+    else PODSDF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sbr_chase2_kernel, 64, 0));
+    long G = (long)sms * (per_sm < 4 ? per_sm : 4);             // all chains co-resident (cooperative launch checks it)
+    const long useful = (N + 2 * B - 1) / (2 * B) + 8;          // sweeps that can be in flight at once
+    if (G > useful) G = useful;
+    if (G > nsweep) G = nsweep;
+    PODSDF_CUDA(cudaLaunchCooperativeKernel(kern, dim3((unsigned)G), dim3(threads), args, 0, st));
     count_launch();
   }
   sbr_band_to_tridiag_kernel<<<ceil_div(N, 256L), 256, 0, st>>>(w.Bb, N, d, e);
