@@ -176,7 +176,17 @@ int eig_top_inplace(int device, double* C_dev, long N, int nm, double* lambda_de
   bool fast_ok = false, side_pending = false;
   if (eligible) {
     PODSDF_CUDA(cudaMemcpyAsync(Ccopy, C_dev, sizeof(double) * nn, cudaMemcpyDeviceToDevice, st));
-    PODSDF_TRY(sbr_tridiagonalize(C_dev, N, d, e, wsbr, st, nullptr));
+    rc = sbr_tridiagonalize(C_dev, N, d, e, wsbr, st, nullptr);
+    if (rc) {                                   // e.g. a cooperative launch refused: the library solver still works
+      cudaGetLastError();
+      PODSDF_CUDA(cudaMemcpyAsync(C_dev, Ccopy, sizeof(double) * nn, cudaMemcpyDeviceToDevice, st));
+      rc = eig_inplace(device, C_dev, N, lambda_dev, st);
+      if (rc) return rc;
+      PODSDF_TRY(launch_rows_gather_descending(C_dev, N, nm, Z, st));
+      PODSDF_CUDA(cudaMemcpyAsync(C_dev, Z, sizeof(double) * zn, cudaMemcpyDeviceToDevice, st));
+      PODSDF_CUDA(cudaStreamSynchronize(st));
+      return 0;
+    }
     // leading nm+1 eigenvalues first (warp-wide multisection, on the caller's stream: the inverse iteration waits
     // for them); the other N-nm-1 by plain bisection on a side stream, concurrently with everything below
     const long first = N - 1 - nm;      // ascending index of the (nm+1)-th largest (>= 0 because 4 nm <= N)
