@@ -552,13 +552,21 @@ def main():
         else:
             shard.generate_injected(slabs, stream)
 
-    for _ in range(args.warmup):
-        df_step()
-    barrier()
+    # the clock sampler starts BEFORE the warm-up, so that it is certainly polling when the timed region begins
+    # (started after it, the first NVML sample sometimes arrived only after the ~0.1 s region had ended)
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler is not None and sampler.mode == "nvidia-smi":
         time.sleep(0.3)                                  # the CLI sampler needs time to start; NVML does not
+    for _ in range(args.warmup):
+        df_step()
     barrier()
+    if sampler is not None and sampler.mode == "nvml":
+        t_wait = time.time()
+        while not sampler.rows and time.time() - t_wait < 0.5:
+            time.sleep(0.002)
+        for _ in range(2):                               # re-warm after any wait: no idle gap before the timed steps
+            df_step()
+        barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     w0 = time.time()
     launches_before = capi.launch_count()

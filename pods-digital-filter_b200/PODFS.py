@@ -195,7 +195,8 @@ def select_fourier(c128, energy_target):
     cmT = np.ascontiguousarray(np.abs(c).T)                                # float32 magnitudes, one row per mode
     last = num_fcs - 1
     rev_index = (last - np.arange(num_fcs)).astype(np.uint64)
-    for i in range(num_modes):
+
+    def one_mode(i):
         cmod = cmT[i]
         # POD:1584 tuple sort, reversed: magnitude descending, ties -> higher index first.  The IEEE bit pattern of
         # a non-negative float32 is monotone in its value, so (~bits(|c|), N-1-index) packed in one uint64 is a
@@ -213,6 +214,15 @@ def select_fourier(c128, energy_target):
         if thresh > 0.0:
             run = np.cumsum(cmod[order].astype(np.float64))
             c_count[i] = min(int(np.searchsorted(run, thresh, side="left")) + 1, num_fcs)
+
+    if num_modes >= 8 and num_fcs >= 4096:
+        # the modes are independent and numpy's sort / cumsum release the interpreter lock: rank them on a few threads
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+            list(ex.map(one_mode, range(num_modes)))
+    else:
+        for i in range(num_modes):
+            one_mode(i)
     return c, c_ind, c_count
 
 

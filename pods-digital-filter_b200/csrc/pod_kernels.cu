@@ -266,27 +266,30 @@ size_t gram_workspace_bytes(long M, long N) {
 
 // ------------------------------------------------------------------------------------------------
 // Projection: Phi[row][m] = scale * dinv[m] * sum_t A[row][t] T[t][m]     (PODFS.py:1329-1333)
-//   CTA = 128 rows x 64 modes (grid.y walks mode blocks); 8 warps, warp tile 16 rows x 64 modes.
+//   CTA = 128 rows x 64 or 128 modes (mode blocks are neighbours in the grid); 8 warps, warp tile 16 rows x all modes.
 // ------------------------------------------------------------------------------------------------
-constexpr int PR = 128, PM = 64, PKB = 16, PST = 3;
+constexpr int PR = 128, PKB = 16, PST = 3;
 constexpr int PPA0 = PKB + 4;  // layout 0: A tile [128 rows][PKB + 4]
 constexpr int PPA1 = PR + 4;   // layout 1: A tile [PKB t][128 + 4]
-constexpr int PPT = PM + 4;    // T tile [PKB t][64 + 4]
 
-template <int LAYOUT>
+// PM = modes per CTA: 64, or 128 when more than 64 modes are asked for (config 4 keeps 100: one pass over A with
+// 13 of 16 column tiles live instead of two passes with 8 + 5 of 8)
+template <int LAYOUT, int PM>
 struct ProjSmem {
+  static constexpr int PPT = PM + 4;    // T tile [PKB t][PM + 4]
   static constexpr int ATILE = (LAYOUT == 0) ? PR * PPA0 : PKB * PPA1;
   static constexpr int TTILE = PKB * PPT;
   static constexpr size_t BYTES = (size_t)PST * (ATILE + TTILE) * sizeof(double);
 };
 
-template <int LAYOUT>
+template <int LAYOUT, int PM>
 __global__ void __launch_bounds__(256, 1)
 project_dmma_kernel(const double* __restrict__ A, const long M, const long N, const double* __restrict__ T,
                     const long ldT, const double* __restrict__ dinv, const int nm, const double scale,
                     double* __restrict__ Phi) {
   extern __shared__ double smem[];
-  constexpr int ATILE = ProjSmem<LAYOUT>::ATILE, TTILE = ProjSmem<LAYOUT>::TTILE;
+  constexpr int ATILE = ProjSmem<LAYOUT, PM>::ATILE, TTILE = ProjSmem<LAYOUT, PM>::TTILE, PPT = ProjSmem<LAYOUT, PM>::PPT;
+  constexpr int NTL = PM / 8;
   double* sA = smem;
   double* sT = smem + PST * ATILE;
   // mode blocks of the same rows are neighbours in the grid: the second one finds its A tiles in L2
@@ -297,7 +300,7 @@ project_dmma_kernel(const double* __restrict__ A, const long M, const long N, co
   const int lr = lane & 3, lc = lane >> 2;
   const int wr = warp * 16;
   const int nchunks = (int)((N + PKB - 1) / PKB);
-  const int ntl = min(8, (nm - m0 + 7) / 8);      // 8-mode column tiles that hold real modes (CTA-uniform)
+  const int ntl = min(NTL, (nm - m0 + 7) / 8);    // 8-mode column tiles that hold real modes (CTA-uniform)
 
   auto load_stage = [&](int chunk, int stage) {
     const long t0 = (long)chunk * PKB;
@@ -320,11 +323,11 @@ project_dmma_kernel(const double* __restrict__ A, const long M, const long N, co
     }
   };
 
-  double acc[2][8][2];
+  double acc[2][NTL][2];
 #pragma unroll
   for (int a = 0; a < 2; ++a)
 #pragma unroll
-    for (int b = 0; b < 8; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+    for (int b = 0; b < NTL; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
 
   for (int s = 0; s < PST - 1; ++s) {
     if (s < nchunks) load_stage(s, s);
@@ -339,18 +342,18 @@ project_dmma_kernel(const double* __restrict__ A, const long M, const long N, co
     const double* tt = sT + (c % PST) * TTILE;
 #pragma unroll
     for (int k4 = 0; k4 < PKB; k4 += 4) {
-      double af[2], bf[8];
+      double af[2], bf[NTL];
       const int t = k4 + lr;
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt)
         af[mt] = (LAYOUT == 0) ? a[(wr + mt * 8 + lc) * PPA0 + t] : a[t * PPA1 + wr + mt * 8 + lc];
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt)
+      for (int nt = 0; nt < NTL; ++nt)
         if (nt < ntl) bf[nt] = tt[t * PPT + nt * 8 + lc];
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt)
+        for (int nt = 0; nt < NTL; ++nt)
           if (nt < ntl) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
     }
   }
@@ -358,7 +361,7 @@ project_dmma_kernel(const double* __restrict__ A, const long M, const long N, co
 #pragma unroll
   for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
+    for (int nt = 0; nt < NTL; ++nt) {
       const long row = row0 + wr + mt * 8 + lc;
       const int m = m0 + nt * 8 + 2 * lr;
       if (row < M) {
@@ -368,23 +371,27 @@ project_dmma_kernel(const double* __restrict__ A, const long M, const long N, co
     }
 }
 
-int launch_project(const double* A, long M, long N, int layout, const double* T, long ldT, const double* dinv,
-                   int nm, double scale, double* Phi, cudaStream_t st) {
+template <int LAYOUT, int PM>
+static int launch_project_t(const double* A, long M, long N, const double* T, long ldT, const double* dinv, int nm,
+                            double scale, double* Phi, cudaStream_t st) {
   const long nblocks = ceil_div(M, (long)PR) * ceil_div(nm, PM);
   if (nblocks > 2147483647L) return fail(PODSDF_ERR_UNSUPPORTED, "too many tiles for one projection launch");
-  dim3 grid((unsigned)nblocks);
-  if (layout == 0) {
-    auto k = project_dmma_kernel<0>;
-    PODSDF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ProjSmem<0>::BYTES));
-    k<<<grid, 256, ProjSmem<0>::BYTES, st>>>(A, M, N, T, ldT, dinv, nm, scale, Phi);
-  } else {
-    auto k = project_dmma_kernel<1>;
-    PODSDF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ProjSmem<1>::BYTES));
-    k<<<grid, 256, ProjSmem<1>::BYTES, st>>>(A, M, N, T, ldT, dinv, nm, scale, Phi);
-  }
+  auto k = project_dmma_kernel<LAYOUT, PM>;
+  PODSDF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ProjSmem<LAYOUT, PM>::BYTES));
+  k<<<dim3((unsigned)nblocks), 256, ProjSmem<LAYOUT, PM>::BYTES, st>>>(A, M, N, T, ldT, dinv, nm, scale, Phi);
   count_launch();
   PODSDF_CUDA(cudaGetLastError());
   return 0;
+}
+
+int launch_project(const double* A, long M, long N, int layout, const double* T, long ldT, const double* dinv,
+                   int nm, double scale, double* Phi, cudaStream_t st) {
+  const bool wide = nm > 64;
+  if (layout == 0)
+    return wide ? launch_project_t<0, 128>(A, M, N, T, ldT, dinv, nm, scale, Phi, st)
+                : launch_project_t<0, 64>(A, M, N, T, ldT, dinv, nm, scale, Phi, st);
+  return wide ? launch_project_t<1, 128>(A, M, N, T, ldT, dinv, nm, scale, Phi, st)
+              : launch_project_t<1, 64>(A, M, N, T, ldT, dinv, nm, scale, Phi, st);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -833,6 +833,172 @@ sbr_chase2_kernel(double* __restrict__ Bb, const long N, double* __restrict__ V2
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Stage 2, four warps per task.  With two warps the task's own dependent arithmetic (~2.4 us) is what the 2 N-long
+// chain is made of (hand-offs through shared memory or DSMEM instead of L2 bought 6 %), so the
+// blocks are split once more by columns: warps 0 / 1 take columns 0-15 / 16-31 of the E-block chain, warps 2 / 3
+// those of the D block; partial matrix-vector products meet in shared memory behind 64-thread named barriers.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pair_barrier(const int id) {
+  asm volatile("bar.sync %0, 64;\n" ::"r"(id) : "memory");
+}
+
+__global__ void __launch_bounds__(128)
+sbr_chase4_kernel(double* __restrict__ Bb, const long N, double* __restrict__ V2, double* __restrict__ TAU2,
+                  const long ntask_max, unsigned* __restrict__ bar) {
+  __shared__ __align__(16) double sB[B][LDB];
+  __shared__ double sv[B], sv2[B], sz[B], sqD[2][B], sY[2][B], sP[2][B];
+  __shared__ double s_tau, s_tau2, s_beta2;
+  __shared__ int s_ok;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int half = warp & 1;                         // which 16 columns of its block this warp owns
+  const int cb = half * (B / 2);
+  unsigned* err = bar + 1;
+  unsigned* prog = bar + 2;
+  const long nsweep = N - 2;
+  for (long i = blockIdx.x; i < nsweep; i += gridDim.x) {
+    const int nt = (int)((N - 1 - i + B - 1) / B);
+    double v = 0.0, tau = 0.0;                       // warp 0: reflector of the current task (lane = row inside J_k)
+    for (int k = 0; k < nt; ++k) {
+      if (threadIdx.x == 0) {                        // dependency: sweep i-1 has finished task k+1
+        int ok = 1;
+        if (i > 0) {
+          const unsigned need = (unsigned)(k + 2);
+          unsigned spins = 0;
+          while (ld_acquire_u32(prog + i - 1) < need) {
+            if (++spins > (1u << 22)) {
+              if ((spins & 0xFFFFu) == 0 && ld_acquire_u32(err) != 0) { ok = 0; break; }
+              if (spins > (1u << 27)) { atomicExch(err, 2u); ok = 0; break; }
+            }
+          }
+        }
+        s_ok = ok;
+      }
+      __syncthreads();
+      if (!s_ok) return;
+      const long j0 = i + 1 + (long)k * B;
+      const int L = (int)min((long)B, N - j0);
+      const int L2 = (int)max(0L, min((long)B, N - j0 - B));
+#pragma unroll
+      for (int cc = 0; cc < B / 4; ++cc) {           // band columns j0 .. j0+L-1 (zero-filled beyond), a quarter per warp
+        const int c = warp * (B / 4) + cc;
+        cpa16_cg(&sB[c][2 * lane], Bb + (j0 + c) * LDB + 2 * lane, c < L);
+      }
+      cpa_commit();
+      if (warp == 0) {
+        if (k == 0) {                                // reflector of column i (overlaps the copies)
+          const double x = (lane < L) ? __ldcg(Bb + i * LDB + 1 + lane) : 0.0;
+          double beta;
+          warp_house(x, lane, v, tau, beta);
+          if (lane < L) __stcg(Bb + i * LDB + 1 + lane, lane == 0 ? beta : 0.0);
+        }
+        if (lane >= L) v = 0.0;
+        if (lane < L) V2[i * N + j0 + lane] = v;
+        if (lane == 0) {
+          TAU2[i * ntask_max + k] = tau;
+          s_tau = tau;
+        }
+        sv[lane] = v;
+      }
+      cpa_wait<0>();
+      __syncthreads();
+      const double tk = s_tau, vl = sv[lane];
+      if (warp >= 2) {
+        // ---- D <- H D H: p = tau D v (each warp sums its 16 columns), q = p - (tau/2)(p^T v) v, D -= v q^T + q v^T
+        double pp[2] = {0.0, 0.0};
+#pragma unroll
+        for (int cc = 0; cc < B / 2; ++cc) {
+          const int c = cb + cc;
+          const int idx = (c <= lane) ? c * LDB + lane - c : lane * LDB + c - lane;
+          pp[cc & 1] = fma((&sB[0][0])[idx], sv[c], pp[cc & 1]);
+        }
+        sP[half][lane] = pp[0] + pp[1];
+        pair_barrier(2);                             // both halves summed; nobody reads D any more
+        const double pl = tk * (sP[0][lane] + sP[1][lane]);
+        const double kk = 0.5 * tk * warp_sum(pl * vl);
+        const double ql = fma(-kk, vl, pl);
+        sqD[half][lane] = ql;                        // each warp keeps its own copy: no second barrier
+        __syncwarp();
+#pragma unroll
+        for (int cc = 0; cc < B / 2; ++cc) {
+          const int c = cb + cc;
+          if (c <= lane) sB[c][lane - c] -= fma(vl, sqD[half][c], ql * sv[c]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int cc = 0; cc < B / 2; ++cc) {         // write back column c, d in [0, L - c)
+          const int c = cb + cc;
+          const int len = L - c, d0 = 2 * lane;
+          double* dst = Bb + (j0 + c) * LDB + d0;
+          if (d0 + 1 < len) __stcg(reinterpret_cast<double2*>(dst), make_double2(sB[c][d0], sB[c][d0 + 1]));
+          else if (d0 < len) __stcg(dst, sB[c][d0]);
+        }
+      } else {
+        double v2 = 0.0, tau2 = 0.0;
+        if (L2 > 0) {
+          // ---- E <- E H (lane = row a of E; each warp its 16 columns)
+          double yy[2] = {0.0, 0.0};
+#pragma unroll
+          for (int cc = 0; cc < B / 2; ++cc) {
+            const int c = cb + cc;
+            yy[cc & 1] = fma(sB[c][B - c + lane], sv[c], yy[cc & 1]);
+          }
+          sY[half][lane] = yy[0] + yy[1];
+          pair_barrier(1);
+          const double yl = tk * (sY[0][lane] + sY[1][lane]);
+#pragma unroll
+          for (int cc = 0; cc < B / 2; ++cc) {
+            const int c = cb + cc;
+            sB[c][B - c + lane] = fma(-yl, sv[c], sB[c][B - c + lane]);
+          }
+          __syncwarp();
+          if (warp == 0) {                           // new reflector from the first column of E
+            double beta2;
+            warp_house(lane < L2 ? sB[0][B + lane] : 0.0, lane, v2, tau2, beta2);
+            if (lane >= L2) v2 = 0.0;
+            sv2[lane] = v2;
+            if (lane == 0) {
+              s_tau2 = tau2;
+              s_beta2 = beta2;
+            }
+          }
+          pair_barrier(1);
+          const double t2 = s_tau2, v2l = sv2[lane];
+          // ---- E <- H2 E: z_c = tau2 v2^T E[:, c]; lanes 0-15 / 16-31 sum rows 0-15 / 16-31 of column cb + (lane & 15)
+          {
+            const int c = cb + (lane & 15), a0 = (lane >> 4) * 16;
+            const double* col = &sB[c][B - c + a0];
+            double zz[2] = {0.0, 0.0};
+#pragma unroll
+            for (int a2 = 0; a2 < 16; ++a2) zz[a2 & 1] = fma(sv2[a0 + a2], col[a2], zz[a2 & 1]);
+            double zl = zz[0] + zz[1];
+            zl += __shfl_xor_sync(0xffffffffu, zl, 16);
+            if (lane < 16) sz[c] = t2 * zl;
+          }
+          __syncwarp();
+#pragma unroll
+          for (int cc = 0; cc < B / 2; ++cc) {
+            const int c = cb + cc;
+            sB[c][B - c + lane] = fma(-v2l, sz[c], sB[c][B - c + lane]);
+          }
+          if (warp == 0) sB[0][B + lane] = (lane == 0) ? s_beta2 : 0.0;     // exactly (beta, 0, ..., 0)
+          __syncwarp();
+#pragma unroll
+          for (int cc = 0; cc < B / 2; ++cc) {       // write back column c, d = B - c + a
+            const int c = cb + cc;
+            if (c < L && lane < L2) __stcg(Bb + (j0 + c) * LDB + B - c + lane, sB[c][B - c + lane]);
+          }
+        }
+        v = v2;
+        tau = tau2;
+      }
+      // ---- publish progress: the CTA barrier orders every warp's stores before thread 0's release store
+      __syncthreads();
+      if (threadIdx.x == 0) st_release_u32(prog + i, (k + 1 == nt) ? 0x7fffffffu : (unsigned)(k + 1));
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256)
 sbr_band_to_tridiag_kernel(const double* __restrict__ Bb, const long N, double* __restrict__ d, double* __restrict__ e) {
   const long c = blockIdx.x * 256L + threadIdx.x;
@@ -879,6 +1045,15 @@ sbr_back_q2_kernel(const double* __restrict__ V2, const double* __restrict__ TAU
     }
     const int nt = (int)((N - 1 - i + B - 1) / B);
     ptau = (tid < nt) ? __ldg(TAU2 + i * ntask_max + tid) : 0.0;
+    // pull the row of sweep i - 4 towards L2 (one request per 128-byte line): the register prefetch above is only
+    // one sweep deep, i.e. shorter than an HBM round trip, and every CTA walks the same rows at about the same time
+    if (i >= 4 && (tid & 15) == 0) {
+#pragma unroll
+      for (int q = 0; q < MAXPF; ++q) {
+        const long e = i - 3 + tid + (long)q * Q2_THREADS;
+        if (e < N) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(V2 + (i - 4) * N + e));
+      }
+    }
   };
   auto park = [&](long i) {
 #pragma unroll
@@ -1197,14 +1372,16 @@ static int sbr_stage2(long N, const SbrWs& w, double* d, double* e, cudaStream_t
     double *V2 = w.V2, *TAU2 = w.TAU2;
     unsigned* bar = w.bar;
     void* args[] = {&Bb, &Narg, &V2, &TAU2, &ntm, &bar};
-    // PODSDF_CHASE=1 (A/B only): one warp per task; default: two warps per task
+    // PODSDF_CHASE (A/B only): 1 = one warp per task, 2 = two warps; default: four warps per task
     const char* variant = getenv("PODSDF_CHASE");
     const int var = variant ? atoi(variant) : 0;
-    const void* kern = (var == 1) ? (const void*)sbr_chase_kernel : (const void*)sbr_chase2_kernel;
-    const int threads = (var == 1) ? 32 : 64;
+    const void* kern = (var == 1) ? (const void*)sbr_chase_kernel
+                                  : ((var == 2) ? (const void*)sbr_chase2_kernel : (const void*)sbr_chase4_kernel);
+    const int threads = (var == 1) ? 32 : ((var == 2) ? 64 : 128);
     int per_sm = 1;
     if (var == 1) PODSDF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sbr_chase_kernel, 32, 0));
-    else PODSDF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sbr_chase2_kernel, 64, 0));
+    else if (var == 2) PODSDF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sbr_chase2_kernel, 64, 0));
+    else PODSDF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sbr_chase4_kernel, 128, 0));
     long G = (long)sms * (per_sm < 4 ? per_sm : 4);             // all chains co-resident (cooperative launch checks it)
     const long useful = (N + 2 * B - 1) / (2 * B) + 8;          // sweeps that can be in flight at once
     if (G > useful) G = useful;
