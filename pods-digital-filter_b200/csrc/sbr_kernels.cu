@@ -1029,7 +1029,7 @@ __global__ void __launch_bounds__(Q2_THREADS, 1)
 sbr_back_q2_kernel(const double* __restrict__ V2, const double* __restrict__ TAU2, const long ntask_max, const long N,
                    double* __restrict__ Z) {
   extern __shared__ double smem_q2[];
-  const long NP = q2_idx(N) + 16;                    // padded length
+  const long NP = q2_idx(N) + 16 + 96;               // padded length (+ a zero tail for the last, short reflector)
   double* zs = smem_q2;
   double* vs = smem_q2 + NP;
   double* ts = smem_q2 + 2 * NP;                     // taus of the current sweep (ntask_max)
@@ -1068,34 +1068,43 @@ sbr_back_q2_kernel(const double* __restrict__ V2, const double* __restrict__ TAU
     park(N - 3);
   }
   __syncthreads();
-  const int sub = tid & 7;
+  // The applying loop is instruction-bound (every warp walks it for every sweep), so its index arithmetic is
+  // hoisted: with base = i + 1 + 32 k the padded index of entry base + r (r < 32) is c0 + 40 k + r + (carry ? 8 : 0),
+  // c0 = (i+1) + 8 ((i+1) >> 5), carry = ((i+1) & 31) + r >= 32 -- all 32-bit, the four offsets fixed per sweep.
+  // Entries beyond N are zero-padded in both arrays, so the last (short) reflector needs no bounds checks.
+  const int sub = tid & 7, kt = tid >> 3;
+  const unsigned gmask = 0xFFu << (tid & 24);
+  for (long r = N + tid; r < N + 64; r += Q2_THREADS) {
+    zs[q2_idx(r)] = 0.0;
+    vs[q2_idx(r)] = 0.0;
+  }
+  __syncthreads();
   for (long i = N - 3; i >= 0; --i) {
     if (i > 0) fetch(i - 1);
     const int nt = (int)((N - 1 - i + B - 1) / B);
-    for (int k0 = 0; k0 < nt; k0 += Q2_THREADS / 8) {        // CTA-uniform trip count
-      const int k = k0 + (tid >> 3);
-      const long e0 = i + 1 + (long)k * B + sub;             // this thread's entries: e0, e0+8, e0+16, e0+24
-      const bool on = k < nt;
+    const int i1 = (int)(i + 1), bo = i1 & 31;
+    const int c0 = i1 + ((i1 >> 5) << 3);
+    int off[4];
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      const int r = sub + 8 * jj;
+      off[jj] = r + ((bo + r >= 32) ? 8 : 0);
+    }
+    for (int k = kt; k < nt; k += Q2_THREADS / 8) {           // whole groups of 8 threads enter or skip together
+      const int cb2 = c0 + 40 * k;
       double vv[4], zz[4], dot = 0.0;
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj) {
-        const long e = e0 + 8 * jj;
-        const bool in = on && e < N;
-        vv[jj] = in ? vs[q2_idx(e)] : 0.0;
-        zz[jj] = in ? zs[q2_idx(e)] : 0.0;
+        vv[jj] = vs[cb2 + off[jj]];
+        zz[jj] = zs[cb2 + off[jj]];
         dot = fma(vv[jj], zz[jj], dot);
       }
-      dot += __shfl_xor_sync(0xffffffffu, dot, 1);
-      dot += __shfl_xor_sync(0xffffffffu, dot, 2);
-      dot += __shfl_xor_sync(0xffffffffu, dot, 4);
-      if (on) {
-        const double sfac = -ts[k] * dot;
+      dot += __shfl_xor_sync(gmask, dot, 1);         // the 8 threads of a reflector: trip counts differ between groups
+      dot += __shfl_xor_sync(gmask, dot, 2);
+      dot += __shfl_xor_sync(gmask, dot, 4);
+      const double sfac = -ts[k] * dot;
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-          const long e = e0 + 8 * jj;
-          if (e < N) zs[q2_idx(e)] = fma(sfac, vv[jj], zz[jj]);
-        }
-      }
+      for (int jj = 0; jj < 4; ++jj) zs[cb2 + off[jj]] = fma(sfac, vv[jj], zz[jj]);
     }
     __syncthreads();                                 // sweep i applied; its reflectors are no longer needed
     if (i > 0) park(i - 1);
@@ -1443,7 +1452,7 @@ int sbr_back_transform(const double* ws, long N, double* Z, int nvec, cudaStream
     return fail(PODSDF_ERR_UNSUPPORTED, "back-transformation: one eigenvector does not fit shared memory");
   {
     const long pfs = (N + Q2_THREADS - 1) / Q2_THREADS;          // prefetched entries per thread and sweep
-    const size_t q2_smem = sizeof(double) * (2 * (size_t)(N + 8 * (N / 32) + 16) + (size_t)w.ntask_max);
+    const size_t q2_smem = sizeof(double) * (2 * (size_t)(N + 8 * (N / 32) + 16 + 96) + (size_t)w.ntask_max);
 #define PODSDF_Q2(M)                                                                                         \
   do {                                                                                                       \
     auto k = sbr_back_q2_kernel<M>;                                                                          \
