@@ -560,11 +560,11 @@ def main():
     for _ in range(args.warmup):
         df_step()
     barrier()
-    if sampler is not None and sampler.mode == "nvml":
-        t_wait = time.time()
+    if sampler is not None and sampler.mode == "nvml" and not sampler.rows:
+        t_wait = time.time()                             # (rare) the poller has not delivered yet: wait, then re-warm
         while not sampler.rows and time.time() - t_wait < 0.5:
             time.sleep(0.002)
-        for _ in range(2):                               # re-warm after any wait: no idle gap before the timed steps
+        for _ in range(2):
             df_step()
         barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

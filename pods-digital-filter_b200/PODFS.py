@@ -215,14 +215,8 @@ def select_fourier(c128, energy_target):
             run = np.cumsum(cmod[order].astype(np.float64))
             c_count[i] = min(int(np.searchsorted(run, thresh, side="left")) + 1, num_fcs)
 
-    if num_modes >= 8 and num_fcs >= 4096:
-        # the modes are independent and numpy's sort / cumsum release the interpreter lock: rank them on a few threads
-        from concurrent.futures import ThreadPoolExecutor
-        with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
-            list(ex.map(one_mode, range(num_modes)))
-    else:
-        for i in range(num_modes):
-            one_mode(i)
+    for i in range(num_modes):      # (a thread pool over the modes was tried: 7x SLOWER, the per-mode numpy calls are too short)
+        one_mode(i)
     return c, c_ind, c_count
 
 

@@ -1017,100 +1017,85 @@ constexpr int Q2_THREADS = 1024;
 
 // Q2: one eigenvector per CTA, held in shared memory.  The reflectors of one sweep act on disjoint 32-element
 // ranges; EIGHT threads share one reflector (4 entries each, 3 shuffle rounds).  A warp per reflector was bound by
-// the shuffle unit (one warp-instruction per clock and SM: 36 ms at N = 10^4, 100 vectors), a thread per reflector
-// by the latency of 64 dependent shared-memory operations on too few warps (42 ms) -- profiles/r02_sbr_profile.md.
-// z and the current reflector row live in shared memory with 8 pads per 32 entries (neighbouring reflectors of a
-// half-warp land in different banks for every sweep offset); the row of sweep i-1 and its taus are fetched
-// (coalesced) into registers while sweep i is applied and parked in shared memory afterwards.
+// the shuffle unit (one warp-instruction per clock and SM: 32-36 ms at N = 10^4, 100 vectors), a thread per
+// reflector by the latency of 64 dependent shared-memory operations on too few warps (42 ms), and staging each
+// reflector row through shared memory by the address arithmetic and the second barrier of the staging (29 ms) --
+// profiles/r02_sbr_profile.md.  So each thread fetches exactly the entries it will use, one sweep ahead, straight
+// into registers (two register sets swap roles, no copies): one barrier per sweep, and the loop body is 8 LDS + 8
+// FMA + 3 shuffles + 4 STS per reflector quarter.  z lives in shared memory with 8 pads per 32 entries, so that the
+// two reflectors of a half-warp land in different banks for every sweep offset.
 __device__ __forceinline__ long q2_idx(long e) { return e + ((e >> 5) << 3); }
+constexpr int Q2F_THREADS = 512;
 
-template <int MAXPF>
-__global__ void __launch_bounds__(Q2_THREADS, 1)
+template <int MAXIT>
+__global__ void __launch_bounds__(Q2F_THREADS, 1)
 sbr_back_q2_kernel(const double* __restrict__ V2, const double* __restrict__ TAU2, const long ntask_max, const long N,
                    double* __restrict__ Z) {
-  extern __shared__ double smem_q2[];
-  const long NP = q2_idx(N) + 16 + 96;               // padded length (+ a zero tail for the last, short reflector)
+  extern __shared__ double smem_q2[];                // z[e] at zs[q2_idx(e)], zero tail beyond N
   double* zs = smem_q2;
-  double* vs = smem_q2 + NP;
-  double* ts = smem_q2 + 2 * NP;                     // taus of the current sweep (ntask_max)
   const int tid = threadIdx.x;
-  double* z = Z + (long)blockIdx.x * N;
-  for (long r = tid; r < N; r += Q2_THREADS) zs[q2_idx(r)] = z[r];
-  double pf[MAXPF], ptau = 0.0;
-  auto fetch = [&](long i) {                         // entries i+1 .. N-1 of row i of V2 and the sweep's taus
-#pragma unroll
-    for (int q = 0; q < MAXPF; ++q) {
-      const long e = i + 1 + tid + (long)q * Q2_THREADS;
-      pf[q] = (e < N) ? __ldg(V2 + i * N + e) : 0.0;
-    }
-    const int nt = (int)((N - 1 - i + B - 1) / B);
-    ptau = (tid < nt) ? __ldg(TAU2 + i * ntask_max + tid) : 0.0;
-    // pull the row of sweep i - 4 towards L2 (one request per 128-byte line): the register prefetch above is only
-    // one sweep deep, i.e. shorter than an HBM round trip, and every CTA walks the same rows at about the same time
-    if (i >= 4 && (tid & 15) == 0) {
-#pragma unroll
-      for (int q = 0; q < MAXPF; ++q) {
-        const long e = i - 3 + tid + (long)q * Q2_THREADS;
-        if (e < N) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(V2 + (i - 4) * N + e));
-      }
-    }
-  };
-  auto park = [&](long i) {
-#pragma unroll
-    for (int q = 0; q < MAXPF; ++q) {
-      const long e = i + 1 + tid + (long)q * Q2_THREADS;
-      if (e < N) vs[q2_idx(e)] = pf[q];
-    }
-    if (tid < ntask_max) ts[tid] = ptau;
-  };
-  if (N >= 3) {
-    fetch(N - 3);
-    park(N - 3);
-  }
-  __syncthreads();
-  // The applying loop is instruction-bound (every warp walks it for every sweep), so its index arithmetic is
-  // hoisted: with base = i + 1 + 32 k the padded index of entry base + r (r < 32) is c0 + 40 k + r + (carry ? 8 : 0),
-  // c0 = (i+1) + 8 ((i+1) >> 5), carry = ((i+1) & 31) + r >= 32 -- all 32-bit, the four offsets fixed per sweep.
-  // Entries beyond N are zero-padded in both arrays, so the last (short) reflector needs no bounds checks.
   const int sub = tid & 7, kt = tid >> 3;
   const unsigned gmask = 0xFFu << (tid & 24);
-  for (long r = N + tid; r < N + 64; r += Q2_THREADS) {
-    zs[q2_idx(r)] = 0.0;
-    vs[q2_idx(r)] = 0.0;
-  }
-  __syncthreads();
-  for (long i = N - 3; i >= 0; --i) {
-    if (i > 0) fetch(i - 1);
+  double* z = Z + (long)blockIdx.x * N;
+  for (long r = tid; r < N + 64; r += Q2F_THREADS) zs[q2_idx(r)] = (r < N) ? z[r] : 0.0;
+  // entries sub, sub+8, sub+16, sub+24 of reflector kt + it * 64 of sweep i (zero beyond the matrix), and its tau
+  auto fetch = [&](long i, double (&v)[MAXIT][4], double (&t)[MAXIT]) {
+    const int nt = (int)((N - 1 - i + B - 1) / B);
+    const double* row = V2 + i * N + i + 1;
+    const long len = N - 1 - i;
+#pragma unroll
+    for (int it = 0; it < MAXIT; ++it) {
+      const int k = kt + it * (Q2F_THREADS / 8);
+      const long o = (long)k * B + sub;
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) v[it][jj] = (o + 8 * jj < len) ? __ldg(row + o + 8 * jj) : 0.0;
+      t[it] = (k < nt) ? __ldg(TAU2 + i * ntask_max + k) : 0.0;
+    }
+  };
+  auto apply = [&](long i, const double (&v)[MAXIT][4], const double (&t)[MAXIT]) {
     const int nt = (int)((N - 1 - i + B - 1) / B);
     const int i1 = (int)(i + 1), bo = i1 & 31;
-    const int c0 = i1 + ((i1 >> 5) << 3);
+    const int c0 = i1 + ((i1 >> 5) << 3);            // padded index of entry i+1; entry i+1+32k+r sits 40k + r (+8) on
     int off[4];
 #pragma unroll
     for (int jj = 0; jj < 4; ++jj) {
       const int r = sub + 8 * jj;
       off[jj] = r + ((bo + r >= 32) ? 8 : 0);
     }
-    for (int k = kt; k < nt; k += Q2_THREADS / 8) {           // whole groups of 8 threads enter or skip together
-      const int cb2 = c0 + 40 * k;
-      double vv[4], zz[4], dot = 0.0;
 #pragma unroll
-      for (int jj = 0; jj < 4; ++jj) {
-        vv[jj] = vs[cb2 + off[jj]];
-        zz[jj] = zs[cb2 + off[jj]];
-        dot = fma(vv[jj], zz[jj], dot);
+    for (int it = 0; it < MAXIT; ++it) {
+      const int k = kt + it * (Q2F_THREADS / 8);
+      if (k < nt) {                                  // whole groups of 8 threads enter or skip together
+        const int cb2 = c0 + 40 * k;
+        double zz[4], dot = 0.0;
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          zz[jj] = zs[cb2 + off[jj]];
+          dot = fma(v[it][jj], zz[jj], dot);
+        }
+        dot += __shfl_xor_sync(gmask, dot, 1);
+        dot += __shfl_xor_sync(gmask, dot, 2);
+        dot += __shfl_xor_sync(gmask, dot, 4);
+        const double sfac = -t[it] * dot;
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) zs[cb2 + off[jj]] = fma(sfac, v[it][jj], zz[jj]);
       }
-      dot += __shfl_xor_sync(gmask, dot, 1);         // the 8 threads of a reflector: trip counts differ between groups
-      dot += __shfl_xor_sync(gmask, dot, 2);
-      dot += __shfl_xor_sync(gmask, dot, 4);
-      const double sfac = -ts[k] * dot;
-#pragma unroll
-      for (int jj = 0; jj < 4; ++jj) zs[cb2 + off[jj]] = fma(sfac, vv[jj], zz[jj]);
     }
-    __syncthreads();                                 // sweep i applied; its reflectors are no longer needed
-    if (i > 0) park(i - 1);
+  };
+  double va[MAXIT][4], vb[MAXIT][4], ta[MAXIT], tb[MAXIT];
+  if (N >= 3) fetch(N - 3, va, ta);
+  __syncthreads();
+  for (long i = N - 3; i >= 0; i -= 2) {             // two sweeps per trip: the register sets swap roles
+    if (i >= 1) fetch(i - 1, vb, tb);
+    apply(i, va, ta);
     __syncthreads();
+    if (i >= 1) {
+      if (i >= 2) fetch(i - 2, va, ta);
+      apply(i - 1, vb, tb);
+      __syncthreads();
+    }
   }
-  for (long r = tid; r < N; r += Q2_THREADS) z[r] = zs[q2_idx(r)];
+  for (long r = tid; r < N; r += Q2F_THREADS) z[r] = zs[q2_idx(r)];
 }
 
 // Q2 for vectors too long for the layout above (two padded arrays): only z in shared memory, one warp per reflector
@@ -1451,22 +1436,23 @@ int sbr_back_transform(const double* ws, long N, double* Z, int nvec, cudaStream
   if (one + fixed > (size_t)max_smem)
     return fail(PODSDF_ERR_UNSUPPORTED, "back-transformation: one eigenvector does not fit shared memory");
   {
-    const long pfs = (N + Q2_THREADS - 1) / Q2_THREADS;          // prefetched entries per thread and sweep
-    const size_t q2_smem = sizeof(double) * (2 * (size_t)(N + 8 * (N / 32) + 16 + 96) + (size_t)w.ntask_max);
+    const long its = (w.ntask_max + Q2F_THREADS / 8 - 1) / (Q2F_THREADS / 8);   // reflectors per thread group and sweep
+    const size_t q2_smem = sizeof(double) * (size_t)(N + 8 * (N / 32) + 16 + 96);
 #define PODSDF_Q2(M)                                                                                         \
   do {                                                                                                       \
     auto k = sbr_back_q2_kernel<M>;                                                                          \
     PODSDF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)q2_smem));         \
-    k<<<nvec, Q2_THREADS, q2_smem, st>>>(w.V2, w.TAU2, w.ntask_max, N, Z);                                   \
+    k<<<nvec, Q2F_THREADS, q2_smem, st>>>(w.V2, w.TAU2, w.ntask_max, N, Z);                                  \
   } while (0)
-    if (q2_smem + 2048 > (size_t)max_smem || pfs > 14 || w.ntask_max > Q2_THREADS) {
+    if (q2_smem + 2048 > (size_t)max_smem || its > 6) {
       if (one + 2048 > (size_t)max_smem)
         return fail(PODSDF_ERR_UNSUPPORTED, "back-transformation: one eigenvector does not fit shared memory");
       PODSDF_CUDA(cudaFuncSetAttribute(sbr_back_q2_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)one));
       sbr_back_q2_long_kernel<<<nvec, Q2_THREADS, one, st>>>(w.V2, w.TAU2, w.ntask_max, N, Z);
-    } else if (pfs <= 4) PODSDF_Q2(4);
-    else if (pfs <= 10) PODSDF_Q2(10);
-    else PODSDF_Q2(14);
+    } else if (its <= 2) PODSDF_Q2(2);
+    else if (its <= 4) PODSDF_Q2(4);
+    else if (its <= 5) PODSDF_Q2(5);
+    else PODSDF_Q2(6);
 #undef PODSDF_Q2
   }
   if (2 * one + fixed <= (size_t)max_smem) {
