@@ -625,9 +625,14 @@ int launch_df_time(const DfGeom& g, const PanelGeom& panel, const Taps& bx, cons
           default: break;
         }
       }
-      switch (nt) {          // from 33 taps on the tensor path wins; beyond, the DFMA register window no longer fits
-        F(33) F(49) F(65) F(97) F(129)
-        default: break;
+      // from 33 taps on the tensor path wins over the pair kernel; beyond, a DFMA register window no longer fits.
+      // The U32 stream's ring-of-8 kernel still holds 33 taps (ring of 40 registers): env PODSDF_TIME_VARIANT=4
+      // routes nf = 16 there (A/B; measured in profiles/r02_config5_sweep.md)
+      if (!(nt == 33 && src == kSrcU32 && g_time_variant == 4)) {
+        switch (nt) {
+          F(33) F(49) F(65) F(97) F(129)
+          default: break;
+        }
       }
 #undef F
     }

@@ -23,6 +23,7 @@
 #include "sbr_kernels.cuh"
 
 #include <cfloat>
+#include <cmath>
 #include <cstdlib>
 
 namespace podsdf {
@@ -1314,11 +1315,26 @@ static int sbr_stage1(double* A, long N, const SbrWs& w, cudaStream_t st) {
     // 1b: X = A22 V, split over K so that the grid fills the machine
     const int row_tiles = (int)((N + XR - 1) / XR - r0 / XR);        // absolute tiles that reach rows >= r0
     const int total_chunks = (int)((N + XKB - 1) / XKB - r0 / XKB);
-    int nsplit = (4 * 148 + row_tiles - 1) / row_tiles;          // two CTAs per SM, two waves
-    if (nsplit > w.max_split) nsplit = w.max_split;
-    int cps = (total_chunks + nsplit - 1) / nsplit;
-    cps = ((cps + 7) / 8) * 8;                               // whole 128-column blocks per split
-    nsplit = (total_chunks + cps - 1) / cps;
+    // split over K: two CTAs fit an SM, so pick the split whose grid fills whole waves of 2 x 148 CTAs best
+    // (at least ~2 waves when the matrix allows it, chunks of whole 128-column blocks)
+    int nsplit = 1, cps = ((total_chunks + 7) / 8) * 8;
+    {
+      double best = -1.0;
+      for (int cand = 1; cand <= w.max_split; ++cand) {
+        int c2 = (total_chunks + cand - 1) / cand;
+        c2 = ((c2 + 7) / 8) * 8;
+        const int ns = (total_chunks + c2 - 1) / c2;
+        const double ctas = (double)row_tiles * ns, slots = 2.0 * 148.0;
+        const double waves = ctas / slots;
+        double eff = waves / ceil(waves);
+        if (waves < 1.0) eff = waves * 0.9;                  // under-filled grids: more CTAs are better
+        if (eff > best + 1e-9) {
+          best = eff;
+          nsplit = ns;
+          cps = c2;
+        }
+      }
+    }
     sbr_symm_kernel<<<dim3(row_tiles, nsplit), 256, XSMEM, st>>>(A, N, r0, Vk, w.Xp, cps);
     // 1c / 1d: W
     const int wct = (int)((n + WR - 1) / WR);
