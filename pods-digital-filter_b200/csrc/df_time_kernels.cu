@@ -626,9 +626,9 @@ int launch_df_time(const DfGeom& g, const PanelGeom& panel, const Taps& bx, cons
         }
       }
       // from 33 taps on the tensor path wins over the pair kernel; beyond, a DFMA register window no longer fits.
-      // The U32 stream's ring-of-8 kernel still holds 33 taps (ring of 40 registers): env PODSDF_TIME_VARIANT=4
-      // routes nf = 16 there (A/B; measured in profiles/r02_config5_sweep.md)
-      if (!(nt == 33 && src == kSrcU32 && g_time_variant == 4)) {
+      // The U32 stream's ring-of-8 kernel still holds 33 taps (ring of 40 registers) and beats the tensor path there
+      // (1.29 vs 1.94 ms per 512 planes, profiles/r02_config5_sweep.md); PODSDF_TIME_VARIANT=2 forces the tensor path
+      if (!(nt == 33 && src == kSrcU32 && g_time_variant != 2)) {
         switch (nt) {
           F(33) F(49) F(65) F(97) F(129)
           default: break;
