@@ -606,6 +606,26 @@ def main():
 
     info = plan.info()
     assert info["passes"] == n_passes, (info, n_passes)
+    # ---- the same shard with a rotated plane normal: the rotation couples the components (DF:1119-1131), so the
+    # three-component plane kernel runs instead of the per-component one (short leg: 1 warm-up + 2 timed steps)
+    rotated = None
+    if args.rng == "philox":
+        plan.set_rotation(df.prof_rotation_matrix(0.6, -0.48, 0.64))
+        df_step()
+        barrier()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record(stream)
+        for _ in range(2):
+            df_step()
+        r1.record(stream)
+        barrier()
+        ms_rot = max_over_ranks(r0.elapsed_time(r1)) / 2
+        tt_r, tp_r = plan.last_kernel_ms()
+        rotated = {"value": world * n_planes / (ms_rot * 1e-3), "unit": "planes/s", "ms_per_step": ms_rot, "normal": [0.6, -0.48, 0.64],
+                   "time_filter_ms": tt_r, "plane_filter_ms": tp_r,
+                   "plane_kernel": "df_plane_panel_kernel (three components per CTA, rotation applied after the Lund step)",
+                   "plane_kernel_frac_of_hbm": 24.0 * ((J + 2 * nf) * (K + 2 * nf) + J * K) * n_planes / (tp_r * 1e-3) / 1e9 / measured_peaks()[0]}
+        plan.set_rotation(None)
     # ---- roofline of the dominant kernel (K-plane: yz filter + Lund, one launch per pass of <= DF_CHUNK planes)
     b_plane, b_time, fl_total, fl_plane = df_algorithmic(J, K, nf, nf, nf)
     if args.rng == "injected":
@@ -705,7 +725,7 @@ def main():
                        "kernels": "tuned" if (info["tuned_time"] and info["tuned_plane"]) else "generic",
                        "planes_per_pass": info["chunk"]},
             "roofline": roofline, "step_roofline": step_roofline, "cpu_baseline": cpu, "e2e": e2e, "cfg1": cfg1,
-            "multi_gpu": multi, "gpu_launches": launches_timed,
+            "multi_gpu": multi, "rotated_normal": rotated, "gpu_launches": launches_timed,
             "gpu_launches_total": launches_all, "clocks": clocks, "sustained": sustained, "pod": pod,
         }
         _emit(line)

@@ -361,3 +361,52 @@ def test_field_statistics_kernels_and_reconstruction_check(P):
     assert np.abs(st["mean_reconstructed"].cpu().numpy()).max() < 1e-12    # fluctuation field: zero mean
     # covariances: reconstruction variance = generated variance minus the discarded energy (per unit volume)
     assert abs((st["cov_generated"][0] - st["cov_reconstructed"][0])) <= st["cov_generated"][0]
+
+
+@pytest.mark.parametrize("N,kind", [(300, "gram"), (515, "indef"), (1029, "gram")])
+def test_two_stage_tridiagonalisation(P, N, kind):
+    """The library-free reduction behind podsdf_eig_sym_top_* (csrc/sbr_kernels.cu): the band matrix after stage 1 and
+    the tridiagonal matrix after stage 2 are orthogonally similar to C -- their spectra equal LAPACK's spectrum of C to
+    rounding -- for a Gram-like (decaying spectrum + noise floor) and an indefinite symmetric matrix, sizes that are not
+    multiples of the panel width or of the tile size."""
+    from scipy.linalg import eigvalsh_tridiagonal
+    rs = np.random.RandomState(N)
+    if kind == "gram":
+        r = min(N, 120)
+        X = rs.standard_normal((r, N)) * (np.arange(1, r + 1)[:, None] ** -0.8)
+        X = np.concatenate([X, 1e-3 * rs.standard_normal((N, N))])
+        C = X.T @ X / N
+    else:
+        A = rs.standard_normal((N, N))
+        C = (A + A.T) / 2
+    lam = np.linalg.eigvalsh(C)
+    nrm = np.abs(lam).max()
+    d, e, band, ms = P._capi.sym_tridiag(C, want_band=True)
+    Bm = np.zeros((N, N))
+    for dd in range(33):
+        v = band[:N - dd, dd]
+        Bm[np.arange(dd, N), np.arange(N - dd)] = v
+        Bm[np.arange(N - dd), np.arange(dd, N)] = v
+    assert np.abs(np.linalg.eigvalsh(Bm) - lam).max() < 1e-12 * nrm
+    assert np.abs(eigvalsh_tridiagonal(d, e) - lam).max() < 1e-12 * nrm
+    assert abs(d.sum() - np.trace(C)) < 1e-11 * nrm * N
+
+
+def test_packed_triangle_roundtrip(P):
+    """podsdf_sym_pack_dev / _unpack_dev (the Gram all-reduce moves N (N + 1) / 2 doubles): unpack(pack(C)) == C for an
+    exactly symmetric C, and the packed order is row-major over j >= i."""
+    torch = pytest.importorskip("torch")
+    capi = P._capi
+    L = capi.lib()
+    N = 301
+    rs = np.random.RandomState(3)
+    A = rs.standard_normal((N, N))
+    C = A + A.T
+    Cd = torch.from_numpy(C).cuda()
+    packed = torch.empty(N * (N + 1) // 2, dtype=torch.float64, device="cuda")
+    out = torch.full((N, N), float("nan"), dtype=torch.float64, device="cuda")
+    capi.check(L.podsdf_sym_pack_dev(0, Cd.data_ptr(), N, packed.data_ptr(), 0))
+    capi.check(L.podsdf_sym_unpack_dev(0, packed.data_ptr(), N, out.data_ptr(), 0))
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy(), C)
+    assert np.array_equal(packed.cpu().numpy(), C[np.triu_indices(N)])
