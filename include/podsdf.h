@@ -146,6 +146,9 @@ PODSDF_API int podsdf_gram_dev(int device, const double* A_dev, long M, long N, 
  * C[i][j], j >= i; unpack writes both triangles. */
 PODSDF_API int podsdf_sym_pack_dev(int device, const double* C_dev, long N, double* packed_dev, void* stream);
 PODSDF_API int podsdf_sym_unpack_dev(int device, const double* packed_dev, long N, double* C_dev, void* stream);
+/* The PODFS entries keep grow-only per-device scratch between calls (Gram split workspace, eigen-solver workspace:
+ * ~3 N^2 doubles after a leading-pairs solve); this frees it (synchronises the device first). */
+PODSDF_API int podsdf_release_scratch(int device);
 /* device time (ms) of the last Gram kernel on this thread */
 PODSDF_API int podsdf_gram_last_ms(double* ms);
 

@@ -55,6 +55,7 @@ SIGNATURES = {
     "podsdf_mean_rows_dev": [_i, _vp, _l, _l, _i, _vp, _i, _vp],
     "podsdf_gram_host": [_i, _vp, _l, _l, _i, _vp, _l, _d, _vp],
     "podsdf_gram_dev": [_i, _vp, _l, _l, _i, _vp, _l, _d, _vp, _vp],
+    "podsdf_release_scratch": [_i],
     "podsdf_gram_last_ms": [_vp],
     "podsdf_sym_pack_dev": [_i, _vp, _l, _vp, _vp],
     "podsdf_sym_unpack_dev": [_i, _vp, _l, _vp, _vp],
@@ -265,6 +266,11 @@ class DfPlan(object):
 
 
 # ---------------------------------------------------------------------------------- PODFS entries
+def release_scratch(device=0):
+    """Free the grow-only device scratch the PODFS entries keep between calls."""
+    check(lib().podsdf_release_scratch(device))
+
+
 def gram(A, layout=LAYOUT_ROWS_BY_TIME, w=None, scale=1.0, C=None, device=0):
     """C = scale * A^T diag(w) A for the (M x N) snapshot matrix in the given layout."""
     A = f64(A, name="A")

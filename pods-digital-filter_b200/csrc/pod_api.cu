@@ -39,6 +39,16 @@ int scratch_get(int device, int slot, size_t bytes, double** out) {
   return 0;
 }
 
+int scratch_release(int device) {
+  std::lock_guard<std::mutex> lk(g_scratch_mu);
+  for (Scratch& s : g_scratch[device & 63]) {
+    if (s.p) cudaFree(s.p);
+    s.p = nullptr;
+    s.bytes = 0;
+  }
+  return 0;
+}
+
 struct DevBuf {  // RAII device allocation
   double* p = nullptr;
   cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 8); }
@@ -298,6 +308,13 @@ int podsdf_gram_dev(int device, const double* A_dev, long M, long N, int layout,
   cudaEventDestroy(e1);
   if (!rc && e != cudaSuccess) rc = cuda_fail(e, "gram", __FILE__, __LINE__);
   return rc;
+}
+
+int podsdf_release_scratch(int device) {
+  PODSDF_TRY(check_device(device));
+  DeviceGuard guard(device);
+  PODSDF_CUDA(cudaDeviceSynchronize());
+  return scratch_release(device);
 }
 
 int podsdf_gram_last_ms(double* ms) {
