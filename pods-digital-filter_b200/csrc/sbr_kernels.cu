@@ -6,8 +6,9 @@
 // matrix-vector products: 0.64 s at N = 10^4); here:
 //
 //   stage 1  dense -> band of half-width b = 32.  Per 32-column panel:
-//              QR of the panel below the band    one cooperative kernel, thread = panel row (registers), one grid
-//                                                barrier per column; also yields the T factor of the block reflector
+//              QR of the panel below the band    one cooperative kernel, thread = panel row (registers), one exchange
+//                                                of partial sums per column through flagged mailbox entries; the T
+//                                                factor of the block reflector by a one-warp kernel behind it
 //              X = A22 V                         FP64 tensor-core MMA (mma.sync m8n8k4), lower triangle read in both
 //                                                orientations, split over K
 //              W = X T - 1/2 V (T^T V^T X T)     two small kernels
@@ -21,6 +22,10 @@
 // Storage: A is N x N with element (r, c) at A[c*N + r] (symmetric, so row- and column-major coincide); skinny
 // matrices are k-major: V[m*N + r] is entry (r, m).  tools/proto_sbr.py is the numpy model of every step below.
 #include "sbr_kernels.cuh"
+
+#include <atomic>
+#include <vector>
+#include <cstdio>
 
 #include <cfloat>
 #include <cmath>
@@ -81,40 +86,99 @@ __device__ __forceinline__ bool grid_barrier(unsigned* counter, unsigned* err, u
   return s_ok != 0;
 }
 
+// ---- flagged 16-byte mailbox entries {lo, flag, hi, flag}: value and "it is there" travel in ONE store and ONE load,
+// each 8-byte half validated by its own copy of the flag (the low-latency protocol of collective libraries).  Replaces
+// "store, fence, count, poll the counter, then load" (three L2 round trips) by one; a flag is never reused: it carries
+// the launch's epoch.
+__device__ __forceinline__ void ll_store(uint4* p, const double v, const unsigned flag) {
+  const unsigned lo = (unsigned)__double2loint(v), hi = (unsigned)__double2hiint(v);
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};\n" ::"l"(p), "r"(lo), "r"(flag), "r"(hi), "r"(flag)
+               : "memory");
+}
+__device__ __forceinline__ bool ll_try(const uint4* p, const unsigned flag, double& v) {
+  unsigned a, b, c, d;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];\n" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(p) : "memory");
+  v = __hiloint2double((int)c, (int)a);
+  return b == flag && d == flag;
+}
+
 // ------------------------------------------------------------------------------------------------
-// Stage 1a: Householder QR of the panel A[r0:N, c0:c0+B] (n = N - r0 rows), LAPACK dgeqr2 + dlarft in one pass.
-//   thread = one panel row, its B entries in registers; column j needs only ONE global reduction: with
-//   S_m = sum_{rows > j} P[r][j] P[r][m] (m >= j) every thread derives beta, tau, v and the update of its row
-//   (v^T P[:, m] = P[j][m] + S_m / (alpha - beta)).  The same reduction carries g_i = V[:, i]^T v_{j-1} (i < j-1)
-//   for the T factor: T[:j, j] = -tau_j T[:j, :j] (V[:, :j]^T v_j).
-//   Partials go through part[phase & 1][cta][B]; every CTA sums them in the same order -> identical values.
-// Outputs: R (upper triangle) back into A, V rows c0 .. c0+B-1 of Vall (explicit ones / zeros), T (B x B, row-major).
+// Stage 1a: Householder QR of the panel A[r0:N, c0:c0+B] (n = N - r0 rows), LAPACK dgeqr2 in one pass.
+//   Column j needs only ONE global reduction: with S_m = sum_{rows > j} P[r][j] P[r][m] (m >= j) every thread derives
+//   beta, tau, v and the update of its entries (v^T P[:, m] = P[j][m] + S_m / (alpha - beta)).  The same reduction
+//   carries g_i = V[:, i]^T v_{j-1} (i < j-1) for the T factor (dlarft), which sbr_tfactor_kernel builds off the
+//   critical path from Gq = [g | tau].
+//   CTA = 256 panel rows x 4 column octets = 1024 threads: thread = (row, 8 columns) in registers, warp = 32 rows of
+//   one octet.  The chain of 33 steps is latency-bound, so the work per thread and step is kept short (8 products,
+//   9 double shuffles by recursive halving) and spread over 32 warps; a thread-per-row version (32 products, 31
+//   shuffles, 8 warps) spent 3.8 k cycles in each of the two compute phases of a step (profiles/r02_sbr_profile.md).
+//   The CTAs exchange their partial sums and row j through mailbox entries mail[j & 1][cta | G][B]: every CTA reads
+//   all of them and adds them up in the same order -> identical reflectors everywhere, no grid barrier.  A CTA can
+//   write parity (j & 1) again only after everybody has published step j + 1, i.e. has finished reading step j.
+// Outputs: R (upper triangle) back into A, V rows c0 .. c0+B-1 of Vall (explicit ones / zeros), Gq (B x B + B).
 // ------------------------------------------------------------------------------------------------
-constexpr int QR_THREADS = 256;    // 8 warps: the row + the reduction tree need ~170 registers per thread
+constexpr int QR_ROWS = 256;                 // panel rows per CTA
+constexpr int QR_OCT = 8;                    // columns per thread
+constexpr int QR_THREADS = QR_ROWS * (B / QR_OCT);
+constexpr int QR_WARPS = QR_THREADS / 32;
+
+// The step's work on one thread's 8 columns depends on where column j lies relative to the octet: D = j - 8 * octet,
+// clamped to -2 (octet entirely right of j + 1), -1 .. 8, 9 (entirely left of j - 1).  D is warp-uniform, so the
+// kernel switches over 12 compile-time variants instead of predicating every column on j (which cost 670 instructions
+// per warp and step, 5 % of them floating point: profiles/r02_sbr_profile.md).
+template <int D>
+__device__ __forceinline__ void qr_terms(const double (&p)[QR_OCT], const double fa, const double fb, double (&t)[QR_OCT]) {
+#pragma unroll
+  for (int s = 0; s < QR_OCT; ++s) {
+    if (D < 0 || (D <= 8 && s >= D)) t[s] = fa * p[s];             // column >= j: dot with column j
+    else if (D == 9 || s < D - 1) t[s] = fb * p[s];               // column < j - 1: V[:, i]^T v_{j-1}
+    else t[s] = 0.0;                                              // column j - 1
+  }
+}
+template <int D>
+__device__ __forceinline__ void qr_update(double (&p)[QR_OCT], const bool mine, const bool top, const double v,
+                                          const double tv, const double beta, const double scale,
+                                          const double2* __restrict__ sr, double* __restrict__ next_col) {
+  if (mine) {
+#pragma unroll
+    for (int s = 0; s < QR_OCT; ++s) {
+      if (D < 0 || (D <= 8 && s > D)) {
+        const double2 x = sr[s];                                  // {S_m, R_m}
+        p[s] = fma(-tv, fma(scale, x.x, x.y), p[s]);
+      } else if (D >= 0 && s == D) {
+        p[s] = top ? beta : v;
+      }
+    }
+  }
+  if (D >= -1 && D <= 6) *next_col = p[D + 1];                    // column j + 1 for everybody's next step
+}
 
 __global__ void __launch_bounds__(QR_THREADS, 1)
 sbr_panel_qr_kernel(double* __restrict__ A, const long N, const int c0, double* __restrict__ Vall,
-                    double* __restrict__ Tout, double* __restrict__ part, double* __restrict__ rowj,
+                    double* __restrict__ Gq, uint4* __restrict__ mail, const unsigned epoch,
                     unsigned* __restrict__ bar) {
-  __shared__ double s_red[QR_THREADS / 32][B];
-  __shared__ double s_S[B], s_R[B], s_T[B][B + 1], s_tau[B];
-  __shared__ double s_part[QR_THREADS];         // the partials of up to QR_THREADS / B CTAs at a time
+  __shared__ double s_red[QR_WARPS][QR_OCT];
+  __shared__ double2 s_SR[B];                  // {S_m, R_m}
+  __shared__ double s_scal[4];
+  __shared__ double s_part[QR_THREADS];        // thread (q, m): the partials of CTAs q, q + QR_WARPS, ... for slot m
+  __shared__ double s_pj[2][QR_ROWS];          // column j of the panel, one entry per row of the CTA
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int oct = warp & 3, rl = (warp >> 2) * 32 + lane;      // column octet, row within the CTA
   const int G = gridDim.x, cta = blockIdx.x;
   const long r0 = c0 + B;
   const long n = N - r0;
-  const long row = (long)cta * QR_THREADS + tid;
+  const long row = (long)cta * QR_ROWS + rl;
   const bool active = row < n;
-  unsigned* counter = bar;
   unsigned* err = bar + 1;
+  const bool up4 = (lane & 4) != 0, up2 = (lane & 2) != 0, up1 = (lane & 1) != 0;
 
-  double p[B];
+  double p[QR_OCT];
 #pragma unroll
-  for (int m = 0; m < B; ++m) p[m] = active ? A[(long)(c0 + m) * N + r0 + row] : 0.0;
-  if (cta == 0)
-    for (int e = tid; e < B * (B + 1); e += QR_THREADS) (&s_T[0][0])[e] = 0.0;
+  for (int s = 0; s < QR_OCT; ++s) p[s] = active ? A[(long)(c0 + oct * QR_OCT + s) * N + r0 + row] : 0.0;
+  if (oct == 0) s_pj[0][rl] = p[0];
+  double vprev = 0.0;                            // v_{j-1}[row]
+  __syncthreads();
 
-  unsigned phase = 0;
 #ifdef PODSDF_CHASE_PROFILE
   long long qc[4] = {0, 0, 0, 0};
   long long qlast = clock64();
@@ -125,124 +189,180 @@ sbr_panel_qr_kernel(double* __restrict__ A, const long N, const int c0, double* 
 #pragma unroll 1
   for (int j = 0; j <= B; ++j) {
     QCLK(3)
-    // p[j] and p[j-1] without dynamic register indexing
-    double pj = 0.0, pjm1 = 0.0;
-#pragma unroll
-    for (int m = 0; m < B; ++m) {
-      if (m == j) pj = p[m];
-      if (m == j - 1) pjm1 = p[m];
-    }
-    // ---- phase A: this row's contributions.  slots m >= j: P[r][j] P[r][m] over rows > j (column j's norm and dots);
-    // slots i < j-1: V[r][i] v_{j-1}[r] over rows >= j-1 (T factor of the column finished in the previous step)
+    const unsigned flag = epoch * 64u + (unsigned)(j + 1);
+    uint4* box = mail + (size_t)(j & 1) * (G + 1) * B;
+    const double pj = (j < B) ? s_pj[j & 1][rl] : 0.0;
+    const int d = j - QR_OCT * oct;
+    const int cls = d < -1 ? -2 : (d > 8 ? 9 : d);
+    // ---- phase A: this thread's contributions.  slots m >= j: P[r][j] P[r][m] over rows > j (column j's norm and
+    // dots); slots i < j-1: V[r][i] v_{j-1}[r] over rows >= j-1 (T factor of the column finished in the previous step)
     const double fa = (j < B && active && row > j) ? pj : 0.0;
-    const double fb = (j >= 1 && active) ? ((row > j - 1) ? pjm1 : (row == j - 1 ? 1.0 : 0.0)) : 0.0;
-    // 32 sums over the 32 lanes of a warp by recursive halving: 31 double shuffles per lane instead of 160 (the
-    // shuffle unit moves one warp per clock per SM: 16 warps x 320 SHFL was the whole phase, r02_sbr_profile.md).
-    // After the five rounds lane l holds the total of slot l.
+    const double fb = vprev;
+    if (j < B && row == j) {                       // the owners of row j post it (zeros when the panel is shorter)
+#pragma unroll
+      for (int s = 0; s < QR_OCT; ++s) ll_store(box + (size_t)G * B + oct * QR_OCT + s, p[s], flag);
+    }
     {
-      double a[B / 2];
-      auto term = [&](int m) { return (m >= j) ? fa * p[m] : ((m < j - 1) ? fb * p[m] : 0.0); };
-      {                                            // first round straight from the products: 16 live values
-        const bool up = (lane & (B / 2)) != 0;
-#pragma unroll
-        for (int q = 0; q < B / 2; ++q) {
-          const double lo = term(q), hi = term(q + B / 2);
-          a[q] = (up ? hi : lo) + __shfl_xor_sync(0xffffffffu, up ? lo : hi, B / 2);
-        }
+      double t[QR_OCT];
+      switch (cls) {
+        case -2: qr_terms<-2>(p, fa, fb, t); break;
+        case -1: qr_terms<-1>(p, fa, fb, t); break;
+        case 0: qr_terms<0>(p, fa, fb, t); break;
+        case 1: qr_terms<1>(p, fa, fb, t); break;
+        case 2: qr_terms<2>(p, fa, fb, t); break;
+        case 3: qr_terms<3>(p, fa, fb, t); break;
+        case 4: qr_terms<4>(p, fa, fb, t); break;
+        case 5: qr_terms<5>(p, fa, fb, t); break;
+        case 6: qr_terms<6>(p, fa, fb, t); break;
+        case 7: qr_terms<7>(p, fa, fb, t); break;
+        case 8: qr_terms<8>(p, fa, fb, t); break;
+        default: qr_terms<9>(p, fa, fb, t); break;
       }
+      // 8 sums over the 32 lanes (rows) of a warp: three rounds of recursive halving (4 + 2 + 1 shuffles), after
+      // which lane l holds slot (l & 7) summed over 8 lanes, then two butterfly rounds over the other lane bits
+      double a4[4], a2[2], a1;
 #pragma unroll
-      for (int half = B / 4; half >= 1; half >>= 1) {
-        const bool up = (lane & half) != 0;
+      for (int q = 0; q < 4; ++q) a4[q] = (up4 ? t[q + 4] : t[q]) + __shfl_xor_sync(0xffffffffu, up4 ? t[q] : t[q + 4], 4);
 #pragma unroll
-        for (int q = 0; q < half; ++q) {
-          const double send = up ? a[q] : a[q + half];
-          const double keep = up ? a[q + half] : a[q];
-          a[q] = keep + __shfl_xor_sync(0xffffffffu, send, half);
-        }
-      }
-      s_red[warp][lane] = a[0];
+      for (int q = 0; q < 2; ++q) a2[q] = (up2 ? a4[q + 2] : a4[q]) + __shfl_xor_sync(0xffffffffu, up2 ? a4[q] : a4[q + 2], 2);
+      a1 = (up1 ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, up1 ? a2[0] : a2[1], 1);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, 8);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, 16);
+      if (lane < QR_OCT) s_red[warp][lane] = a1;
     }
     __syncthreads();
-    if (tid < B) {
+    if (tid < B) {                                 // slot tid: octet tid / 8 -> warps (tid / 8), (tid / 8) + 4, ...
       double v = 0.0;
 #pragma unroll
-      for (int w = 0; w < QR_THREADS / 32; ++w) v += s_red[w][tid];
-      __stcg(part + ((long)(j & 1) * G + cta) * B + tid, v);
-    }
-    if (j < B && active && row == j) {
-#pragma unroll
-      for (int m = 0; m < B; ++m) __stcg(rowj + (j & 1) * B + m, p[m]);
+      for (int g = 0; g < QR_WARPS / 4; ++g) v += s_red[g * 4 + (tid >> 3)][tid & 7];
+      ll_store(box + (size_t)cta * B + tid, v, flag);
     }
     QCLK(0)
-    if (!grid_barrier(counter, err, ++phase)) return;
-    QCLK(1)
-    // ---- phase B: everyone sums the partials in the same order
+    // ---- phase B: collect everybody's partial sums; thread (q, m) takes CTAs q, q + QR_WARPS, ... of slot m, two in
+    // flight at a time, and adds them in CTA order
+    int fail = 0;
+    double rj = 0.0;
     {
-      // all threads fetch (L2: other CTAs' data) in one round trip, then B threads add the partial sums up -- in
-      // the same order in every CTA, so everybody derives identical reflectors
-      double rj = 0.0, v = 0.0;
-      if (tid < B && j < B) rj = __ldcg(rowj + (j & 1) * B + tid);
-      double acc = 0.0;                              // thread (q, m) adds CTAs q, q + 8, ... : one round trip
-      for (int g2 = tid / B; g2 < G; g2 += QR_THREADS / B)
-        acc += __ldcg(part + ((long)(j & 1) * G + g2) * B + (tid % B));
-      s_part[tid] = acc;
-      __syncthreads();
-      if (tid < B) {
-#pragma unroll
-        for (int q = 0; q < QR_THREADS / B; ++q) v += s_part[q * B + tid];
+      double acc = 0.0;
+      for (int g0 = warp; g0 < G; g0 += 2 * QR_WARPS) {
+        const uint4* e0 = box + (size_t)g0 * B + lane;
+        const uint4* e1 = e0 + (size_t)QR_WARPS * B;
+        double val0 = 0.0, val1 = 0.0;
+        bool need0 = true, need1 = g0 + QR_WARPS < G;
+        unsigned spins = 0;
+        while (need0 || need1) {
+          if (need0) need0 = !ll_try(e0, flag, val0);
+          if (need1) need1 = !ll_try(e1, flag, val1);
+          if ((need0 || need1) && ++spins > (1u << 16)) {
+            if ((spins & 0xFFFu) == 0 && ld_acquire_u32(err) != 0) { fail = 1; break; }
+            if (spins > (1u << 23)) { atomicExch(err, 2u); fail = 1; break; }
+          }
+        }
+        acc += val0 + val1;
       }
-      if (tid < B) {
-        s_S[tid] = v;
-        s_R[tid] = rj;
+      s_part[tid] = acc;
+      if (tid < B && j < B && !fail) {
+        unsigned spins = 0;
+        while (!ll_try(box + (size_t)G * B + tid, flag, rj)) {
+          if (++spins > (1u << 23)) { atomicExch(err, 2u); fail = 1; break; }
+        }
+      }
+    }
+    if (__syncthreads_or(fail)) return;
+    QCLK(1)
+    if (tid < B) {                                 // warp 0: totals (same order in every CTA), then the reflector's scalars
+      double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+#pragma unroll
+      for (int q = 0; q < QR_WARPS; q += 4) {
+        v0 += s_part[q * B + tid];
+        v1 += s_part[(q + 1) * B + tid];
+        v2 += s_part[(q + 2) * B + tid];
+        v3 += s_part[(q + 3) * B + tid];
+      }
+      const double v = (v0 + v1) + (v2 + v3);
+      s_SR[tid] = make_double2(v, rj);
+      if (cta == 0 && j >= 1 && tid < j - 1) Gq[(j - 1) * B + tid] = v;   // g of the column finished in step j-1
+      if (j < B) {
+        const double alpha = __shfl_sync(0xffffffffu, rj, j), sigma = __shfl_sync(0xffffffffu, v, j);
+        double beta = alpha, tau = 0.0, scale = 0.0;
+        if (sigma > 0.0) {
+          beta = -copysign(sqrt(fma(alpha, alpha, sigma)), alpha);
+          tau = (beta - alpha) / beta;
+          scale = 1.0 / (alpha - beta);
+        }
+        if (tid == 0) {
+          s_scal[0] = beta;
+          s_scal[1] = tau;
+          s_scal[2] = scale;
+          if (cta == 0) Gq[B * B + j] = tau;
+        }
       }
     }
     __syncthreads();
-    if (cta == 0 && j >= 1 && tid < j - 1) {            // T[:j-1, j-1] = -tau_{j-1} T[:j-1, :j-1] g, g = s_S[0 .. j-2]
-      double acc = 0.0;
-      for (int l = tid; l < j - 1; ++l) acc = fma(s_T[tid][l], s_S[l], acc);
-      s_T[tid][j - 1] = -s_tau[j - 1] * acc;
-    }
     if (j < B) {
-      const double alpha = s_R[j], sigma = s_S[j];
-      double beta = alpha, tau = 0.0, scale = 0.0;
-      if (sigma > 0.0) {
-        beta = -copysign(sqrt(fma(alpha, alpha, sigma)), alpha);
-        tau = (beta - alpha) / beta;
-        scale = 1.0 / (alpha - beta);
+      const double beta = s_scal[0], tau = s_scal[1], scale = s_scal[2];
+      const bool mine = active && row >= j, top = row == j;
+      const double v = mine ? (top ? 1.0 : pj * scale) : 0.0;
+      const double tv = tau * v;
+      const double2* sr = s_SR + oct * QR_OCT;
+      double* nc = &s_pj[(j + 1) & 1][rl];
+      switch (cls) {
+        case -2: qr_update<-2>(p, mine, top, v, tv, beta, scale, sr, nc); break;
+        case -1: qr_update<-1>(p, mine, top, v, tv, beta, scale, sr, nc); break;
+        case 0: qr_update<0>(p, mine, top, v, tv, beta, scale, sr, nc); break;
+        case 1: qr_update<1>(p, mine, top, v, tv, beta, scale, sr, nc); break;
+        case 2: qr_update<2>(p, mine, top, v, tv, beta, scale, sr, nc); break;
+        case 3: qr_update<3>(p, mine, top, v, tv, beta, scale, sr, nc); break;
+        case 4: qr_update<4>(p, mine, top, v, tv, beta, scale, sr, nc); break;
+        case 5: qr_update<5>(p, mine, top, v, tv, beta, scale, sr, nc); break;
+        case 6: qr_update<6>(p, mine, top, v, tv, beta, scale, sr, nc); break;
+        case 7: qr_update<7>(p, mine, top, v, tv, beta, scale, sr, nc); break;
+        case 8: qr_update<8>(p, mine, top, v, tv, beta, scale, sr, nc); break;
+        default: break;                            // octet left of column j - 1: finished
       }
-      if (cta == 0 && tid == 0) {
-        s_tau[j] = tau;
-        s_T[j][j] = tau;
-      }
-      if (active && row >= j) {
-        const bool top = row == j;
-        const double v = top ? 1.0 : pj * scale;
-        const double tv = tau * v;
-#pragma unroll
-        for (int m = 0; m < B; ++m) {
-          if (m > j) p[m] = fma(-tv, fma(scale, s_S[m], s_R[m]), p[m]);
-          if (m == j) p[m] = top ? beta : v;
-        }
-      }
+      vprev = v;
     }
     __syncthreads();
     QCLK(2)
   }
 #ifdef PODSDF_CHASE_PROFILE
   if (tid == 0 && cta == 0 && (c0 == 0 || c0 == 4992))
-    printf("qr c0 %d G %d: cycles per column: phaseA %lld, barrier %lld, phaseB %lld, loop %lld\n", c0, G, qc[0] / (B + 1),
+    printf("qr c0 %d G %d: cycles per column: phaseA %lld, wait %lld, phaseB %lld, loop %lld\n", c0, G, qc[0] / (B + 1),
            qc[1] / (B + 1), qc[2] / (B + 1), qc[3] / (B + 1));
 #endif
   // ---- write back: R (rows < B, upper triangle incl. diagonal) into A; V (unit lower trapezoid) into Vall
   if (active) {
 #pragma unroll
-    for (int m = 0; m < B; ++m) {
-      if (row <= m) A[(long)(c0 + m) * N + r0 + row] = p[m];
-      Vall[(long)(c0 + m) * N + r0 + row] = (row > m) ? p[m] : (row == m ? 1.0 : 0.0);
+    for (int s = 0; s < QR_OCT; ++s) {
+      const int m = oct * QR_OCT + s;
+      if (row <= m) A[(long)(c0 + m) * N + r0 + row] = p[s];
+      Vall[(long)(c0 + m) * N + r0 + row] = (row > m) ? p[s] : (row == m ? 1.0 : 0.0);
     }
   }
-  if (cta == 0)
-    for (int e = tid; e < B * B; e += QR_THREADS) Tout[e] = s_T[e / B][e % B];
+}
+
+// T factor of the panel's block reflector (dlarft, forward / columnwise) from Gq = [g (B x B) | tau (B)]:
+//   T[j][j] = tau_j,  T[:j, j] = -tau_j T[:j, :j] g_j,  g_j[l] = V[:, l]^T v_j (l < j).
+// Row i of T only depends on row i: one lane per row, no synchronisation.  Runs behind the QR on its stream, beside
+// the symm kernel of the same panel (T is first needed by sbr_s_kernel).
+__global__ void __launch_bounds__(B)
+sbr_tfactor_kernel(const double* __restrict__ Gq, double* __restrict__ Tout) {
+  __shared__ double sT[B][B + 1], sG[B][B + 1], sTau[B];
+  const int i = threadIdx.x;
+  for (int m = 0; m < B; ++m) {
+    sT[i][m] = 0.0;
+    sG[m][i] = Gq[m * B + i];                    // coalesced; sG[j][l] = g_j[l]
+  }
+  sTau[i] = Gq[B * B + i];
+  __syncwarp();
+  sT[i][i] = sTau[i];
+  for (int j = i + 1; j < B; ++j) {
+    double acc = 0.0;
+    for (int l = i; l < j; ++l) acc = fma(sT[i][l], sG[j][l], acc);
+    sT[i][j] = -sTau[j] * acc;
+  }
+  __syncwarp();
+  for (int m = 0; m < B; ++m) Tout[m * B + i] = sT[m][i];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -438,42 +558,74 @@ sbr_w2_kernel(const double* __restrict__ X, const double* __restrict__ V, const 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Stage 1e: A22 -= V W^T + W V^T on the tiles (I >= J) of the trailing matrix (diagonal tiles in full).
-//   CTA = 128 x 128 tile, 8 warps x (64 x 32), K = 2B in chunks of 16 (gram-kernel micro-kernel, layout [k][128+4]):
+// Stage 1e: A22 -= V W^T + W V^T on the tiles (I >= J) of the trailing matrix (diagonal 128-blocks in full).
+//   CTA = 128 (i) x 64 (j) tile, 4 warps x (64 x 32), K = 2B resident in shared memory ([k][pitch], the gram kernel's
+//   micro-kernel); two CTAs per SM, so that one CTA's loads (old tile -> accumulators, operands -> shared memory) and
+//   stores overlap the other's DMMAs -- at K = 64 they are half of a tile's time (profiles/r02_sbr_profile.md).
 //   operand a (rows i): k < B -> -V[k][i], else -W[k-B][i];  operand b (rows j): k < B -> W[k][j], else V[k-B][j].
 //   The accumulators start as the old tile, so the epilogue is a plain store.
+//   Tiles are anchored at absolute multiples of 128 rows / 64 columns (see sbr_symm_kernel); with h = 1 when r0 lies in
+//   the upper half of its 128-block, row r (from the block of r0) holds the column blocks 0 .. 2r + 1 - h.
 // ------------------------------------------------------------------------------------------------
-constexpr int UT = 128, UKB = 16, UP = UT + 4;
-constexpr size_t USMEM = (size_t)2 * 2 * B * UP * sizeof(double);
+constexpr int UT = 128, UTJ = 64, UPA = UT + 4, UPB = UTJ + 4;
+constexpr int U_THREADS = 128;
+constexpr size_t USMEM = (size_t)2 * B * (UPA + UPB) * sizeof(double);
 
-__global__ void __launch_bounds__(256, 1)
+__device__ __forceinline__ void cpa16(void* smem_dst, const void* gsrc, bool valid) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int bytes = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gsrc), "r"(bytes) : "memory");
+}
+
+// number of CTAs of one update: part 0 = every tile, 1 = the first column block only (it holds the next panel),
+// 2 = the other column blocks -- parts 1 + 2 let the next panel's QR overlap most of the update
+static inline long syr2k_ctas(long N, long r0, int part) {
+  const long side = (N + UT - 1) / UT - r0 / UT;
+  const long h = (r0 % UT) / UTJ;
+  if (part == 1) return side;
+  if (part == 2) return side * side - h * side;
+  return side * (side + 1) - h * side;
+}
+
+__global__ void __launch_bounds__(U_THREADS, 2)
 sbr_syr2k_kernel(double* __restrict__ A, const long N, const long r0, const double* __restrict__ V,
                  const double* __restrict__ W, const int part) {
   extern __shared__ double smem[];
-  double* sA = smem;                    // [2B][UP]
-  double* sB = smem + 2 * B * UP;       // [2B][UP]
-  // part 0: every lower tile (ib >= jb);  part 1: the first tile column only (jb = 0: it holds the next panel);
-  // part 2: the other tile columns (jb >= 1) -- parts 1 + 2 let the next panel's QR overlap most of the update
-  int ib = 0, rem = blockIdx.x;         // linear id -> (ib >= jb): row ib holds ib + 1 tiles
-  if (part == 1) {
-    ib = blockIdx.x;
-    rem = 0;
-  } else {
-    while (rem > ib) { rem -= ib + 1; ++ib; }
-    if (part == 2) { ++ib; ++rem; }
-  }
-  const long tile0 = r0 / UT;           // tiles anchored at absolute multiples of 128 (see sbr_symm_kernel)
-  const long i0 = (tile0 + ib) * UT, j0 = (tile0 + rem) * UT;
+  double* sA = smem;                    // [2B][UPA]
+  double* sB = smem + 2 * B * UPA;      // [2B][UPB]
+  const long tile0 = r0 / UT;
+  const int h = (int)((r0 % UT) / UTJ);
+  int r = 0, rem = blockIdx.x;          // linear id -> (row r, column block rem)
+  for (int cnt = (part == 2 ? 1 : 2) - h; rem >= cnt; cnt += 2) { rem -= cnt; ++r; }
+  if (part == 1) { r = blockIdx.x; rem = 0; }
+  if (part == 2) ++rem;
+  const long i0 = (tile0 + r) * UT, j0 = (2 * tile0 + h + rem) * UTJ;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm = (warp >> 2) * 64, wn = (warp & 3) * 32;
+  const int wm = (warp >> 1) * 64, wn = (warp & 1) * 32;
   const int lr = lane & 3, lc = lane >> 2;
 
-  for (int e = tid; e < 2 * B * UT; e += 256) {
-    const int k = e / UT, x = e % UT;
-    const double* pa = (k < B) ? V + (long)k * N : W + (long)(k - B) * N;
-    const double* pb = (k < B) ? W + (long)k * N : V + (long)(k - B) * N;
-    cpa8(sA + k * UP + x, pa + i0 + x, (i0 + x >= r0) && (i0 + x < N));
-    cpa8(sB + k * UP + x, pb + j0 + x, (j0 + x >= r0) && (j0 + x < N));
+  if ((N & 1) == 0) {                   // rows of V / W start 16-byte aligned: two entries per copy
+    for (int e = tid; e < 2 * B * (UT / 2); e += U_THREADS) {
+      const int k = e / (UT / 2), x = 2 * (e % (UT / 2));
+      const double* pa = (k < B) ? V + (long)k * N : W + (long)(k - B) * N;
+      cpa16(sA + k * UPA + x, pa + i0 + x, (i0 + x >= r0) && (i0 + x < N));
+    }
+    for (int e = tid; e < 2 * B * (UTJ / 2); e += U_THREADS) {
+      const int k = e / (UTJ / 2), x = 2 * (e % (UTJ / 2));
+      const double* pb = (k < B) ? W + (long)k * N : V + (long)(k - B) * N;
+      cpa16(sB + k * UPB + x, pb + j0 + x, (j0 + x >= r0) && (j0 + x < N));
+    }
+  } else {
+    for (int e = tid; e < 2 * B * UT; e += U_THREADS) {
+      const int k = e / UT, x = e % UT;
+      const double* pa = (k < B) ? V + (long)k * N : W + (long)(k - B) * N;
+      cpa8(sA + k * UPA + x, pa + i0 + x, (i0 + x >= r0) && (i0 + x < N));
+    }
+    for (int e = tid; e < 2 * B * UTJ; e += U_THREADS) {
+      const int k = e / UTJ, x = e % UTJ;
+      const double* pb = (k < B) ? W + (long)k * N : V + (long)(k - B) * N;
+      cpa8(sB + k * UPB + x, pb + j0 + x, (j0 + x >= r0) && (j0 + x < N));
+    }
   }
   cpa_commit();
 
@@ -492,11 +644,11 @@ sbr_syr2k_kernel(double* __restrict__ A, const long N, const long r0, const doub
 #pragma unroll 4
   for (int k4 = 0; k4 < 2 * B; k4 += 4) {
     double af[8], bf[4];
-    const int r = k4 + lr;
+    const int rr = k4 + lr;
 #pragma unroll
-    for (int mt = 0; mt < 8; ++mt) af[mt] = -sA[r * UP + wm + mt * 8 + lc];
+    for (int mt = 0; mt < 8; ++mt) af[mt] = -sA[rr * UPA + wm + mt * 8 + lc];
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt) bf[nt] = sB[r * UP + wn + nt * 8 + lc];
+    for (int nt = 0; nt < 4; ++nt) bf[nt] = sB[rr * UPB + wn + nt * 8 + lc];
 #pragma unroll
     for (int mt = 0; mt < 8; ++mt)
 #pragma unroll
@@ -1213,7 +1365,7 @@ sbr_back_q1_kernel(const double* __restrict__ Vall, const double* __restrict__ T
 // workspace layout
 // ------------------------------------------------------------------------------------------------
 struct SbrWs {
-  double *Vall, *Tall, *W, *X, *Xp, *Zp, *S, *part, *rowj, *Bb, *V2, *TAU2;
+  double *Vall, *Tall, *W, *X, *Xp, *Zp, *S, *mail, *Gq, *Bb, *V2, *TAU2;
   unsigned* bar;      // [0] barrier counter, [1] error flag, [2..] sweep progress (N)
   long npanel, ntask_max;
   int max_split, max_qr_ctas;
@@ -1230,7 +1382,7 @@ static SbrWs sbr_layout(double* ws, long N, size_t* total) {
   w.npanel = sbr_npanel(N);
   w.ntask_max = (N + B - 1) / B + 1;
   w.max_split = 16;
-  w.max_qr_ctas = (int)((N + QR_THREADS - 1) / QR_THREADS);
+  w.max_qr_ctas = (int)((N + QR_ROWS - 1) / QR_ROWS);
   size_t off = 0;
   auto take = [&](size_t cnt) {
     double* q = ws + off;
@@ -1244,8 +1396,8 @@ static SbrWs sbr_layout(double* ws, long N, size_t* total) {
   w.Xp = take((size_t)w.max_split * B * N);
   w.Zp = take((size_t)((N + WR - 1) / WR) * B * B);
   w.S = take((size_t)B * B);
-  w.part = take((size_t)2 * w.max_qr_ctas * B);
-  w.rowj = take((size_t)2 * B);
+  w.mail = take((size_t)2 * (w.max_qr_ctas + 1) * B * 2);      // 16-byte mailbox entries, two parities
+  w.Gq = take((size_t)B * B + B);
   w.Bb = take((size_t)N * LDB);
   w.V2 = take((size_t)N * N);
   w.TAU2 = take((size_t)N * w.ntask_max);
@@ -1263,7 +1415,7 @@ size_t sbr_workspace_doubles(long N) {
 // second (high-priority) stream + events per device: the QR of panel k+1 runs beside the bulk of panel k's update
 struct SbrStreams {
   cudaStream_t qr = nullptr;
-  cudaEvent_t head = nullptr, qr_done = nullptr;
+  cudaEvent_t head = nullptr, qr_done = nullptr, t_done = nullptr;
   bool ok = false;
 };
 static SbrStreams& sbr_streams(int dev) {
@@ -1274,24 +1426,30 @@ static SbrStreams& sbr_streams(int dev) {
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
     x.ok = cudaStreamCreateWithPriority(&x.qr, cudaStreamNonBlocking, hi) == cudaSuccess &&
            cudaEventCreateWithFlags(&x.head, cudaEventDisableTiming) == cudaSuccess &&
-           cudaEventCreateWithFlags(&x.qr_done, cudaEventDisableTiming) == cudaSuccess;
+           cudaEventCreateWithFlags(&x.qr_done, cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&x.t_done, cudaEventDisableTiming) == cudaSuccess;
   }
   return x;
 }
 
-static int sbr_launch_qr(double* A, long N, long k, const SbrWs& w, cudaStream_t st) {
+static int sbr_launch_qr(double* A, long N, long k, const SbrWs& w, cudaStream_t st, cudaEvent_t after_qr) {
+  static std::atomic<unsigned> epochs{0};
   const int c0 = (int)(k * B);
   const long n = N - c0 - B;
-  PODSDF_CUDA(cudaMemsetAsync(w.bar, 0, sizeof(unsigned), st));       // barrier counter (the error flag stays)
-  const int G = (int)((n + QR_THREADS - 1) / QR_THREADS);
+  const int G = (int)((n + QR_ROWS - 1) / QR_ROWS);
   double* Aarg = A;
   long Narg = N;
   int c0arg = c0;
-  double *Varg = w.Vall, *Targ = w.Tall + k * B * B, *parg = w.part, *rarg = w.rowj;
+  double *Varg = w.Vall, *garg = w.Gq;
+  uint4* marg = reinterpret_cast<uint4*>(w.mail);
+  unsigned earg = (epochs.fetch_add(1u) + 1u) & 0x03FFFFFFu;          // flag = epoch * 64 + step: 26 bits of epoch
+  if (earg == 0) earg = (epochs.fetch_add(1u) + 1u) & 0x03FFFFFFu;
   unsigned* barg = w.bar;
-  void* args[] = {&Aarg, &Narg, &c0arg, &Varg, &Targ, &parg, &rarg, &barg};
+  void* args[] = {&Aarg, &Narg, &c0arg, &Varg, &garg, &marg, &earg, &barg};
   PODSDF_CUDA(cudaLaunchCooperativeKernel((const void*)sbr_panel_qr_kernel, dim3(G), dim3(QR_THREADS), args, 0, st));
-  count_launch();
+  if (after_qr) PODSDF_CUDA(cudaEventRecord(after_qr, st));
+  sbr_tfactor_kernel<<<1, B, 0, st>>>(w.Gq, w.Tall + k * B * B);      // off the critical path: T is first used by 1d
+  count_launch(2);
   return 0;
 }
 
@@ -1306,7 +1464,21 @@ static int sbr_stage1(double* A, long N, const SbrWs& w, cudaStream_t st) {
   }
   SbrStreams& ss = sbr_streams(dev);
   if (!ss.ok) return fail(PODSDF_ERR_CUDA, "stream creation failed");
-  if (w.npanel > 0) PODSDF_TRY(sbr_launch_qr(A, N, 0, w, st));
+  // mailbox flags of earlier solves (or whatever the allocation held) must not look like this solve's
+  PODSDF_CUDA(cudaMemsetAsync(w.mail, 0, sizeof(double) * 4 * (size_t)(w.max_qr_ctas + 1) * B, st));
+  if (w.npanel > 0) PODSDF_TRY(sbr_launch_qr(A, N, 0, w, st, nullptr));
+  bool t_elsewhere = false;             // the T factor of panel k is being built on the QR stream
+  // PODSDF_SBR_TRACE=1 (diagnosis only): events around the phases of every panel, averages printed per quarter
+  static const bool trace = getenv("PODSDF_SBR_TRACE") && atoi(getenv("PODSDF_SBR_TRACE")) != 0;
+  std::vector<cudaEvent_t> tev;
+  auto mark = [&](long k, int slot, cudaStream_t s2) {
+    if (!trace) return;
+    if (tev.empty()) {
+      tev.resize((size_t)w.npanel * 6);
+      for (auto& x : tev) cudaEventCreate(&x);
+    }
+    cudaEventRecord(tev[(size_t)k * 6 + slot], s2);
+  };
   for (long k = 0; k < w.npanel; ++k) {
     const int c0 = (int)(k * B);
     const long r0 = c0 + B, n = N - r0;
@@ -1335,36 +1507,72 @@ static int sbr_stage1(double* A, long N, const SbrWs& w, cudaStream_t st) {
         }
       }
     }
+    mark(k, 0, st);
     sbr_symm_kernel<<<dim3(row_tiles, nsplit), 256, XSMEM, st>>>(A, N, r0, Vk, w.Xp, cps);
     // 1c / 1d: W
     const int wct = (int)((n + WR - 1) / WR);
     sbr_w1_kernel<<<wct, 256, 0, st>>>(w.Xp, nsplit, Vk, N, r0, w.X, w.Zp);
+    if (t_elsewhere) PODSDF_CUDA(cudaStreamWaitEvent(st, ss.t_done, 0));
+    t_elsewhere = false;
     sbr_s_kernel<<<1, B * B, 0, st>>>(Tk, w.Zp, wct, w.S);
     sbr_w2_kernel<<<(int)((n + WR2 - 1) / WR2), 256, 0, st>>>(w.X, Vk, Tk, w.S, N, r0, w.W);
     count_launch(4);
+    mark(k, 1, st);
     // 1e: rank-2b update of the lower tiles.  The first tile column (it contains the next panel) goes first; the
     // next panel's QR -- a latency-bound chain of grid barriers on a few SMs -- then runs on the high-priority
     // stream beside the rest of the update.
     const int side = (int)((N + UT - 1) / UT - r0 / UT);
     const bool ahead = k + 1 < w.npanel;
     if (ahead && side > 1) {
-      sbr_syr2k_kernel<<<side, 256, USMEM, st>>>(A, N, r0, Vk, w.W, 1);
+      sbr_syr2k_kernel<<<(unsigned)syr2k_ctas(N, r0, 1), U_THREADS, USMEM, st>>>(A, N, r0, Vk, w.W, 1);
       PODSDF_CUDA(cudaEventRecord(ss.head, st));
       PODSDF_CUDA(cudaStreamWaitEvent(ss.qr, ss.head, 0));
-      PODSDF_TRY(sbr_launch_qr(A, N, k + 1, w, ss.qr));
-      PODSDF_CUDA(cudaEventRecord(ss.qr_done, ss.qr));
-      sbr_syr2k_kernel<<<side * (side - 1) / 2, 256, USMEM, st>>>(A, N, r0, Vk, w.W, 2);
+      mark(k, 2, st);
+      mark(k, 4, ss.qr);
+      PODSDF_TRY(sbr_launch_qr(A, N, k + 1, w, ss.qr, ss.qr_done));
+      mark(k, 5, ss.qr);
+      PODSDF_CUDA(cudaEventRecord(ss.t_done, ss.qr));
+      t_elsewhere = true;
+      sbr_syr2k_kernel<<<(unsigned)syr2k_ctas(N, r0, 2), U_THREADS, USMEM, st>>>(A, N, r0, Vk, w.W, 2);
+      mark(k, 3, st);
       PODSDF_CUDA(cudaStreamWaitEvent(st, ss.qr_done, 0));
       count_launch(2);
     } else {
-      sbr_syr2k_kernel<<<side * (side + 1) / 2, 256, USMEM, st>>>(A, N, r0, Vk, w.W, 0);
+      sbr_syr2k_kernel<<<(unsigned)syr2k_ctas(N, r0, 0), U_THREADS, USMEM, st>>>(A, N, r0, Vk, w.W, 0);
       count_launch();
-      if (ahead) PODSDF_TRY(sbr_launch_qr(A, N, k + 1, w, st));
+      if (ahead) PODSDF_TRY(sbr_launch_qr(A, N, k + 1, w, st, nullptr));
     }
   }
   sbr_extract_band_kernel<<<ceil_div(N * LDB, 256L), 256, 0, st>>>(A, N, w.Bb);
   count_launch();
   PODSDF_CUDA(cudaGetLastError());
+  if (trace && !tev.empty()) {
+    cudaStreamSynchronize(st);
+    cudaStreamSynchronize(ss.qr);
+    const long np = w.npanel - 2;       // panels with look-ahead and a successor
+    for (int qtr = 0; qtr < 4; ++qtr) {
+      double sum[6] = {0, 0, 0, 0, 0, 0};
+      long cnt = 0;
+      for (long k = qtr * np / 4; k < (qtr + 1) * np / 4; ++k) {
+        auto el = [&](long ka, int a, long kb, int b) {
+          float ms = 0.f;
+          if (cudaEventElapsedTime(&ms, tev[(size_t)ka * 6 + a], tev[(size_t)kb * 6 + b]) != cudaSuccess) { cudaGetLastError(); return 0.0; }
+          return (double)ms * 1e3;
+        };
+        sum[0] += el(k, 0, k, 1);       // symm + W
+        sum[1] += el(k, 1, k, 2);       // head column of the update
+        sum[2] += el(k, 2, k, 3);       // rest of the update
+        sum[3] += el(k, 4, k, 5);       // QR + T factor of panel k + 1 (its stream)
+        sum[4] += el(k, 3, k + 1, 0);   // main stream waiting for the QR
+        sum[5] += el(k, 0, k + 1, 0);   // whole panel
+        ++cnt;
+      }
+      if (cnt > 0)
+        fprintf(stderr, "sbr trace, panels %ld..%ld (us): symm+W %.1f, head %.1f, rest %.1f, QR+T %.1f, wait %.1f, panel %.1f\n",
+                qtr * np / 4, (qtr + 1) * np / 4 - 1, sum[0] / cnt, sum[1] / cnt, sum[2] / cnt, sum[3] / cnt, sum[4] / cnt, sum[5] / cnt);
+    }
+    for (auto& x : tev) cudaEventDestroy(x);
+  }
   return 0;
 }
 
