@@ -23,6 +23,7 @@
 // matrices are k-major: V[m*N + r] is entry (r, m).  tools/proto_sbr.py is the numpy model of every step below.
 #include "sbr_kernels.cuh"
 
+#include <algorithm>
 #include <atomic>
 #include <vector>
 #include <cstdio>
@@ -48,10 +49,39 @@ __device__ __forceinline__ void cpa8(void* smem_dst, const void* gsrc, bool vali
   const int bytes = valid ? 8 : 0;
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(d), "l"(gsrc), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void cpa16(void* smem_dst, const void* gsrc, bool valid) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int bytes = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gsrc), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void cpa_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N_>
 __device__ __forceinline__ void cpa_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N_) : "memory");
+}
+
+// TMA bulk copies (global -> shared, completion on an mbarrier): one instruction moves a whole operand row
+__device__ __forceinline__ void mbar_init(unsigned mbar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(mbar), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned mbar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(mbar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned mbar) {
+  asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(mbar) : "memory");
 }
 
 // ---- grid barrier for the cooperative kernels (all CTAs co-resident: launched with cudaLaunchCooperativeKernel).
@@ -117,10 +147,11 @@ __device__ __forceinline__ bool ll_try(const uint4* p, const unsigned flag, doub
 //   write parity (j & 1) again only after everybody has published step j + 1, i.e. has finished reading step j.
 // Outputs: R (upper triangle) back into A, V rows c0 .. c0+B-1 of Vall (explicit ones / zeros), Gq (B x B + B).
 // ------------------------------------------------------------------------------------------------
-constexpr int QR_ROWS = 256;                 // panel rows per CTA
 constexpr int QR_OCT = 8;                    // columns per thread
-constexpr int QR_THREADS = QR_ROWS * (B / QR_OCT);
-constexpr int QR_WARPS = QR_THREADS / 32;
+// panel rows per CTA: 256 (1024 threads) for tall panels; shorter panels take 128 or 64 rows per CTA -- the steps are a
+// latency chain, so fewer rows per SM shorten it as long as the number of mailboxes to read stays small
+constexpr int QR_ROWS_MAX = 256;
+static inline int qr_rows_for(long n) { return n > 8192 ? 256 : (n > 2048 ? 128 : 64); }
 
 // The step's work on one thread's 8 columns depends on where column j lies relative to the octet: D = j - 8 * octet,
 // clamped to -2 (octet entirely right of j + 1), -1 .. 8, 9 (entirely left of j - 1).  D is warp-uniform, so the
@@ -153,10 +184,14 @@ __device__ __forceinline__ void qr_update(double (&p)[QR_OCT], const bool mine, 
   if (D >= -1 && D <= 6) *next_col = p[D + 1];                    // column j + 1 for everybody's next step
 }
 
-__global__ void __launch_bounds__(QR_THREADS, 1)
+template <int QR_ROWS>
+__global__ void __launch_bounds__(QR_ROWS * (B / QR_OCT), 1)
 sbr_panel_qr_kernel(double* __restrict__ A, const long N, const int c0, double* __restrict__ Vall,
                     double* __restrict__ Gq, uint4* __restrict__ mail, const unsigned epoch,
                     unsigned* __restrict__ bar) {
+  constexpr int QR_THREADS = QR_ROWS * (B / QR_OCT);
+  constexpr int QR_WARPS = QR_THREADS / 32;
+  constexpr int IF = QR_ROWS == 256 ? 2 : 4;   // mailbox reads in flight per thread (registers: 64 per thread at 1024)
   __shared__ double s_red[QR_WARPS][QR_OCT];
   __shared__ double2 s_SR[B];                  // {S_m, R_m}
   __shared__ double s_scal[4];
@@ -238,27 +273,38 @@ sbr_panel_qr_kernel(double* __restrict__ A, const long N, const int c0, double* 
       ll_store(box + (size_t)cta * B + tid, v, flag);
     }
     QCLK(0)
-    // ---- phase B: collect everybody's partial sums; thread (q, m) takes CTAs q, q + QR_WARPS, ... of slot m, two in
+    // ---- phase B: collect everybody's partial sums; thread (q, m) takes CTAs q, q + QR_WARPS, ... of slot m, IF in
     // flight at a time, and adds them in CTA order
     int fail = 0;
     double rj = 0.0;
     {
       double acc = 0.0;
-      for (int g0 = warp; g0 < G; g0 += 2 * QR_WARPS) {
+      for (int g0 = warp; g0 < G; g0 += IF * QR_WARPS) {
+        double val[IF];
+        bool need[IF];
+#pragma unroll
+        for (int u = 0; u < IF; ++u) {
+          val[u] = 0.0;
+          need[u] = g0 + u * QR_WARPS < G;
+        }
         const uint4* e0 = box + (size_t)g0 * B + lane;
-        const uint4* e1 = e0 + (size_t)QR_WARPS * B;
-        double val0 = 0.0, val1 = 0.0;
-        bool need0 = true, need1 = g0 + QR_WARPS < G;
         unsigned spins = 0;
-        while (need0 || need1) {
-          if (need0) need0 = !ll_try(e0, flag, val0);
-          if (need1) need1 = !ll_try(e1, flag, val1);
-          if ((need0 || need1) && ++spins > (1u << 16)) {
+        bool pending = true;
+        while (pending) {
+          pending = false;
+#pragma unroll
+          for (int u = 0; u < IF; ++u)
+            if (need[u]) {
+              need[u] = !ll_try(e0 + (size_t)u * QR_WARPS * B, flag, val[u]);
+              pending |= need[u];
+            }
+          if (pending && ++spins > (1u << 16)) {
             if ((spins & 0xFFFu) == 0 && ld_acquire_u32(err) != 0) { fail = 1; break; }
             if (spins > (1u << 23)) { atomicExch(err, 2u); fail = 1; break; }
           }
         }
-        acc += val0 + val1;
+#pragma unroll
+        for (int u = 0; u < IF; ++u) acc += val[u];
       }
       s_part[tid] = acc;
       if (tid < B && j < B && !fail) {
@@ -383,7 +429,7 @@ sbr_symm_kernel(const double* __restrict__ A, const long N, const long r0, const
                 double* __restrict__ Xp, const int chunks_per_split) {
   extern __shared__ double smem[];
   double* sA = smem;
-  double* sV = smem + XST * XATILE;
+  double* sV = sA + XST * XATILE;
   // tiles are anchored at absolute multiples of 128 (not at r0), so "diagonal tile" means the same elements for
   // every panel; rows / columns below r0 are masked
   const long tile = r0 / XR + blockIdx.x;                    // absolute row-tile index
@@ -397,22 +443,44 @@ sbr_symm_kernel(const double* __restrict__ A, const long N, const long r0, const
   const int nchunks = max(0, c_end - c_begin);
 
   auto tmajor = [&](int chunk) { return ((long)chunk * XKB) / XR <= tile; };   // t-block <= row block
+  // even N: every row starts 16-byte aligned -> two entries per copy (the copies' address arithmetic and predicates
+  // compete with the DMMAs for issue slots: 8-byte copies cost 15 % of the kernel; bulk copies of 128-byte rows were
+  // 2.5x slower than either, profiles/r02_sbr_profile.md)
+  const bool vec = (N & 1) == 0;
   auto load_stage = [&](int chunk, int stage) {
     const long t0 = (long)chunk * XKB;
     double* a = sA + stage * XATILE;
     double* vv = sV + stage * XVTILE;
-    if (tmajor(chunk)) {                                      // A[t*N + row]: rows contiguous
+    if (vec) {
+      if (tmajor(chunk)) {                                      // A[t*N + row]: rows contiguous
+        for (int e = tid; e < XKB * XR / 2; e += 256) {
+          const int t = e / (XR / 2), r = 2 * (e % (XR / 2));
+          cpa16(a + t * XPA1 + r, A + (t0 + t) * N + row0 + r, (row0 + r >= r0) && (row0 + r < N) && (t0 + t < N));
+        }
+      } else {                                                  // A[row*N + t]: t contiguous
+        for (int e = tid; e < XR * XKB / 2; e += 256) {
+          const int r = e / (XKB / 2), t = 2 * (e % (XKB / 2));
+          cpa16(a + r * XPA0 + t, A + (row0 + r) * N + t0 + t, (row0 + r >= r0) && (row0 + r < N) && (t0 + t < N));
+        }
+      }
+      {                                                         // V[m][t] -> sV[m][t]: B * XKB / 2 = 256 copies
+        const int m = tid / (XKB / 2), t = 2 * (tid % (XKB / 2));
+        cpa16(vv + m * XPV + t, V + (long)m * N + t0 + t, t0 + t < N);
+      }
+      return;
+    }
+    if (tmajor(chunk)) {                                        // A[t*N + row]: rows contiguous
       for (int e = tid; e < XKB * XR; e += 256) {
         const int t = e / XR, r = e % XR;
         cpa8(a + t * XPA1 + r, A + (t0 + t) * N + row0 + r, (row0 + r >= r0) && (row0 + r < N) && (t0 + t < N));
       }
-    } else {                                                  // A[row*N + t]: t contiguous
+    } else {                                                    // A[row*N + t]: t contiguous
       for (int e = tid; e < XR * XKB; e += 256) {
         const int r = e / XKB, t = e % XKB;
         cpa8(a + r * XPA0 + t, A + (row0 + r) * N + t0 + t, (row0 + r >= r0) && (row0 + r < N) && (t0 + t < N));
       }
     }
-    for (int e = tid; e < B * XKB; e += 256) {                // V[m][t] -> sV[m][t]
+    for (int e = tid; e < B * XKB; e += 256) {                  // V[m][t] -> sV[m][t]
       const int m = e / XKB, t = e % XKB;
       cpa8(vv + m * XPV + t, V + (long)m * N + t0 + t, t0 + t < N);
     }
@@ -569,13 +637,7 @@ sbr_w2_kernel(const double* __restrict__ X, const double* __restrict__ V, const 
 // ------------------------------------------------------------------------------------------------
 constexpr int UT = 128, UTJ = 64, UPA = UT + 4, UPB = UTJ + 4;
 constexpr int U_THREADS = 128;
-constexpr size_t USMEM = (size_t)2 * B * (UPA + UPB) * sizeof(double);
-
-__device__ __forceinline__ void cpa16(void* smem_dst, const void* gsrc, bool valid) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  const int bytes = valid ? 16 : 0;
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gsrc), "r"(bytes) : "memory");
-}
+constexpr size_t USMEM = (size_t)(2 + 2 * B * (UPA + UPB)) * sizeof(double);    // mbarrier + operands
 
 // number of CTAs of one update: part 0 = every tile, 1 = the first column block only (it holds the next panel),
 // 2 = the other column blocks -- parts 1 + 2 let the next panel's QR overlap most of the update
@@ -587,33 +649,60 @@ static inline long syr2k_ctas(long N, long r0, int part) {
   return side * (side + 1) - h * side;
 }
 
+// At K = 64 a tile's loads and stores are as long as its DMMAs, and with four warps per CTA they were bound by the
+// ISSUE of their address arithmetic and predicates (prologue = 49 % of the warp samples, profiles/r02_sbr_profile.md):
+//   * even N: the 2 x 64 operand rows arrive by 128 bulk copies issued by one warp.  They are not masked: entries
+//     outside [r0, N) are other rows' or stale values, which only reach accumulator rows / columns that are not stored
+//     (reads stay inside the workspace: the skinny matrices are followed by other buffers);
+//   * tiles entirely inside [r0, N) take a path without predicates, addresses = 8 column pointers + immediates.
+// -DPODSDF_SYR2K_RED=1 (A/B): accumulators start at zero and the epilogue adds them at the L2 -- measured equal
+// (101.5 vs 102.4 ms for stage 1), so the plain read / store form stays
+#ifndef PODSDF_SYR2K_RED
+#define PODSDF_SYR2K_RED 0
+#endif
+#if PODSDF_SYR2K_RED
+#define U_OUT(ptr, val) atomicAdd((ptr), (val))     // result unused -> RED.ADD.F64 at the L2: no read of the old tile
+#else
+#define U_OUT(ptr, val) (*(ptr) = (val))
+#endif
 __global__ void __launch_bounds__(U_THREADS, 2)
 sbr_syr2k_kernel(double* __restrict__ A, const long N, const long r0, const double* __restrict__ V,
                  const double* __restrict__ W, const int part) {
   extern __shared__ double smem[];
-  double* sA = smem;                    // [2B][UPA]
-  double* sB = smem + 2 * B * UPA;      // [2B][UPB]
+  double* sA = smem + 2;                // [2B][UPA]  (smem[0]: the mbarrier)
+  double* sB = sA + 2 * B * UPA;        // [2B][UPB]
+  const unsigned mbar = (unsigned)__cvta_generic_to_shared(smem);
   const long tile0 = r0 / UT;
   const int h = (int)((r0 % UT) / UTJ);
-  int r = 0, rem = blockIdx.x;          // linear id -> (row r, column block rem)
-  for (int cnt = (part == 2 ? 1 : 2) - h; rem >= cnt; cnt += 2) { rem -= cnt; ++r; }
-  if (part == 1) { r = blockIdx.x; rem = 0; }
-  if (part == 2) ++rem;
+  int r, rem;                           // linear id -> (row r, column block rem); row q holds 2 q + c blocks
+  if (part == 1) {
+    r = blockIdx.x;
+    rem = 0;
+  } else {
+    const int c1 = (part == 2 ? 0 : 1) - h, id = blockIdx.x;     // blocks before row q: q^2 + c1 q
+    r = (int)((sqrtf((float)(c1 * c1 + 4 * id)) - (float)c1) * 0.5f);
+    while (r > 0 && r * r + c1 * r > id) --r;
+    while ((r + 1) * (r + 1) + c1 * (r + 1) <= id) ++r;
+    rem = id - (r * r + c1 * r) + (part == 2 ? 1 : 0);
+  }
   const long i0 = (tile0 + r) * UT, j0 = (2 * tile0 + h + rem) * UTJ;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = (warp >> 1) * 64, wn = (warp & 1) * 32;
   const int lr = lane & 3, lc = lane >> 2;
+  const bool bulk = (N & 1) == 0;       // operand rows start 16-byte aligned
 
-  if ((N & 1) == 0) {                   // rows of V / W start 16-byte aligned: two entries per copy
-    for (int e = tid; e < 2 * B * (UT / 2); e += U_THREADS) {
-      const int k = e / (UT / 2), x = 2 * (e % (UT / 2));
-      const double* pa = (k < B) ? V + (long)k * N : W + (long)(k - B) * N;
-      cpa16(sA + k * UPA + x, pa + i0 + x, (i0 + x >= r0) && (i0 + x < N));
-    }
-    for (int e = tid; e < 2 * B * (UTJ / 2); e += U_THREADS) {
-      const int k = e / (UTJ / 2), x = 2 * (e % (UTJ / 2));
-      const double* pb = (k < B) ? W + (long)k * N : V + (long)(k - B) * N;
-      cpa16(sB + k * UPB + x, pb + j0 + x, (j0 + x >= r0) && (j0 + x < N));
+  if (bulk) {
+    if (tid == 0) mbar_init(mbar, 1);
+    __syncthreads();
+    if (warp == 0) {
+      if (lane == 0) mbar_expect_tx(mbar, 2 * B * (UT + UTJ) * (unsigned)sizeof(double));
+      __syncwarp();
+      for (int k = lane; k < 2 * B; k += 32) {
+        const double* pa = (k < B) ? V + (long)k * N : W + (long)(k - B) * N;
+        const double* pb = (k < B) ? W + (long)k * N : V + (long)(k - B) * N;
+        bulk_g2s((unsigned)__cvta_generic_to_shared(sA + k * UPA), pa + i0, UT * sizeof(double), mbar);
+        bulk_g2s((unsigned)__cvta_generic_to_shared(sB + k * UPB), pb + j0, UTJ * sizeof(double), mbar);
+      }
     }
   } else {
     for (int e = tid; e < 2 * B * UT; e += U_THREADS) {
@@ -626,21 +715,45 @@ sbr_syr2k_kernel(double* __restrict__ A, const long N, const long r0, const doub
       const double* pb = (k < B) ? W + (long)k * N : V + (long)(k - B) * N;
       cpa8(sB + k * UPB + x, pb + j0 + x, (j0 + x >= r0) && (j0 + x < N));
     }
+    cpa_commit();
   }
-  cpa_commit();
 
+  const bool full = i0 >= r0 && i0 + UT <= N && j0 >= r0 && j0 + UTJ <= N;
+  double* const c00 = A + (j0 + wn + 2 * lr) * N + i0 + wm + lc;     // element (mt, nt, e) at c00[(nt * 8 + e) * N + mt * 8]
   double acc[8][4][2];
+#if PODSDF_SYR2K_RED
 #pragma unroll
   for (int mt = 0; mt < 8; ++mt)
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
-      const long i = i0 + wm + mt * 8 + lc, j = j0 + wn + nt * 8 + 2 * lr;
-      const bool iok = i >= r0 && i < N;
-      acc[mt][nt][0] = (iok && j >= r0 && j < N) ? A[j * N + i] : 0.0;
-      acc[mt][nt][1] = (iok && j + 1 >= r0 && j + 1 < N) ? A[(j + 1) * N + i] : 0.0;
-    }
-  cpa_wait<0>();
-  __syncthreads();
+    for (int nt = 0; nt < 4; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+#else
+  if (full) {
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const double* col = c00 + (long)(nt * 8 + e) * N;
+#pragma unroll
+        for (int mt = 0; mt < 8; ++mt) acc[mt][nt][e] = col[mt * 8];
+      }
+  } else {
+#pragma unroll
+    for (int mt = 0; mt < 8; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const long i = i0 + wm + mt * 8 + lc, j = j0 + wn + nt * 8 + 2 * lr;
+        const bool iok = i >= r0 && i < N;
+        acc[mt][nt][0] = (iok && j >= r0 && j < N) ? A[j * N + i] : 0.0;
+        acc[mt][nt][1] = (iok && j + 1 >= r0 && j + 1 < N) ? A[(j + 1) * N + i] : 0.0;
+      }
+  }
+#endif
+  if (bulk) {
+    mbar_wait(mbar, 0);
+  } else {
+    cpa_wait<0>();
+    __syncthreads();
+  }
 #pragma unroll 4
   for (int k4 = 0; k4 < 2 * B; k4 += 4) {
     double af[8], bf[4];
@@ -654,15 +767,26 @@ sbr_syr2k_kernel(double* __restrict__ A, const long N, const long r0, const doub
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) dmma884s(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
   }
+  if (full) {
 #pragma unroll
-  for (int mt = 0; mt < 8; ++mt)
+    for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
-      const long i = i0 + wm + mt * 8 + lc, j = j0 + wn + nt * 8 + 2 * lr;
-      const bool iok = i >= r0 && i < N;
-      if (iok && j >= r0 && j < N) A[j * N + i] = acc[mt][nt][0];
-      if (iok && j + 1 >= r0 && j + 1 < N) A[(j + 1) * N + i] = acc[mt][nt][1];
-    }
+      for (int e = 0; e < 2; ++e) {
+        double* col = c00 + (long)(nt * 8 + e) * N;
+#pragma unroll
+        for (int mt = 0; mt < 8; ++mt) U_OUT(col + mt * 8, acc[mt][nt][e]);
+      }
+  } else {
+#pragma unroll
+    for (int mt = 0; mt < 8; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const long i = i0 + wm + mt * 8 + lc, j = j0 + wn + nt * 8 + 2 * lr;
+        const bool iok = i >= r0 && i < N;
+        if (iok && j >= r0 && j < N) U_OUT(A + j * N + i, acc[mt][nt][0]);
+        if (iok && j + 1 >= r0 && j + 1 < N) U_OUT(A + (j + 1) * N + i, acc[mt][nt][1]);
+      }
+  }
 }
 
 // Stage 1f: lower band storage Bb[c][d] = A[c][c + d] (d <= B), zero where the bulge will live (B < d < LDB)
@@ -1382,7 +1506,7 @@ static SbrWs sbr_layout(double* ws, long N, size_t* total) {
   w.npanel = sbr_npanel(N);
   w.ntask_max = (N + B - 1) / B + 1;
   w.max_split = 16;
-  w.max_qr_ctas = (int)((N + QR_ROWS - 1) / QR_ROWS);
+  w.max_qr_ctas = std::max((int)((N + QR_ROWS_MAX - 1) / QR_ROWS_MAX), 64);
   size_t off = 0;
   auto take = [&](size_t cnt) {
     double* q = ws + off;
@@ -1436,7 +1560,8 @@ static int sbr_launch_qr(double* A, long N, long k, const SbrWs& w, cudaStream_t
   static std::atomic<unsigned> epochs{0};
   const int c0 = (int)(k * B);
   const long n = N - c0 - B;
-  const int G = (int)((n + QR_ROWS - 1) / QR_ROWS);
+  const int rows = qr_rows_for(n);
+  const int G = (int)((n + rows - 1) / rows);
   double* Aarg = A;
   long Narg = N;
   int c0arg = c0;
@@ -1446,7 +1571,9 @@ static int sbr_launch_qr(double* A, long N, long k, const SbrWs& w, cudaStream_t
   if (earg == 0) earg = (epochs.fetch_add(1u) + 1u) & 0x03FFFFFFu;
   unsigned* barg = w.bar;
   void* args[] = {&Aarg, &Narg, &c0arg, &Varg, &garg, &marg, &earg, &barg};
-  PODSDF_CUDA(cudaLaunchCooperativeKernel((const void*)sbr_panel_qr_kernel, dim3(G), dim3(QR_THREADS), args, 0, st));
+  const void* fn = rows == 256 ? (const void*)sbr_panel_qr_kernel<256>
+                               : (rows == 128 ? (const void*)sbr_panel_qr_kernel<128> : (const void*)sbr_panel_qr_kernel<64>);
+  PODSDF_CUDA(cudaLaunchCooperativeKernel(fn, dim3(G), dim3(rows * (B / QR_OCT)), args, 0, st));
   if (after_qr) PODSDF_CUDA(cudaEventRecord(after_qr, st));
   sbr_tfactor_kernel<<<1, B, 0, st>>>(w.Gq, w.Tall + k * B * B);      // off the critical path: T is first used by 1d
   count_launch(2);
