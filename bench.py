@@ -485,7 +485,7 @@ def main():
     ap.add_argument("--pod-rows", type=int, default=CFG4["rows_per_gpu"])
     ap.add_argument("--pod-snapshots", type=int, default=CFG4["snapshots"])
     ap.add_argument("--pod-modes", type=int, default=CFG4["modes"])
-    ap.add_argument("--pod-steps", type=int, default=1)
+    ap.add_argument("--pod-steps", type=int, default=2)
     ap.add_argument("--no-pod", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
@@ -763,12 +763,18 @@ def run_pod(args, pkg, torch, dist, dev, local_rank, rank, world, barrier, max_o
     steps = max(1, args.pod_steps)
     e0.record()
     gram_ms = 0.0
-    for _ in range(steps):
+    step_ms = []                                   # per-step device time (the host parts -- ranking of the Fourier
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]   # coefficients -- can hiccup)
+    marks[0].record()
+    for i in range(steps):
         res = pkg.pipeline.pod_resident(A, M, N, 0, nm, CFG4["dt"], CFG4["et"], local_rank, group, timers)
         g_ms = np.zeros(1)
         capi.check(capi.lib().podsdf_gram_last_ms(capi.ptr(g_ms)))
         gram_ms += float(g_ms[0])
+        marks[i + 1].record()
     e1.record()
+    torch.cuda.synchronize(dev)
+    step_ms = [marks[i].elapsed_time(marks[i + 1]) for i in range(steps)]
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1)) / steps
     gram_ms /= steps
@@ -778,6 +784,7 @@ def run_pod(args, pkg, torch, dist, dev, local_rank, rank, world, barrier, max_o
     orth = float((phi.T @ phi - torch.eye(res["nm"], dtype=torch.float64, device=dev)).abs().max()) if world == 1 else None
     return {
         "metric": "pod_snapshots_per_s", "value": N / (ms * 1e-3), "unit": "snapshots/s", "ms_per_step": ms, "steps": steps,
+        "ms_each_step": step_ms,
         "config": {"workload": "cfg4 row shard: %d rows x %d snapshots per GPU (x%d GPUs), %d modes, et=0.9" % (M, N, world, nm)},
         "parts_ms": {k: v / steps for k, v in timers.items()},
         "roofline": {"kernel": "gram_dmma_kernel (FP64 mma.sync m8n8k4, upper-triangular tiles)", "bound": "tensor",

@@ -268,7 +268,10 @@ size_t gram_workspace_bytes(long M, long N) {
 // Projection: Phi[row][m] = scale * dinv[m] * sum_t A[row][t] T[t][m]     (PODFS.py:1329-1333)
 //   CTA = 128 rows x 64 or 128 modes (mode blocks are neighbours in the grid); 8 warps, warp tile 16 rows x all modes.
 // ------------------------------------------------------------------------------------------------
-constexpr int PR = 128, PKB = 16, PST = 3;
+#ifndef PODSDF_PKB
+#define PODSDF_PKB 32
+#endif
+constexpr int PR = 128, PKB = PODSDF_PKB, PST = 3;   // K chunk of 32: half as many CTA barriers as 16 (same trade as the Gram kernel's)
 constexpr int PPA0 = PKB + 4;  // layout 0: A tile [128 rows][PKB + 4]
 constexpr int PPA1 = PR + 4;   // layout 1: A tile [PKB t][128 + 4]
 
@@ -286,7 +289,7 @@ template <int LAYOUT, int PM>
 __global__ void __launch_bounds__(256, 1)
 project_dmma_kernel(const double* __restrict__ A, const long M, const long N, const double* __restrict__ T,
                     const long ldT, const double* __restrict__ dinv, const int nm, const double scale,
-                    double* __restrict__ Phi) {
+                    double* __restrict__ Phi, const int vec) {
   extern __shared__ double smem[];
   constexpr int ATILE = ProjSmem<LAYOUT, PM>::ATILE, TTILE = ProjSmem<LAYOUT, PM>::TTILE, PPT = ProjSmem<LAYOUT, PM>::PPT;
   constexpr int NTL = PM / 8;
@@ -306,6 +309,24 @@ project_dmma_kernel(const double* __restrict__ A, const long M, const long N, co
     const long t0 = (long)chunk * PKB;
     double* a = sA + stage * ATILE;
     double* tt = sT + stage * TTILE;
+    if (vec) {          // every row of A and T starts 16-byte aligned and has an even length: two entries per copy
+      if (LAYOUT == 0) {
+        for (int e = tid; e < PR * PKB / 2; e += 256) {
+          const int r = e / (PKB / 2), t = 2 * (e % (PKB / 2));
+          cp_async_16(a + r * PPA0 + t, A + (row0 + r) * N + t0 + t, (row0 + r < M) && (t0 + t < N));
+        }
+      } else {
+        for (int e = tid; e < PKB * PR / 2; e += 256) {
+          const int t = e / (PR / 2), r = 2 * (e % (PR / 2));
+          cp_async_16(a + t * PPA1 + r, A + (t0 + t) * M + row0 + r, (row0 + r < M) && (t0 + t < N));
+        }
+      }
+      for (int e = tid; e < PKB * PM / 2; e += 256) {
+        const int t = e / (PM / 2), m = 2 * (e % (PM / 2));
+        cp_async_16(tt + t * PPT + m, T + (t0 + t) * ldT + m0 + m, (t0 + t < N) && (m0 + m < nm));
+      }
+      return;
+    }
     if (LAYOUT == 0) {
       for (int e = tid; e < PR * PKB; e += 256) {
         const int r = e / PKB, t = e % PKB;
@@ -378,7 +399,10 @@ static int launch_project_t(const double* A, long M, long N, const double* T, lo
   if (nblocks > 2147483647L) return fail(PODSDF_ERR_UNSUPPORTED, "too many tiles for one projection launch");
   auto k = project_dmma_kernel<LAYOUT, PM>;
   PODSDF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ProjSmem<LAYOUT, PM>::BYTES));
-  k<<<dim3((unsigned)nblocks), 256, ProjSmem<LAYOUT, PM>::BYTES, st>>>(A, M, N, T, ldT, dinv, nm, scale, Phi);
+  // 16-byte copies: aligned bases, even row lengths (layout 0: rows of length N; layout 1: rows of length M), even nm
+  const bool aligned = (((uintptr_t)A | (uintptr_t)T) & 15) == 0;
+  const int vec = aligned && ((LAYOUT == 0 ? N : M) % 2 == 0) && (ldT % 2 == 0) && (nm % 2 == 0) ? 1 : 0;
+  k<<<dim3((unsigned)nblocks), 256, ProjSmem<LAYOUT, PM>::BYTES, st>>>(A, M, N, T, ldT, dinv, nm, scale, Phi, vec);
   count_launch();
   PODSDF_CUDA(cudaGetLastError());
   return 0;

@@ -128,7 +128,21 @@ def test_config4_shard_podfs_identities(P):
     assert float((V @ V.T - torch.eye(N, dtype=torch.float64, device=dev)).abs().max()) < 1e-11
     assert abs(float(lam.sum()) - float(torch.trace(C0))) < 1e-12 * float(torch.trace(C0))
     assert bool((lam[1:] >= lam[:-1]).all())                                            # ascending, as documented
-    del C0
+    # the route PODFS takes at this size (all eigenvalues + nm leading vectors, no library call: two-stage
+    # tridiagonalisation with the 256-row panel QR, bulge chasing, multisection, inverse iteration, back-transformation)
+    import ctypes
+    C1 = C0.clone()
+    lam1 = torch.empty(N, dtype=torch.float64, device=dev)
+    route = ctypes.c_int(-1)
+    capi.check(L.podsdf_eig_sym_top_dev(0, C1.data_ptr(), N, nm, lam1.data_ptr(), ctypes.byref(route), st))
+    torch.cuda.synchronize()
+    assert route.value == 1
+    assert float((lam1 - lam).abs().max()) < 1e-12 * lam0
+    Vt = C1[:nm]                                                                        # rows = leading vectors, descending
+    lt = torch.flip(lam1, dims=[0])[:nm]
+    assert float((Vt @ C0 - lt[:, None] * Vt).abs().max()) < 1e-12 * lam0
+    assert float((Vt @ Vt.T - torch.eye(nm, dtype=torch.float64, device=dev)).abs().max()) < 1e-12
+    del C0, C1
     # projection: orthonormal spatial modes and the captured-energy identity |A - Phi T'|_F^2 / N = sum of the rest
     lam_h = lam.cpu().numpy()
     energy, nm_kept, T = P.pipeline.select_modes(lam_h, lambda j: V[j].cpu().numpy(), N, nm)

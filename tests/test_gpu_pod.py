@@ -364,12 +364,13 @@ def test_field_statistics_kernels_and_reconstruction_check(P):
 
 
 @pytest.mark.parametrize("N,kind", [(3, "indef"), (5, "gram"), (33, "indef"), (34, "gram"), (64, "indef"), (65, "gram"),
-                                    (100, "indef"), (300, "gram"), (515, "indef"), (1029, "gram")])
+                                    (100, "indef"), (300, "gram"), (515, "indef"), (1029, "gram"), (2500, "gram")])
 def test_two_stage_tridiagonalisation(P, N, kind):
     """The library-free reduction behind podsdf_eig_sym_top_* (csrc/sbr_kernels.cu): the band matrix after stage 1 and
     the tridiagonal matrix after stage 2 are orthogonally similar to C -- their spectra equal LAPACK's spectrum of C to
     rounding -- for a Gram-like (decaying spectrum + noise floor) and an indefinite symmetric matrix, sizes that are not
-    multiples of the panel width or of the tile size."""
+    multiples of the panel width or of the tile size (N = 2500 takes the 128-row panel QR for its first panels, the others
+    the 64-row one; the 256-row one runs in test_gpu_fullsize at N = 10^4)."""
     from scipy.linalg import eigvalsh_tridiagonal
     rs = np.random.RandomState(N)
     if kind == "gram":
