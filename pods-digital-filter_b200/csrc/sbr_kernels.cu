@@ -537,7 +537,6 @@ sbr_symm_kernel(const double* __restrict__ A, const long N, const long r0, const
 // Stage 1c: X = sum of the split partials; Zp[cta] = V_chunk^T X_chunk (B x B partial of V^T X)
 // ------------------------------------------------------------------------------------------------
 constexpr int WR = 64;    // rows per CTA of sbr_w1_kernel
-constexpr int W1_MAXSPLIT = 16;   // = SbrWs::max_split
 constexpr int WR2 = 32;   // rows per CTA of sbr_w2_kernel
 
 __global__ void __launch_bounds__(256)
@@ -547,22 +546,12 @@ sbr_w1_kernel(const double* __restrict__ Xp, const int nsplit, const double* __r
   const long n = N - r0;
   const long row0 = (long)blockIdx.x * WR;
   const int tid = threadIdx.x;
-  // the split partials of one entry are fetched together (up to W1_MAXSPLIT loads in flight instead of a chain of
-  // nsplit dependent round trips) and added in a fixed tree
-#pragma unroll
-  for (int q = 0; q < B * WR / 256; ++q) {
-    const int e = tid + 256 * q;
+  for (int e = tid; e < B * WR; e += 256) {
     const int m = e / WR, r = e % WR;
     const bool ok = row0 + r < n;
-    const double* src = Xp + (long)m * N + r0 + row0 + r;
-    double v[W1_MAXSPLIT];
-#pragma unroll
-    for (int s = 0; s < W1_MAXSPLIT; ++s) v[s] = (ok && s < nsplit) ? __ldcg(src + (long)s * B * N) : 0.0;
-#pragma unroll
-    for (int w = W1_MAXSPLIT / 2; w >= 1; w >>= 1)
-#pragma unroll
-      for (int s = 0; s < w; ++s) v[s] += v[s + w];
-    const double x = v[0];
+    double x = 0.0;
+    if (ok)
+      for (int s = 0; s < nsplit; ++s) x += Xp[((long)s * B + m) * N + r0 + row0 + r];
     sX[m][r] = x;
     sV[m][r] = ok ? V[(long)m * N + r0 + row0 + r] : 0.0;
     if (ok) X[(long)m * N + r0 + row0 + r] = x;
@@ -582,31 +571,16 @@ __global__ void __launch_bounds__(B * B)
 sbr_s_kernel(const double* __restrict__ T, const double* __restrict__ Zp, const int nz, double* __restrict__ S) {
   __shared__ double sT[B][B + 1], sZ[B][B + 1], sU[B][B + 1];
   const int e = threadIdx.x, a = e / B, c = e % B;
-  // the partials sit in L2 and the kernel is on every panel's critical path: 16 loads in flight per thread (four were
-  // 39 dependent round trips at nz = 156: 16 us per panel), summed in a fixed order
-  double z[16];
-#pragma unroll
-  for (int u = 0; u < 16; ++u) z[u] = 0.0;
+  double z0 = 0.0, z1 = 0.0, z2 = 0.0, z3 = 0.0;       // four independent streams of loads, fixed order
   int g2 = 0;
-  for (; g2 + 15 < nz; g2 += 16) {
-    double v[16];
-#pragma unroll
-    for (int u = 0; u < 16; ++u) v[u] = __ldcg(Zp + (long)(g2 + u) * B * B + e);
-#pragma unroll
-    for (int u = 0; u < 16; ++u) z[u] += v[u];
+  for (; g2 + 3 < nz; g2 += 4) {
+    z0 += Zp[(long)g2 * B * B + e];
+    z1 += Zp[(long)(g2 + 1) * B * B + e];
+    z2 += Zp[(long)(g2 + 2) * B * B + e];
+    z3 += Zp[(long)(g2 + 3) * B * B + e];
   }
-  {
-    double v[16];
-#pragma unroll
-    for (int u = 0; u < 16; ++u) v[u] = (g2 + u < nz) ? __ldcg(Zp + (long)(g2 + u) * B * B + e) : 0.0;
-#pragma unroll
-    for (int u = 0; u < 16; ++u) z[u] += v[u];
-  }
-#pragma unroll
-  for (int w = 8; w >= 1; w >>= 1)
-#pragma unroll
-    for (int u = 0; u < w; ++u) z[u] += z[u + w];
-  sZ[a][c] = z[0];
+  for (; g2 < nz; ++g2) z0 += Zp[(long)g2 * B * B + e];
+  sZ[a][c] = (z0 + z1) + (z2 + z3);
   sT[a][c] = T[e];
   __syncthreads();
   double acc = 0.0;                                    // U = Z T (T upper triangular)
@@ -1531,7 +1505,7 @@ static SbrWs sbr_layout(double* ws, long N, size_t* total) {
   SbrWs w;
   w.npanel = sbr_npanel(N);
   w.ntask_max = (N + B - 1) / B + 1;
-  w.max_split = W1_MAXSPLIT;
+  w.max_split = 16;
   w.max_qr_ctas = std::max((int)((N + QR_ROWS_MAX - 1) / QR_ROWS_MAX), 64);
   size_t off = 0;
   auto take = [&](size_t cnt) {
