@@ -399,6 +399,7 @@ int podsdf_sym_tridiag_host(int device, const double* C_host, long N, double* d_
   if (!C_host || !d_host || !e_host || N < 3) return fail(PODSDF_ERR_INVALID, "bad argument");
   PODSDF_TRY(check_device(device));
   DeviceGuard guard(device);
+  std::lock_guard<std::recursive_mutex> lk(g_solver_mu);     // the look-ahead stream and its events are per device
   DevBuf C, ws, de, band;
   const size_t nn = sizeof(double) * (size_t)N * N;
   PODSDF_CUDA(C.alloc(nn));
