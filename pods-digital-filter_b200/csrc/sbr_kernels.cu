@@ -1276,6 +1276,211 @@ sbr_chase4_kernel(double* __restrict__ Bb, const long N, double* __restrict__ V2
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Stage 2, four warps per task, the critical hand-off through a mailbox.  Of the 32 band columns of task (i, k), 31
+// were written by task (i-1, k) -- a whole task time before they are needed -- and ONE, the last, by task (i-1, k+1),
+// whose completion is what task (i, k) waits for: it is that task's column 0, final as soon as its D block is updated
+// and the new reflector is known (H2 leaves (beta, 0, ..., 0) below).  So a task posts its column 0 in flagged 16-byte
+// entries {lo, flag, hi, flag} (flag = sweep + 1) as soon as it is final, mid-task, and never writes it to the band;
+// the next sweep polls those 64 entries: data and "it is there" in one L2 round trip, instead of "finish the task,
+// store, release, poll, load".  Slots are per (sweep parity, task): sweep i+2 reaches task k only after sweep i+1 has
+// finished task k+1, i.e. long after it read slot (i, k).  The 31 other columns and the progress counters go through
+// the band as before (waited for with k+1 instead of k+2: never the critical edge).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+sbr_chase5_kernel(double* __restrict__ Bb, const long N, double* __restrict__ V2, double* __restrict__ TAU2,
+                  const long ntask_max, unsigned* __restrict__ bar, uint4* __restrict__ mail) {
+  __shared__ __align__(16) double sB[B][LDB];
+  __shared__ double sv[B], sv2[B], sz[B], sqD[2][B], sY[2][B], sP[2][B];
+  __shared__ double s_tau, s_tau2, s_beta2;
+  __shared__ int s_ok;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int half = warp & 1;                         // which 16 columns of its block this warp owns
+  const int cb = half * (B / 2);
+  unsigned* err = bar + 1;
+  unsigned* prog = bar + 2;
+  const long nsweep = N - 2;
+  for (long i = blockIdx.x; i < nsweep; i += gridDim.x) {
+    const int nt = (int)((N - 1 - i + B - 1) / B);
+    const unsigned myflag = (unsigned)(i + 1), inflag = (unsigned)i;       // mailbox flags: sweep index + 1
+    uint4* outbox = mail + (size_t)(i & 1) * ntask_max * LDB;              // slot of task k: outbox + k * LDB
+    const uint4* inbox = mail + (size_t)((i + 1) & 1) * ntask_max * LDB;   // the previous sweep's
+    double v = 0.0, tau = 0.0;                       // warp 0: reflector of the current task (lane = row inside J_k)
+    for (int k = 0; k < nt; ++k) {
+      if (threadIdx.x == 0) {                        // columns 0 .. 30 come from task k of sweep i-1, through the band
+        int ok = 1;
+        if (i > 0) {
+          const unsigned need = (unsigned)(k + 1);
+          unsigned spins = 0;
+          while (ld_acquire_u32(prog + i - 1) < need) {
+            if (++spins > (1u << 22)) {
+              if ((spins & 0xFFFFu) == 0 && ld_acquire_u32(err) != 0) { ok = 0; break; }
+              if (spins > (1u << 27)) { atomicExch(err, 2u); ok = 0; break; }
+            }
+          }
+        }
+        s_ok = ok;
+      }
+      __syncthreads();
+      if (!s_ok) return;
+      const long j0 = i + 1 + (long)k * B;
+      const int L = (int)min((long)B, N - j0);
+      const int L2 = (int)max(0L, min((long)B, N - j0 - B));
+      const bool boxed = i > 0 && L == B;            // column 31 arrives in the mailbox of task (i-1, k+1)
+      const bool keep0 = k == 0;                     // column 0 of task 0 has no mailbox reader: it goes to the band
+#pragma unroll
+      for (int cc = 0; cc < B / 4; ++cc) {           // band columns j0 .. j0+L-1 (zero-filled beyond), a quarter per warp
+        const int c = warp * (B / 4) + cc;
+        if (c < B - 1 || !boxed) cpa16_cg(&sB[c][2 * lane], Bb + (j0 + c) * LDB + 2 * lane, c < L);
+      }
+      cpa_commit();
+      int fail = 0;
+      if (warp == 3 && boxed) {                      // (warp 3 has nothing else to do here) value and flag in one load
+        const uint4* e0 = inbox + (size_t)(k + 1) * LDB + lane;
+        double x0 = 0.0, x1 = 0.0;
+        bool need0 = true, need1 = true;
+        unsigned spins = 0;
+        while (need0 || need1) {
+          if (need0) need0 = !ll_try(e0, inflag, x0);
+          if (need1) need1 = !ll_try(e0 + 32, inflag, x1);
+          if ((need0 || need1) && ++spins > (1u << 18)) {
+            if ((spins & 0xFFFu) == 0 && ld_acquire_u32(err) != 0) { fail = 1; break; }
+            if (spins > (1u << 25)) { atomicExch(err, 3u); fail = 1; break; }
+          }
+        }
+        sB[B - 1][lane] = x0;
+        sB[B - 1][lane + 32] = x1;
+      }
+      if (warp == 0) {
+        if (k == 0) {                                // reflector of column i (overlaps the copies)
+          const double x = (lane < L) ? __ldcg(Bb + i * LDB + 1 + lane) : 0.0;
+          double beta;
+          warp_house(x, lane, v, tau, beta);
+          if (lane < L) __stcg(Bb + i * LDB + 1 + lane, lane == 0 ? beta : 0.0);
+        }
+        if (lane >= L) v = 0.0;
+        if (lane < L) V2[i * N + j0 + lane] = v;
+        if (lane == 0) {
+          TAU2[i * ntask_max + k] = tau;
+          s_tau = tau;
+        }
+        sv[lane] = v;
+      }
+      cpa_wait<0>();
+      if (__syncthreads_or(fail)) return;
+      const double tk = s_tau, vl = sv[lane];
+      if (warp >= 2) {
+        // ---- D <- H D H: p = tau D v (each warp sums its 16 columns), q = p - (tau/2)(p^T v) v, D -= v q^T + q v^T
+        double pp[2] = {0.0, 0.0};
+#pragma unroll
+        for (int cc = 0; cc < B / 2; ++cc) {
+          const int c = cb + cc;
+          const int idx = (c <= lane) ? c * LDB + lane - c : lane * LDB + c - lane;
+          pp[cc & 1] = fma((&sB[0][0])[idx], sv[c], pp[cc & 1]);
+        }
+        sP[half][lane] = pp[0] + pp[1];
+        pair_barrier(2);                             // both halves summed; nobody reads D any more
+        const double pl = tk * (sP[0][lane] + sP[1][lane]);
+        const double kk = 0.5 * tk * warp_sum(pl * vl);
+        const double ql = fma(-kk, vl, pl);
+        sqD[half][lane] = ql;                        // each warp keeps its own copy: no second barrier
+        __syncwarp();
+#pragma unroll
+        for (int cc = 0; cc < B / 2; ++cc) {
+          const int c = cb + cc;
+          if (c <= lane) sB[c][lane - c] -= fma(vl, sqD[half][c], ql * sv[c]);
+        }
+        __syncwarp();
+        if (warp == 2 && !keep0)                     // column 0 is final for this sweep: straight to the next sweep
+          ll_store(outbox + (size_t)k * LDB + lane, lane < L ? sB[0][lane] : 0.0, myflag);
+#pragma unroll
+        for (int cc = 0; cc < B / 2; ++cc) {         // write back column c, d in [0, L - c)
+          const int c = cb + cc;
+          if (c == 0 && !keep0) continue;
+          const int len = L - c, d0 = 2 * lane;
+          double* dst = Bb + (j0 + c) * LDB + d0;
+          if (d0 + 1 < len) __stcg(reinterpret_cast<double2*>(dst), make_double2(sB[c][d0], sB[c][d0 + 1]));
+          else if (d0 < len) __stcg(dst, sB[c][d0]);
+        }
+      } else {
+        double v2 = 0.0, tau2 = 0.0;
+        if (L2 > 0) {
+          // ---- E <- E H (lane = row a of E; each warp its 16 columns)
+          double yy[2] = {0.0, 0.0};
+#pragma unroll
+          for (int cc = 0; cc < B / 2; ++cc) {
+            const int c = cb + cc;
+            yy[cc & 1] = fma(sB[c][B - c + lane], sv[c], yy[cc & 1]);
+          }
+          sY[half][lane] = yy[0] + yy[1];
+          pair_barrier(1);
+          const double yl = tk * (sY[0][lane] + sY[1][lane]);
+#pragma unroll
+          for (int cc = 0; cc < B / 2; ++cc) {
+            const int c = cb + cc;
+            sB[c][B - c + lane] = fma(-yl, sv[c], sB[c][B - c + lane]);
+          }
+          __syncwarp();
+          if (warp == 0) {                           // new reflector from the first column of E
+            double beta2;
+            warp_house(lane < L2 ? sB[0][B + lane] : 0.0, lane, v2, tau2, beta2);
+            if (lane >= L2) v2 = 0.0;
+            sv2[lane] = v2;
+            if (lane == 0) {
+              s_tau2 = tau2;
+              s_beta2 = beta2;
+            }
+            // H2 leaves exactly (beta, 0, ..., 0) in the first column of E: the next sweep can have it now
+            if (!keep0) ll_store(outbox + (size_t)k * LDB + B + lane, lane == 0 ? beta2 : 0.0, myflag);
+          }
+          pair_barrier(1);
+          const double t2 = s_tau2, v2l = sv2[lane];
+          // ---- E <- H2 E: z_c = tau2 v2^T E[:, c]; lanes 0-15 / 16-31 sum rows 0-15 / 16-31 of column cb + (lane & 15)
+          {
+            const int c = cb + (lane & 15), a0 = (lane >> 4) * 16;
+            const double* col = &sB[c][B - c + a0];
+            double zz[2] = {0.0, 0.0};
+#pragma unroll
+            for (int a2 = 0; a2 < 16; ++a2) zz[a2 & 1] = fma(sv2[a0 + a2], col[a2], zz[a2 & 1]);
+            double zl = zz[0] + zz[1];
+            zl += __shfl_xor_sync(0xffffffffu, zl, 16);
+            if (lane < 16) sz[c] = t2 * zl;
+          }
+          __syncwarp();
+#pragma unroll
+          for (int cc = 0; cc < B / 2; ++cc) {
+            const int c = cb + cc;
+            sB[c][B - c + lane] = fma(-v2l, sz[c], sB[c][B - c + lane]);
+          }
+          if (warp == 0) sB[0][B + lane] = (lane == 0) ? s_beta2 : 0.0;     // exactly (beta, 0, ..., 0)
+          __syncwarp();
+#pragma unroll
+          for (int cc = 0; cc < B / 2; ++cc) {       // write back column c, d = B - c + a
+            const int c = cb + cc;
+            if (c == 0 && !keep0) continue;
+            if (c < L && lane < L2) __stcg(Bb + (j0 + c) * LDB + B - c + lane, sB[c][B - c + lane]);
+          }
+        } else if (warp == 0 && !keep0) {            // no E block: the lower half of column 0 as it was loaded
+          ll_store(outbox + (size_t)k * LDB + B + lane, sB[0][B + lane], myflag);
+        }
+        if (warp == 1 && boxed) {
+          // Column 31 came through the mailbox, so the band never saw the (beta, 0, ..., 0) that closed it in the
+          // previous sweep: what the band holds below its first entry is two sweeps old.  Write the whole column
+          // (later sweeps read entries of it that no task of this sweep writes).
+          double* dst = Bb + (j0 + B - 1) * LDB;
+          __stcg(dst + 1 + lane, sB[B - 1][1 + lane]);
+          if (lane < B - 1) __stcg(dst + B + 1 + lane, sB[B - 1][B + 1 + lane]);
+        }
+        v = v2;
+        tau = tau2;
+      }
+      // ---- publish progress: the CTA barrier orders every warp's stores before thread 0's release store
+      __syncthreads();
+      if (threadIdx.x == 0) st_release_u32(prog + i, (k + 1 == nt) ? 0x7fffffffu : (unsigned)(k + 1));
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256)
 sbr_band_to_tridiag_kernel(const double* __restrict__ Bb, const long N, double* __restrict__ d, double* __restrict__ e) {
   const long c = blockIdx.x * 256L + threadIdx.x;
@@ -1489,7 +1694,7 @@ sbr_back_q1_kernel(const double* __restrict__ Vall, const double* __restrict__ T
 // workspace layout
 // ------------------------------------------------------------------------------------------------
 struct SbrWs {
-  double *Vall, *Tall, *W, *X, *Xp, *Zp, *S, *mail, *Gq, *Bb, *V2, *TAU2;
+  double *Vall, *Tall, *W, *X, *Xp, *Zp, *S, *mail, *Gq, *Bb, *V2, *TAU2, *mail2;
   unsigned* bar;      // [0] barrier counter, [1] error flag, [2..] sweep progress (N)
   long npanel, ntask_max;
   int max_split, max_qr_ctas;
@@ -1525,6 +1730,7 @@ static SbrWs sbr_layout(double* ws, long N, size_t* total) {
   w.Bb = take((size_t)N * LDB);
   w.V2 = take((size_t)N * N);
   w.TAU2 = take((size_t)N * w.ntask_max);
+  w.mail2 = take((size_t)2 * w.ntask_max * LDB * 2);          // stage-2 mailboxes: [sweep parity][task][64] entries of 16 bytes
   w.bar = reinterpret_cast<unsigned*>(take((size_t)(N + 64) / 2 + 64));
   if (total) *total = off;
   return w;
@@ -1716,17 +1922,20 @@ static int sbr_stage2(long N, const SbrWs& w, double* d, double* e, cudaStream_t
     long Narg = N, ntm = w.ntask_max;
     double *V2 = w.V2, *TAU2 = w.TAU2;
     unsigned* bar = w.bar;
-    void* args[] = {&Bb, &Narg, &V2, &TAU2, &ntm, &bar};
-    // PODSDF_CHASE (A/B only): 1 = one warp per task, 2 = two warps; default: four warps per task
+    uint4* mail2 = reinterpret_cast<uint4*>(w.mail2);
+    void* args[] = {&Bb, &Narg, &V2, &TAU2, &ntm, &bar, &mail2};
+    // PODSDF_CHASE (A/B only): 1 = one warp per task, 2 = two warps, 4 = four warps with every hand-off through the
+    // band; default: four warps per task, the critical column through mailboxes
     const char* variant = getenv("PODSDF_CHASE");
     const int var = variant ? atoi(variant) : 0;
     const void* kern = (var == 1) ? (const void*)sbr_chase_kernel
-                                  : ((var == 2) ? (const void*)sbr_chase2_kernel : (const void*)sbr_chase4_kernel);
+                     : (var == 2) ? (const void*)sbr_chase2_kernel
+                     : (var == 4) ? (const void*)sbr_chase4_kernel : (const void*)sbr_chase5_kernel;
     const int threads = (var == 1) ? 32 : ((var == 2) ? 64 : 128);
     int per_sm = 1;
-    if (var == 1) PODSDF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sbr_chase_kernel, 32, 0));
-    else if (var == 2) PODSDF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sbr_chase2_kernel, 64, 0));
-    else PODSDF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sbr_chase4_kernel, 128, 0));
+    PODSDF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, 0));
+    // mailbox flags of an earlier solve must not look like this one's (flag = sweep + 1 > 0)
+    PODSDF_CUDA(cudaMemsetAsync(w.mail2, 0, sizeof(double) * 4 * (size_t)w.ntask_max * LDB, st));
     long G = (long)sms * (per_sm < 4 ? per_sm : 4);             // all chains co-resident (cooperative launch checks it)
     const long useful = (N + 2 * B - 1) / (2 * B) + 8;          // sweeps that can be in flight at once
     if (G > useful) G = useful;
