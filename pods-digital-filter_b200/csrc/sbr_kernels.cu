@@ -1290,10 +1290,10 @@ sbr_chase4_kernel(double* __restrict__ Bb, const long N, double* __restrict__ V2
 __global__ void __launch_bounds__(128)
 sbr_chase5_kernel(double* __restrict__ Bb, const long N, double* __restrict__ V2, double* __restrict__ TAU2,
                   const long ntask_max, unsigned* __restrict__ bar, uint4* __restrict__ mail) {
-  __shared__ __align__(16) double sB[B][LDB];
+  __shared__ __align__(16) double sBB[2][B][LDB];   // task k works in sBB[k & 1]; the other half receives task k+1's columns
   __shared__ double sv[B], sv2[B], sz[B], sqD[2][B], sY[2][B], sP[2][B];
   __shared__ double s_tau, s_tau2, s_beta2;
-  __shared__ int s_ok;
+  __shared__ int s_ok, s_pre[2];                    // s_pre[k & 1]: the prefetch of task k's columns succeeded
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int half = warp & 1;                         // which 16 columns of its block this warp owns
   const int cb = half * (B / 2);
@@ -1307,33 +1307,38 @@ sbr_chase5_kernel(double* __restrict__ Bb, const long N, double* __restrict__ V2
     const uint4* inbox = mail + (size_t)((i + 1) & 1) * ntask_max * LDB;   // the previous sweep's
     double v = 0.0, tau = 0.0;                       // warp 0: reflector of the current task (lane = row inside J_k)
     for (int k = 0; k < nt; ++k) {
-      if (threadIdx.x == 0) {                        // columns 0 .. 30 come from task k of sweep i-1, through the band
-        int ok = 1;
-        if (i > 0) {
-          const unsigned need = (unsigned)(k + 1);
-          unsigned spins = 0;
-          while (ld_acquire_u32(prog + i - 1) < need) {
-            if (++spins > (1u << 22)) {
-              if ((spins & 0xFFFFu) == 0 && ld_acquire_u32(err) != 0) { ok = 0; break; }
-              if (spins > (1u << 27)) { atomicExch(err, 2u); ok = 0; break; }
-            }
-          }
-        }
-        s_ok = ok;
-      }
-      __syncthreads();
-      if (!s_ok) return;
+      double (*sB)[LDB] = sBB[k & 1];
       const long j0 = i + 1 + (long)k * B;
       const int L = (int)min((long)B, N - j0);
       const int L2 = (int)max(0L, min((long)B, N - j0 - B));
       const bool boxed = i > 0 && L == B;            // column 31 arrives in the mailbox of task (i-1, k+1)
       const bool keep0 = k == 0;                     // column 0 of task 0 has no mailbox reader: it goes to the band
+      if (k == 0) {
+        // first task of the sweep: columns 0 .. 30 come from task 0 of sweep i-1, through the band (later tasks find
+        // theirs prefetched by the D warps of the task before)
+        if (threadIdx.x == 0) {
+          int ok = 1;
+          if (i > 0) {
+            unsigned spins = 0;
+            while (ld_acquire_u32(prog + i - 1) < 1u) {
+              if (++spins > (1u << 22)) {
+                if ((spins & 0xFFFFu) == 0 && ld_acquire_u32(err) != 0) { ok = 0; break; }
+                if (spins > (1u << 27)) { atomicExch(err, 2u); ok = 0; break; }
+              }
+            }
+          }
+          s_ok = ok;
+          s_pre[0] = 1;
+        }
+        __syncthreads();
+        if (!s_ok) return;
 #pragma unroll
-      for (int cc = 0; cc < B / 4; ++cc) {           // band columns j0 .. j0+L-1 (zero-filled beyond), a quarter per warp
-        const int c = warp * (B / 4) + cc;
-        if (c < B - 1 || !boxed) cpa16_cg(&sB[c][2 * lane], Bb + (j0 + c) * LDB + 2 * lane, c < L);
+        for (int cc = 0; cc < B / 4; ++cc) {         // band columns j0 .. j0+L-1 (zero-filled beyond), a quarter per warp
+          const int c = warp * (B / 4) + cc;
+          if (c < B - 1 || !boxed) cpa16_cg(&sB[c][2 * lane], Bb + (j0 + c) * LDB + 2 * lane, c < L);
+        }
+        cpa_commit();
       }
-      cpa_commit();
       int fail = 0;
       if (warp == 3 && boxed) {                      // (warp 3 has nothing else to do here) value and flag in one load
         const uint4* e0 = inbox + (size_t)(k + 1) * LDB + lane;
@@ -1368,6 +1373,7 @@ sbr_chase5_kernel(double* __restrict__ Bb, const long N, double* __restrict__ V2
       }
       cpa_wait<0>();
       if (__syncthreads_or(fail)) return;
+      if (!s_pre[k & 1]) return;                     // the prefetch of this task's columns gave up waiting
       const double tk = s_tau, vl = sv[lane];
       if (warp >= 2) {
         // ---- D <- H D H: p = tau D v (each warp sums its 16 columns), q = p - (tau/2)(p^T v) v, D -= v q^T + q v^T
@@ -1401,6 +1407,37 @@ sbr_chase5_kernel(double* __restrict__ Bb, const long N, double* __restrict__ V2
           double* dst = Bb + (j0 + c) * LDB + d0;
           if (d0 + 1 < len) __stcg(reinterpret_cast<double2*>(dst), make_double2(sB[c][d0], sB[c][d0 + 1]));
           else if (d0 < len) __stcg(dst, sB[c][d0]);
+        }
+        if (k + 1 < nt) {
+          // ---- the D warps are done long before the E chain: they fetch the next task's columns 0 .. 30 (written by
+          // task k+1 of sweep i-1 -- wait for its release) into the other buffer, off everybody's critical path
+          if (threadIdx.x == 64) {
+            int ok = 1;
+            if (i > 0) {
+              const unsigned need = (unsigned)(k + 2);
+              unsigned spins = 0;
+              while (ld_acquire_u32(prog + i - 1) < need) {
+                if (++spins > (1u << 22)) {
+                  if ((spins & 0xFFFFu) == 0 && ld_acquire_u32(err) != 0) { ok = 0; break; }
+                  if (spins > (1u << 27)) { atomicExch(err, 2u); ok = 0; break; }
+                }
+              }
+            }
+            s_pre[(k + 1) & 1] = ok;
+          }
+          pair_barrier(2);
+          if (s_pre[(k + 1) & 1]) {
+            double (*sN)[LDB] = sBB[(k + 1) & 1];
+            const long jn = j0 + B;
+            const int Ln = (int)min((long)B, N - jn);
+            const bool boxed_n = i > 0 && Ln == B;
+#pragma unroll
+            for (int cc = 0; cc < B / 2; ++cc) {
+              const int c = cb + cc;
+              if (c < B - 1 || !boxed_n) cpa16_cg(&sN[c][2 * lane], Bb + (jn + c) * LDB + 2 * lane, c < Ln);
+            }
+          }
+          cpa_commit();
         }
       } else {
         double v2 = 0.0, tau2 = 0.0;
