@@ -1518,6 +1518,235 @@ sbr_chase5_kernel(double* __restrict__ Bb, const long N, double* __restrict__ V2
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Stage 2, two task groups per sweep.  Task k+1 of a sweep needs from task k only the reflector that task k derives
+// half-way (from the first column of its E block); the second half of task k (H2 applied to E, write-back) touches
+// columns J_k only, which task k+1 never reads.  So a CTA holds TWO groups of four warps that take the even / odd tasks
+// of its sweep: group B starts task k+1 as soon as group A has the reflector (named-barrier hand-off through shared
+// memory) and the mailbox column of task k+1 has arrived, while group A finishes task k.  Per sweep the start of task
+// k then trails the previous sweep's by (half a task + mailbox hop) instead of (a whole task + half a task + hop).
+// Everything else as in sbr_chase5_kernel.  Barriers: 1 + g = group g (128 threads), 3 + g / 5 + g = its E / D warp
+// pair (64), 7 + g = reflector hand-off INTO group g (warp 0 of each group: 64), 9 + g = "the task before yours has
+// released its progress" into group g (64).  No early exits: a timed-out wait raises the error flag and s_dead, every
+// other wait in the CTA then falls through, and the (wrong) result is discarded by the host -- barriers stay balanced.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void named_sync(const int id, const int count) {
+  asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void named_arrive(const int id, const int count) {
+  asm volatile("bar.arrive %0, %1;\n" ::"r"(id), "r"(count) : "memory");
+}
+
+__global__ void __launch_bounds__(256)
+sbr_chase6_kernel(double* __restrict__ Bb, const long N, double* __restrict__ V2, double* __restrict__ TAU2,
+                  const long ntask_max, unsigned* __restrict__ bar, uint4* __restrict__ mail) {
+  __shared__ __align__(16) double sBB[2][B][LDB];   // group g works in sBB[g]
+  __shared__ double sv_[2][B], sv2_[2][B], sz_[2][B], sqD_[2][2][B], sY_[2][2][B], sP_[2][2][B];
+  __shared__ double s_tau_[2], s_tau2_[2], s_beta2_[2];
+  __shared__ volatile int s_dead;
+  const int g = threadIdx.x >> 7;                    // task group: tasks k with (k & 1) == g
+  const int lane = threadIdx.x & 31, warp = (threadIdx.x >> 5) & 3;   // warp within the group
+  const int half = warp & 1;                         // which 16 columns of its block this warp owns
+  const int cb = half * (B / 2);
+  const bool leader = (threadIdx.x & 127) == 0;
+  double (*sB)[LDB] = sBB[g];
+  double* sv = sv_[g];
+  double* sv2 = sv2_[g];
+  double* sz = sz_[g];
+  double (*sqD)[B] = sqD_[g];
+  double (*sY)[B] = sY_[g];
+  double (*sP)[B] = sP_[g];
+  const int GB = 1 + g, EB = 3 + g, DB = 5 + g, HB_in = 7 + g, HB_out = 7 + (g ^ 1), RB_in = 9 + g, RB_out = 9 + (g ^ 1);
+  unsigned* err = bar + 1;
+  unsigned* prog = bar + 2;
+  const long nsweep = N - 2;
+  if (threadIdx.x == 0) s_dead = 0;
+  __syncthreads();
+  for (long i = blockIdx.x; i < nsweep; i += gridDim.x) {
+    const int nt = (int)((N - 1 - i + B - 1) / B);
+    const unsigned myflag = (unsigned)(i + 1), inflag = (unsigned)i;       // mailbox flags: sweep index + 1
+    uint4* outbox = mail + (size_t)(i & 1) * ntask_max * LDB;              // slot of task k: outbox + k * LDB
+    const uint4* inbox = mail + (size_t)((i + 1) & 1) * ntask_max * LDB;   // the previous sweep's
+    for (int k = g; k < nt; k += 2) {
+      const long j0 = i + 1 + (long)k * B;
+      const int L = (int)min((long)B, N - j0);
+      const int L2 = (int)max(0L, min((long)B, N - j0 - B));
+      const bool boxed = i > 0 && L == B;            // column 31 arrives in the mailbox of task (i-1, k+1)
+      const bool keep0 = k == 0;                     // column 0 of task 0 has no mailbox reader: it goes to the band
+      // ---- columns 0 .. 30: written by task k of sweep i-1, through the band
+      if (leader && i > 0) {
+        const unsigned need = (unsigned)(k + 1);
+        unsigned spins = 0;
+        while (!s_dead && ld_acquire_u32(prog + i - 1) < need) {
+          if (++spins > (1u << 22)) {
+            if ((spins & 0xFFFFu) == 0 && ld_acquire_u32(err) != 0) { s_dead = 1; break; }
+            if (spins > (1u << 27)) { atomicExch(err, 2u); s_dead = 1; break; }
+          }
+        }
+      }
+      named_sync(GB, 128);
+#pragma unroll
+      for (int cc = 0; cc < B / 4; ++cc) {           // band columns j0 .. j0+L-1 (zero-filled beyond), a quarter per warp
+        const int c = warp * (B / 4) + cc;
+        if (c < B - 1 || !boxed) cpa16_cg(&sB[c][2 * lane], Bb + (j0 + c) * LDB + 2 * lane, c < L);
+      }
+      cpa_commit();
+      if (warp == 3 && boxed) {                      // column 31: value and flag in one load
+        const uint4* e0 = inbox + (size_t)(k + 1) * LDB + lane;
+        double x0 = 0.0, x1 = 0.0;
+        bool need0 = true, need1 = true;
+        unsigned spins = 0;
+        while ((need0 || need1) && !s_dead) {
+          if (need0) need0 = !ll_try(e0, inflag, x0);
+          if (need1) need1 = !ll_try(e0 + 32, inflag, x1);
+          if ((need0 || need1) && ++spins > (1u << 18)) {
+            if ((spins & 0xFFFu) == 0 && ld_acquire_u32(err) != 0) { s_dead = 1; break; }
+            if (spins > (1u << 25)) { atomicExch(err, 3u); s_dead = 1; break; }
+          }
+        }
+        sB[B - 1][lane] = (need0 || need1) ? 0.0 : x0;
+        sB[B - 1][lane + 32] = (need0 || need1) ? 0.0 : x1;
+      }
+      if (warp == 0) {
+        double v, tau;
+        if (k == 0) {                                // reflector of column i (overlaps the copies)
+          const double x = (lane < L) ? __ldcg(Bb + i * LDB + 1 + lane) : 0.0;
+          double beta;
+          warp_house(x, lane, v, tau, beta);
+          if (lane < L) __stcg(Bb + i * LDB + 1 + lane, lane == 0 ? beta : 0.0);
+        } else {                                     // handed over by the other group, half-way through task k-1
+          named_sync(HB_in, 64);
+          v = sv2_[g ^ 1][lane];
+          tau = s_tau2_[g ^ 1];
+        }
+        if (lane >= L) v = 0.0;
+        if (lane < L) V2[i * N + j0 + lane] = v;
+        if (lane == 0) {
+          TAU2[i * ntask_max + k] = tau;
+          s_tau_[g] = tau;
+        }
+        sv[lane] = v;
+      }
+      cpa_wait<0>();
+      named_sync(GB, 128);
+      const double tk = s_tau_[g], vl = sv[lane];
+      if (warp >= 2) {
+        // ---- D <- H D H: p = tau D v (each warp sums its 16 columns), q = p - (tau/2)(p^T v) v, D -= v q^T + q v^T
+        double pp[2] = {0.0, 0.0};
+#pragma unroll
+        for (int cc = 0; cc < B / 2; ++cc) {
+          const int c = cb + cc;
+          const int idx = (c <= lane) ? c * LDB + lane - c : lane * LDB + c - lane;
+          pp[cc & 1] = fma((&sB[0][0])[idx], sv[c], pp[cc & 1]);
+        }
+        sP[half][lane] = pp[0] + pp[1];
+        named_sync(DB, 64);                          // both halves summed; nobody reads D any more
+        const double pl = tk * (sP[0][lane] + sP[1][lane]);
+        const double kk = 0.5 * tk * warp_sum(pl * vl);
+        const double ql = fma(-kk, vl, pl);
+        sqD[half][lane] = ql;                        // each warp keeps its own copy: no second barrier
+        __syncwarp();
+#pragma unroll
+        for (int cc = 0; cc < B / 2; ++cc) {
+          const int c = cb + cc;
+          if (c <= lane) sB[c][lane - c] -= fma(vl, sqD[half][c], ql * sv[c]);
+        }
+        __syncwarp();
+        if (warp == 2 && !keep0)                     // column 0 is final for this sweep: straight to the next sweep
+          ll_store(outbox + (size_t)k * LDB + lane, lane < L ? sB[0][lane] : 0.0, myflag);
+#pragma unroll
+        for (int cc = 0; cc < B / 2; ++cc) {         // write back column c, d in [0, L - c)
+          const int c = cb + cc;
+          if (c == 0 && !keep0) continue;
+          const int len = L - c, d0 = 2 * lane;
+          double* dst = Bb + (j0 + c) * LDB + d0;
+          if (d0 + 1 < len) __stcg(reinterpret_cast<double2*>(dst), make_double2(sB[c][d0], sB[c][d0 + 1]));
+          else if (d0 < len) __stcg(dst, sB[c][d0]);
+        }
+      } else {
+        if (L2 > 0) {
+          // ---- E <- E H (lane = row a of E; each warp its 16 columns)
+          double yy[2] = {0.0, 0.0};
+#pragma unroll
+          for (int cc = 0; cc < B / 2; ++cc) {
+            const int c = cb + cc;
+            yy[cc & 1] = fma(sB[c][B - c + lane], sv[c], yy[cc & 1]);
+          }
+          sY[half][lane] = yy[0] + yy[1];
+          named_sync(EB, 64);
+          const double yl = tk * (sY[0][lane] + sY[1][lane]);
+#pragma unroll
+          for (int cc = 0; cc < B / 2; ++cc) {
+            const int c = cb + cc;
+            sB[c][B - c + lane] = fma(-yl, sv[c], sB[c][B - c + lane]);
+          }
+          __syncwarp();
+          if (warp == 0) {                           // new reflector from the first column of E
+            double v2, tau2, beta2;
+            warp_house(lane < L2 ? sB[0][B + lane] : 0.0, lane, v2, tau2, beta2);
+            if (lane >= L2) v2 = 0.0;
+            sv2[lane] = v2;
+            if (lane == 0) {
+              s_tau2_[g] = tau2;
+              s_beta2_[g] = beta2;
+            }
+            // H2 leaves exactly (beta, 0, ..., 0) in the first column of E: the next sweep can have it now
+            if (!keep0) ll_store(outbox + (size_t)k * LDB + B + lane, lane == 0 ? beta2 : 0.0, myflag);
+            if (k + 1 < nt) {                        // ... and the other group the reflector of task k+1
+              __threadfence_block();
+              named_arrive(HB_out, 64);
+            }
+          }
+          named_sync(EB, 64);
+          const double t2 = s_tau2_[g], v2l = sv2[lane];
+          // ---- E <- H2 E: z_c = tau2 v2^T E[:, c]; lanes 0-15 / 16-31 sum rows 0-15 / 16-31 of column cb + (lane & 15)
+          {
+            const int c = cb + (lane & 15), a0 = (lane >> 4) * 16;
+            const double* col = &sB[c][B - c + a0];
+            double zz[2] = {0.0, 0.0};
+#pragma unroll
+            for (int a2 = 0; a2 < 16; ++a2) zz[a2 & 1] = fma(sv2[a0 + a2], col[a2], zz[a2 & 1]);
+            double zl = zz[0] + zz[1];
+            zl += __shfl_xor_sync(0xffffffffu, zl, 16);
+            if (lane < 16) sz[c] = t2 * zl;
+          }
+          __syncwarp();
+#pragma unroll
+          for (int cc = 0; cc < B / 2; ++cc) {
+            const int c = cb + cc;
+            sB[c][B - c + lane] = fma(-v2l, sz[c], sB[c][B - c + lane]);
+          }
+          if (warp == 0) sB[0][B + lane] = (lane == 0) ? s_beta2_[g] : 0.0;     // exactly (beta, 0, ..., 0)
+          __syncwarp();
+#pragma unroll
+          for (int cc = 0; cc < B / 2; ++cc) {       // write back column c, d = B - c + a
+            const int c = cb + cc;
+            if (c == 0 && !keep0) continue;
+            if (c < L && lane < L2) __stcg(Bb + (j0 + c) * LDB + B - c + lane, sB[c][B - c + lane]);
+          }
+        } else if (warp == 0) {                      // no E block (hence no task k+1): the lower half of column 0 as loaded
+          if (!keep0) ll_store(outbox + (size_t)k * LDB + B + lane, sB[0][B + lane], myflag);
+        }
+        if (warp == 1 && boxed) {
+          // Column 31 came through the mailbox, so the band never saw the (beta, 0, ..., 0) that closed it in the
+          // previous sweep: write the whole column (later sweeps read entries of it that no task of this sweep writes).
+          double* dst = Bb + (j0 + B - 1) * LDB;
+          __stcg(dst + 1 + lane, sB[B - 1][1 + lane]);
+          if (lane < B - 1) __stcg(dst + B + 1 + lane, sB[B - 1][B + 1 + lane]);
+        }
+      }
+      // ---- publish progress (in task order): the group barrier orders every warp's stores before the release store
+      named_sync(GB, 128);
+      if (warp == 0) {
+        if (k > 0) named_sync(RB_in, 64);            // task k-1 has released
+        if (lane == 0) st_release_u32(prog + i, (k + 1 == nt) ? 0x7fffffffu : (unsigned)(k + 1));
+        if (k + 1 < nt) named_arrive(RB_out, 64);
+      }
+    }
+    __syncthreads();                                 // both groups done with the sweep (barrier phases realigned)
+  }
+}
+
 __global__ void __launch_bounds__(256)
 sbr_band_to_tridiag_kernel(const double* __restrict__ Bb, const long N, double* __restrict__ d, double* __restrict__ e) {
   const long c = blockIdx.x * 256L + threadIdx.x;
@@ -1962,13 +2191,14 @@ static int sbr_stage2(long N, const SbrWs& w, double* d, double* e, cudaStream_t
     uint4* mail2 = reinterpret_cast<uint4*>(w.mail2);
     void* args[] = {&Bb, &Narg, &V2, &TAU2, &ntm, &bar, &mail2};
     // PODSDF_CHASE (A/B only): 1 = one warp per task, 2 = two warps, 4 = four warps with every hand-off through the
-    // band; default: four warps per task, the critical column through mailboxes
+    // band, 5 = four warps, the critical column through mailboxes; default: the same with two task groups per sweep
     const char* variant = getenv("PODSDF_CHASE");
     const int var = variant ? atoi(variant) : 0;
     const void* kern = (var == 1) ? (const void*)sbr_chase_kernel
                      : (var == 2) ? (const void*)sbr_chase2_kernel
-                     : (var == 4) ? (const void*)sbr_chase4_kernel : (const void*)sbr_chase5_kernel;
-    const int threads = (var == 1) ? 32 : ((var == 2) ? 64 : 128);
+                     : (var == 4) ? (const void*)sbr_chase4_kernel
+                     : (var == 5) ? (const void*)sbr_chase5_kernel : (const void*)sbr_chase6_kernel;
+    const int threads = (var == 1) ? 32 : ((var == 2) ? 64 : ((var == 4 || var == 5) ? 128 : 256));
     int per_sm = 1;
     PODSDF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, 0));
     // mailbox flags of an earlier solve must not look like this one's (flag = sweep + 1 > 0)
