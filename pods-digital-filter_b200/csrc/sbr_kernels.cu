@@ -1537,14 +1537,17 @@ __device__ __forceinline__ void named_arrive(const int id, const int count) {
   asm volatile("bar.arrive %0, %1;\n" ::"r"(id), "r"(count) : "memory");
 }
 
-__global__ void __launch_bounds__(256)
+template <int NG>
+__global__ void __launch_bounds__(128 * NG)
 sbr_chase6_kernel(double* __restrict__ Bb, const long N, double* __restrict__ V2, double* __restrict__ TAU2,
                   const long ntask_max, unsigned* __restrict__ bar, uint4* __restrict__ mail) {
-  __shared__ __align__(16) double sBB[2][B][LDB];   // group g works in sBB[g]
-  __shared__ double sv_[2][B], sv2_[2][B], sz_[2][B], sqD_[2][2][B], sY_[2][2][B], sP_[2][2][B];
-  __shared__ double s_tau_[2], s_tau2_[2], s_beta2_[2];
+  extern __shared__ __align__(16) double smem_chase[];
+  double (*sBB)[B][LDB] = reinterpret_cast<double (*)[B][LDB]>(smem_chase);   // group g works in sBB[g]
+  __shared__ double sv_[NG][B], sv2_[NG][B], sz_[NG][B], sqD_[NG][2][B], sY_[NG][2][B], sP_[NG][2][B];
+  __shared__ double s_tau_[NG], s_tau2_[NG], s_beta2_[NG];
   __shared__ volatile int s_dead;
-  const int g = threadIdx.x >> 7;                    // task group: tasks k with (k & 1) == g
+  const int g = threadIdx.x >> 7;                    // task group: tasks k with k % NG == g
+  const int gp = (g + NG - 1) % NG, gn = (g + 1) % NG;   // the groups of tasks k-1 / k+1
   const int lane = threadIdx.x & 31, warp = (threadIdx.x >> 5) & 3;   // warp within the group
   const int half = warp & 1;                         // which 16 columns of its block this warp owns
   const int cb = half * (B / 2);
@@ -1556,7 +1559,9 @@ sbr_chase6_kernel(double* __restrict__ Bb, const long N, double* __restrict__ V2
   double (*sqD)[B] = sqD_[g];
   double (*sY)[B] = sY_[g];
   double (*sP)[B] = sP_[g];
-  const int GB = 1 + g, EB = 3 + g, DB = 5 + g, HB_in = 7 + g, HB_out = 7 + (g ^ 1), RB_in = 9 + g, RB_out = 9 + (g ^ 1);
+  const int GB = 1 + g, EB = 1 + NG + g, DB = 1 + 2 * NG + g, HB_in = 1 + 3 * NG + g, HB_out = 1 + 3 * NG + gn,
+            RB_in = 1 + 4 * NG + g, RB_out = 1 + 4 * NG + gn;
+  static_assert(5 * NG <= 15, "sixteen named barriers per CTA");
   unsigned* err = bar + 1;
   unsigned* prog = bar + 2;
   const long nsweep = N - 2;
@@ -1567,7 +1572,7 @@ sbr_chase6_kernel(double* __restrict__ Bb, const long N, double* __restrict__ V2
     const unsigned myflag = (unsigned)(i + 1), inflag = (unsigned)i;       // mailbox flags: sweep index + 1
     uint4* outbox = mail + (size_t)(i & 1) * ntask_max * LDB;              // slot of task k: outbox + k * LDB
     const uint4* inbox = mail + (size_t)((i + 1) & 1) * ntask_max * LDB;   // the previous sweep's
-    for (int k = g; k < nt; k += 2) {
+    for (int k = g; k < nt; k += NG) {
       const long j0 = i + 1 + (long)k * B;
       const int L = (int)min((long)B, N - j0);
       const int L2 = (int)max(0L, min((long)B, N - j0 - B));
@@ -1616,8 +1621,8 @@ sbr_chase6_kernel(double* __restrict__ Bb, const long N, double* __restrict__ V2
           if (lane < L) __stcg(Bb + i * LDB + 1 + lane, lane == 0 ? beta : 0.0);
         } else {                                     // handed over by the other group, half-way through task k-1
           named_sync(HB_in, 64);
-          v = sv2_[g ^ 1][lane];
-          tau = s_tau2_[g ^ 1];
+          v = sv2_[gp][lane];
+          tau = s_tau2_[gp];
         }
         if (lane >= L) v = 0.0;
         if (lane < L) V2[i * N + j0 + lane] = v;
@@ -2191,23 +2196,28 @@ static int sbr_stage2(long N, const SbrWs& w, double* d, double* e, cudaStream_t
     uint4* mail2 = reinterpret_cast<uint4*>(w.mail2);
     void* args[] = {&Bb, &Narg, &V2, &TAU2, &ntm, &bar, &mail2};
     // PODSDF_CHASE (A/B only): 1 = one warp per task, 2 = two warps, 4 = four warps with every hand-off through the
-    // band, 5 = four warps, the critical column through mailboxes; default: the same with two task groups per sweep
+    // band, 5 = four warps, the critical column through mailboxes, 7 = three task groups per sweep (67 ms: twelve
+    // latency-bound warps on an SM slow each other down); default: two task groups (47 ms)
     const char* variant = getenv("PODSDF_CHASE");
     const int var = variant ? atoi(variant) : 0;
     const void* kern = (var == 1) ? (const void*)sbr_chase_kernel
                      : (var == 2) ? (const void*)sbr_chase2_kernel
                      : (var == 4) ? (const void*)sbr_chase4_kernel
-                     : (var == 5) ? (const void*)sbr_chase5_kernel : (const void*)sbr_chase6_kernel;
-    const int threads = (var == 1) ? 32 : ((var == 2) ? 64 : ((var == 4 || var == 5) ? 128 : 256));
+                     : (var == 5) ? (const void*)sbr_chase5_kernel
+                     : (var == 7) ? (const void*)sbr_chase6_kernel<3> : (const void*)sbr_chase6_kernel<2>;
+    const int groups = (var == 7) ? 3 : 2;
+    const int threads = (var == 1) ? 32 : ((var == 2) ? 64 : ((var == 4 || var == 5) ? 128 : 128 * groups));
+    const size_t dyn = (var == 1 || var == 2 || var == 4 || var == 5) ? 0 : (size_t)groups * B * LDB * sizeof(double);
+    if (dyn > 0) PODSDF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
     int per_sm = 1;
-    PODSDF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, 0));
+    PODSDF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, dyn));
     // mailbox flags of an earlier solve must not look like this one's (flag = sweep + 1 > 0)
     PODSDF_CUDA(cudaMemsetAsync(w.mail2, 0, sizeof(double) * 4 * (size_t)w.ntask_max * LDB, st));
     long G = (long)sms * (per_sm < 4 ? per_sm : 4);             // all chains co-resident (cooperative launch checks it)
     const long useful = (N + 2 * B - 1) / (2 * B) + 8;          // sweeps that can be in flight at once
     if (G > useful) G = useful;
     if (G > nsweep) G = nsweep;
-    PODSDF_CUDA(cudaLaunchCooperativeKernel(kern, dim3((unsigned)G), dim3(threads), args, 0, st));
+    PODSDF_CUDA(cudaLaunchCooperativeKernel(kern, dim3((unsigned)G), dim3(threads), args, dyn, st));
     count_launch();
   }
   sbr_band_to_tridiag_kernel<<<ceil_div(N, 256L), 256, 0, st>>>(w.Bb, N, d, e);
