@@ -13,9 +13,10 @@
 //                                                orientations, split over K
 //              W = X T - 1/2 V (T^T V^T X T)     two small kernels
 //              A22 -= V W^T + W V^T              FP64 tensor-core MMA rank-2b update, lower tiles + full diagonal tiles
-//   stage 2  band -> tridiagonal by bulge chasing (Murata-Horikoshi / Lang): sweep i = chain of b x b tasks, one CTA
-//            (two warps: diagonal block / sub-diagonal block) per sweep, sweeps pipelined two tasks apart through
-//            progress counters in global memory (persistent cooperative kernel)
+//   stage 2  band -> tridiagonal by bulge chasing (Murata-Horikoshi / Lang): sweep i = chain of b x b tasks, one CTA per
+//            sweep in a persistent cooperative kernel: two groups of four warps take the even / odd tasks (a task's
+//            successor starts when its reflector is known); of the 32 band columns of a task, 31 come through the band
+//            one task early and the one it actually waits for through flagged mailbox entries, posted mid-task
 //   back     eigenvectors of T -> eigenvectors of C: stage-2 reflectors (reverse order), then the block reflectors of
 //            stage 1, one CTA per vector with the vector in shared memory
 //
