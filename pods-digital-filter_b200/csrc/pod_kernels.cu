@@ -576,8 +576,59 @@ mean_rows_l1_kernel(double* __restrict__ A, const long M, const long N, double* 
     for (long t = 0; t < N; ++t) A[t * M + row] -= m;
 }
 
+// Layout 0, rows up to MR_MAXPT * 256 entries long: one CTA per row keeps the row in registers between the sum and the
+// subtraction, so the matrix is read once and written once (the warp-per-row kernel above reads it twice: 94 GB instead
+// of 63 GB at 393 216 x 10^4, 14.2 ms -> see DESIGN.md section 6).
+constexpr int MR_MAXPT = 40;
+__global__ void __launch_bounds__(256)
+mean_rows_l0_reg_kernel(double* __restrict__ A, const long M, const long N, double* __restrict__ mean, const int sub) {
+  __shared__ double s_part[8];
+  __shared__ double s_mean;
+  const long row = blockIdx.x;
+  double* p = A + row * N;
+  const int tid = threadIdx.x;
+  double v[MR_MAXPT];
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+  for (int q = 0; q < MR_MAXPT; ++q) {
+    const long t = tid + 256L * q;
+    v[q] = (t < N) ? __ldcs(p + t) : 0.0;           // streamed: nothing of this row is read again
+  }
+#pragma unroll
+  for (int q = 0; q < MR_MAXPT; q += 4) {
+    s0 += v[q];
+    s1 += v[q + 1];
+    s2 += v[q + 2];
+    s3 += v[q + 3];
+  }
+  double s = (s0 + s1) + (s2 + s3);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((tid & 31) == 0) s_part[tid >> 5] = s;
+  __syncthreads();
+  if (tid == 0) {
+    double tot = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) tot += s_part[w];
+    const double m = tot / (double)N;
+    s_mean = m;
+    mean[row] = m;
+  }
+  if (!sub) return;
+  __syncthreads();
+  const double m = s_mean;
+#pragma unroll
+  for (int q = 0; q < MR_MAXPT; ++q) {
+    const long t = tid + 256L * q;
+    if (t < N) p[t] = v[q] - m;
+  }
+}
+static_assert(MR_MAXPT % 4 == 0, "four partial sums");
+
 int launch_mean_rows(double* A, long M, long N, int layout, double* mean, int subtract, cudaStream_t st) {
-  if (layout == 0)
+  if (layout == 0 && N <= 256L * MR_MAXPT && N >= 2048 && M <= 2147483647L)
+    mean_rows_l0_reg_kernel<<<(unsigned)M, 256, 0, st>>>(A, M, N, mean, subtract);
+  else if (layout == 0)
     mean_rows_l0_kernel<<<ceil_div(M, 8), 256, 0, st>>>(A, M, N, mean, subtract);
   else
     mean_rows_l1_kernel<<<ceil_div(M, 256), 256, 0, st>>>(A, M, N, mean, subtract);

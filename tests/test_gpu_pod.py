@@ -170,6 +170,25 @@ def test_pod_weighted_branch_against_oracle(P):
     _check_pod(P, A, N, M // 3, nm, 0.02, 0.9, ref, None, weights=w)
 
 
+@pytest.mark.parametrize("M,N", [(37, 2048), (19, 3001), (5, 10240), (11, 10241), (300, 2047)])
+def test_row_means_long_rows(P, M, N):
+    """podsdf_mean_rows_dev, layout 0 (DF:1492-1495): rows of 2048 .. 10240 entries take the kernel that keeps a row in
+    registers between the sum and the subtraction; shorter / longer rows the two-pass kernel.  Both against numpy, with
+    and without the in-place subtraction."""
+    torch = pytest.importorskip("torch")
+    capi, L = P._capi, P._capi.lib()
+    rs = np.random.RandomState(M + N)
+    A = rs.standard_normal((M, N)) + 5.0 * rs.standard_normal((M, 1))
+    for sub in (0, 1):
+        d = torch.from_numpy(A.copy()).cuda()
+        mean = torch.full((M,), float("nan"), dtype=torch.float64, device="cuda")
+        capi.check(L.podsdf_mean_rows_dev(0, d.data_ptr(), M, N, 0, mean.data_ptr(), sub, 0))
+        torch.cuda.synchronize()
+        assert np.abs(mean.cpu().numpy() - A.mean(1)).max() < 1e-13
+        want = A - A.mean(1)[:, None] if sub else A
+        assert np.abs(d.cpu().numpy() - want).max() < 1e-13
+
+
 def test_device_entries_mean_gram_project(P):
     torch = pytest.importorskip("torch")
     capi = P._capi
