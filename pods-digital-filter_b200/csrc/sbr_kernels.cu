@@ -121,14 +121,21 @@ __device__ __forceinline__ bool grid_barrier(unsigned* counter, unsigned* err, u
 // each 8-byte half validated by its own copy of the flag (the low-latency protocol of collective libraries).  Replaces
 // "store, fence, count, poll the counter, then load" (three L2 round trips) by one; a flag is never reused: it carries
 // the launch's epoch.
+#ifdef PODSDF_LL_RELAXED
+#define PODSDF_LL_ST "st.relaxed.gpu.global.v4.u32"
+#define PODSDF_LL_LD "ld.relaxed.gpu.global.v4.u32"
+#else
+#define PODSDF_LL_ST "st.volatile.global.v4.u32"
+#define PODSDF_LL_LD "ld.volatile.global.v4.u32"
+#endif
 __device__ __forceinline__ void ll_store(uint4* p, const double v, const unsigned flag) {
   const unsigned lo = (unsigned)__double2loint(v), hi = (unsigned)__double2hiint(v);
-  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};\n" ::"l"(p), "r"(lo), "r"(flag), "r"(hi), "r"(flag)
+  asm volatile(PODSDF_LL_ST " [%0], {%1, %2, %3, %4};\n" ::"l"(p), "r"(lo), "r"(flag), "r"(hi), "r"(flag)
                : "memory");
 }
 __device__ __forceinline__ bool ll_try(const uint4* p, const unsigned flag, double& v) {
   unsigned a, b, c, d;
-  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];\n" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(p) : "memory");
+  asm volatile(PODSDF_LL_LD " {%0, %1, %2, %3}, [%4];\n" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(p) : "memory");
   v = __hiloint2double((int)c, (int)a);
   return b == flag && d == flag;
 }
