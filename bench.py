@@ -786,7 +786,7 @@ def run_pod(args, pkg, torch, dist, dev, local_rank, rank, world, barrier, max_o
         "metric": "pod_snapshots_per_s", "value": N / (ms * 1e-3), "unit": "snapshots/s", "ms_per_step": ms, "steps": steps,
         "ms_each_step": step_ms,
         "config": {"workload": "cfg4 row shard: %d rows x %d snapshots per GPU (x%d GPUs), %d modes, et=0.9" % (M, N, world, nm)},
-        "parts_ms": {k: v / steps for k, v in timers.items()},
+        "parts_ms": {k: (v / steps if not isinstance(v, list) else v) for k, v in timers.items()},
         "roofline": {"kernel": "gram_dmma_kernel (FP64 mma.sync m8n8k4, upper-triangular tiles)", "bound": "tensor",
                      "achieved": tf, "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": tf / FP64_DMMA_PEAK_TFLOPS,
                      "peak_source": "measured FP64 DMMA peak on this pool (tools/probe_fp64.cu); MEASURED_PEAKS.json has no FP64 entry",

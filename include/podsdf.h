@@ -187,7 +187,8 @@ PODSDF_API int podsdf_project_dev(int device, const double* A_dev, long M, long 
 
 /* ref: fourier_coefficients POD:1562-1573.  c[n][i] = (1/N) sum_j a[j][i] exp(-2 pi i (n - N/2) j / N)
  * for the first nm columns of the row-major (N x ld) matrix a.  Output interleaved complex128
- * c[N][nm][2].  The complex64 cast, ranking and energy cut (POD:1577-1593) stay in the shim. */
+ * c[N][nm][2].  The complex64 cast, ranking and energy cut (POD:1577-1593) stay in the shim.
+ * The _dev entry is asynchronous: c_dev is complete in the order of `stream` (its workspace is a cached device buffer). */
 PODSDF_API int podsdf_dft_modes_host(int device, const double* a_host, long N, long ld, int nm, double* c_host);
 PODSDF_API int podsdf_dft_modes_dev(int device, const double* a_dev, long N, long ld, int nm, double* c_dev,
                          void* stream);

@@ -23,7 +23,7 @@ struct Scratch {
   double* p = nullptr;
   size_t bytes = 0;
 };
-Scratch g_scratch[64][3];
+Scratch g_scratch[64][4];      // slots: 0 Gram partials, 1 library solver, 2 leading-pairs solve, 3 DFT workspace
 std::mutex g_scratch_mu;
 int scratch_get(int device, int slot, size_t bytes, double** out) {
   std::lock_guard<std::mutex> lk(g_scratch_mu);
@@ -498,11 +498,19 @@ int podsdf_dft_modes_dev(int device, const double* a_dev, long N, long ld, int n
   PODSDF_TRY(check_device(device));
   DeviceGuard guard(device);
   cudaStream_t st = (cudaStream_t)stream;
-  DevBuf tw;
-  PODSDF_CUDA(tw.alloc(sizeof(double) * dft_workspace_doubles(N, nm)));
-  int rc = launch_dft(a_dev, N, ld, nm, tw.p, c_dev, st);
-  cudaError_t e = cudaStreamSynchronize(st);  // twiddle table is freed on return
-  if (!rc && e != cudaSuccess) rc = cuda_fail(e, "dft", __FILE__, __LINE__);
+  // The workspace (twiddle table + intermediate) lives in the grow-only scratch: no allocation, no free and no
+  // host-side wait per call (an allocate / synchronise / free here stalled the host for 0.2 - 0.4 s per PODFS step
+  // once the process held tens of GB).  A call that re-uses the table on another stream waits for the previous one.
+  static cudaEvent_t dft_done[64] = {};
+  static std::mutex dft_mu;
+  std::lock_guard<std::mutex> lk(dft_mu);
+  cudaEvent_t& ev = dft_done[device & 63];
+  if (!ev) PODSDF_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  else PODSDF_CUDA(cudaStreamWaitEvent(st, ev, 0));
+  double* tw = nullptr;
+  PODSDF_TRY(scratch_get(device, 3, sizeof(double) * dft_workspace_doubles(N, nm), &tw));
+  const int rc = launch_dft(a_dev, N, ld, nm, tw, c_dev, st);
+  PODSDF_CUDA(cudaEventRecord(ev, st));
   return rc;
 }
 
