@@ -635,16 +635,18 @@ sbr_w2_kernel(const double* __restrict__ X, const double* __restrict__ V, const 
 
 // ------------------------------------------------------------------------------------------------
 // Stage 1e: A22 -= V W^T + W V^T on the tiles (I >= J) of the trailing matrix (diagonal 128-blocks in full).
-//   CTA = 128 (i) x 64 (j) tile, 4 warps x (64 x 32), K = 2B resident in shared memory ([k][pitch], the gram kernel's
+//   CTA = 128 (i) x 64 (j) tile, 8 warps x (32 x 32), K = 2B resident in shared memory ([k][pitch], the gram kernel's
 //   micro-kernel); two CTAs per SM, so that one CTA's loads (old tile -> accumulators, operands -> shared memory) and
-//   stores overlap the other's DMMAs -- at K = 64 they are half of a tile's time (profiles/r02_sbr_profile.md).
+//   stores overlap the other's DMMAs -- at K = 64 they are half of a tile's time (profiles/r02_sbr_profile.md).  Eight
+//   warps, not four: a lone warp per scheduler drives the FP64 tensor pipe at ~45 % (its DMMAs wait on each other's issue),
+//   two reach what the Gram kernel reaches -- so each CTA brings its own two.
 //   operand a (rows i): k < B -> -V[k][i], else -W[k-B][i];  operand b (rows j): k < B -> W[k][j], else V[k-B][j].
 //   The accumulators start as the old tile, so the epilogue is a plain store.
 //   Tiles are anchored at absolute multiples of 128 rows / 64 columns (see sbr_symm_kernel); with h = 1 when r0 lies in
 //   the upper half of its 128-block, row r (from the block of r0) holds the column blocks 0 .. 2r + 1 - h.
 // ------------------------------------------------------------------------------------------------
 constexpr int UT = 128, UTJ = 64, UPA = UT + 4, UPB = UTJ + 4;
-constexpr int U_THREADS = 128;
+constexpr int U_THREADS = 256;
 constexpr size_t USMEM = (size_t)(2 + 2 * B * (UPA + UPB)) * sizeof(double);    // mbarrier + operands
 
 // number of CTAs of one update: part 0 = every tile, 1 = the first column block only (it holds the next panel),
@@ -695,7 +697,7 @@ sbr_syr2k_kernel(double* __restrict__ A, const long N, const long r0, const doub
   }
   const long i0 = (tile0 + r) * UT, j0 = (2 * tile0 + h + rem) * UTJ;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm = (warp >> 1) * 64, wn = (warp & 1) * 32;
+  const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;     // 8 warps: 4 row groups of 32 x 2 column groups of 32
   const int lr = lane & 3, lc = lane >> 2;
   const bool bulk = (N & 1) == 0;       // operand rows start 16-byte aligned
 
@@ -728,10 +730,10 @@ sbr_syr2k_kernel(double* __restrict__ A, const long N, const long r0, const doub
 
   const bool full = i0 >= r0 && i0 + UT <= N && j0 >= r0 && j0 + UTJ <= N;
   double* const c00 = A + (j0 + wn + 2 * lr) * N + i0 + wm + lc;     // element (mt, nt, e) at c00[(nt * 8 + e) * N + mt * 8]
-  double acc[8][4][2];
+  double acc[4][4][2];
 #if PODSDF_SYR2K_RED
 #pragma unroll
-  for (int mt = 0; mt < 8; ++mt)
+  for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
 #else
@@ -742,11 +744,11 @@ sbr_syr2k_kernel(double* __restrict__ A, const long N, const long r0, const doub
       for (int e = 0; e < 2; ++e) {
         const double* col = c00 + (long)(nt * 8 + e) * N;
 #pragma unroll
-        for (int mt = 0; mt < 8; ++mt) acc[mt][nt][e] = col[mt * 8];
+        for (int mt = 0; mt < 4; ++mt) acc[mt][nt][e] = col[mt * 8];
       }
   } else {
 #pragma unroll
-    for (int mt = 0; mt < 8; ++mt)
+    for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) {
         const long i = i0 + wm + mt * 8 + lc, j = j0 + wn + nt * 8 + 2 * lr;
@@ -764,14 +766,14 @@ sbr_syr2k_kernel(double* __restrict__ A, const long N, const long r0, const doub
   }
 #pragma unroll 4
   for (int k4 = 0; k4 < 2 * B; k4 += 4) {
-    double af[8], bf[4];
+    double af[4], bf[4];
     const int rr = k4 + lr;
 #pragma unroll
-    for (int mt = 0; mt < 8; ++mt) af[mt] = -sA[rr * UPA + wm + mt * 8 + lc];
+    for (int mt = 0; mt < 4; ++mt) af[mt] = -sA[rr * UPA + wm + mt * 8 + lc];
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) bf[nt] = sB[rr * UPB + wn + nt * 8 + lc];
 #pragma unroll
-    for (int mt = 0; mt < 8; ++mt)
+    for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) dmma884s(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
   }
@@ -782,11 +784,11 @@ sbr_syr2k_kernel(double* __restrict__ A, const long N, const long r0, const doub
       for (int e = 0; e < 2; ++e) {
         double* col = c00 + (long)(nt * 8 + e) * N;
 #pragma unroll
-        for (int mt = 0; mt < 8; ++mt) U_OUT(col + mt * 8, acc[mt][nt][e]);
+        for (int mt = 0; mt < 4; ++mt) U_OUT(col + mt * 8, acc[mt][nt][e]);
       }
   } else {
 #pragma unroll
-    for (int mt = 0; mt < 8; ++mt)
+    for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) {
         const long i = i0 + wm + mt * 8 + lc, j = j0 + wn + nt * 8 + 2 * lr;
