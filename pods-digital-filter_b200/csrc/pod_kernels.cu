@@ -51,6 +51,17 @@ constexpr int GT = 128;   // snapshots per tile side
 #endif
 constexpr int GKB = PODSDF_GKB;   // rows (reduction depth) per pipeline stage
 constexpr int GST = 3;    // cp.async stages
+#ifndef PODSDF_GRAM_WARPS
+#define PODSDF_GRAM_WARPS 8
+#endif
+// warps per CTA: 8 (warp tile 64 x 32) or 16 (32 x 32, -DPODSDF_GRAM_WARPS=16).  Measured at 393 216 x 10^4: 1.244 s with
+// 8, 1.266 s with 16 -- two warps per scheduler already keep the tensor pipe at 87 %, four pay more shared-memory loads
+// per DMMA (0.5 instead of 0.375) for nothing.  (The rank-2b update of the eigen-solver, whose CTAs spend half their
+// time outside the MMA loop, is the opposite case: there a lone warp per scheduler reached 45 %.)
+constexpr int GWARPS = PODSDF_GRAM_WARPS;
+constexpr int GTHR = 32 * GWARPS;
+constexpr int GMT = 128 / (GWARPS / 4) / 8;   // 8-row MMA tiles per warp
+static_assert(GWARPS == 8 || GWARPS == 16, "warp layout");
 constexpr int GP0 = GT + 4;   // layout-0 pitch (132 = 4 mod 16)
 constexpr int GP1 = GKB + 4;  // layout-1 pitch (20 = 4 mod 16)
 
@@ -61,7 +72,7 @@ struct GramSmem {
 };
 
 template <int LAYOUT, bool VEC, bool WEIGHT>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(GTHR, 1)
 gram_dmma_kernel(const double* __restrict__ A, const long M, const long N, const double* __restrict__ w,
                  const long P, double* __restrict__ W, const int ntile_side, const long rows_per_split) {
   extern __shared__ double smem[];
@@ -80,7 +91,7 @@ gram_dmma_kernel(const double* __restrict__ A, const long M, const long N, const
   const int nchunks = (int)((r_end - r_begin + GKB - 1) / GKB);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm = (warp >> 2) * 64, wn = (warp & 3) * 32;  // warp tile origin inside the CTA tile
+  const int wm = (warp >> 2) * (GMT * 8), wn = (warp & 3) * 32;  // warp tile origin inside the CTA tile
   const int lr = lane & 3, lc = lane >> 2;
 
   auto load_stage = [&](int chunk, int stage) {
@@ -89,14 +100,14 @@ gram_dmma_kernel(const double* __restrict__ A, const long M, const long N, const
     double* b = sB + stage * TILE;
     if (LAYOUT == 0) {
       if (VEC) {  // 16-byte copies: GKB rows x 64 pairs per operand
-        for (int e = tid; e < GKB * (GT / 2); e += 256) {
+        for (int e = tid; e < GKB * (GT / 2); e += GTHR) {
           const int r = e / (GT / 2), x = (e % (GT / 2)) * 2;
           const bool rok = r0 + r < r_end;
           cp_async_16(a + r * GP0 + x, A + (r0 + r) * N + i0 + x, rok && (i0 + x < N));
           cp_async_16(b + r * GP0 + x, A + (r0 + r) * N + j0 + x, rok && (j0 + x < N));
         }
       } else {
-        for (int e = tid; e < GKB * GT; e += 256) {
+        for (int e = tid; e < GKB * GT; e += GTHR) {
           const int r = e / GT, x = e % GT;
           const bool rok = r0 + r < r_end;
           cp_async_8(a + r * GP0 + x, A + (r0 + r) * N + i0 + x, rok && (i0 + x < N));
@@ -105,14 +116,14 @@ gram_dmma_kernel(const double* __restrict__ A, const long M, const long N, const
       }
     } else {
       if (VEC) {
-        for (int e = tid; e < GT * (GKB / 2); e += 256) {
+        for (int e = tid; e < GT * (GKB / 2); e += GTHR) {
           const int t = e / (GKB / 2), r = (e % (GKB / 2)) * 2;
           const bool rok = r0 + r < r_end;  // M even and r0 even under VEC, so pairs never straddle
           cp_async_16(a + t * GP1 + r, A + (i0 + t) * M + r0 + r, rok && (i0 + t < N));
           cp_async_16(b + t * GP1 + r, A + (j0 + t) * M + r0 + r, rok && (j0 + t < N));
         }
       } else {
-        for (int e = tid; e < GT * GKB; e += 256) {
+        for (int e = tid; e < GT * GKB; e += GTHR) {
           const int t = e / GKB, r = e % GKB;
           const bool rok = r0 + r < r_end;
           cp_async_8(a + t * GP1 + r, A + (i0 + t) * M + r0 + r, rok && (i0 + t < N));
@@ -126,9 +137,9 @@ gram_dmma_kernel(const double* __restrict__ A, const long M, const long N, const
     }
   };
 
-  double acc[8][4][2];
+  double acc[GMT][4][2];
 #pragma unroll
-  for (int a = 0; a < 8; ++a)
+  for (int a = 0; a < GMT; ++a)
 #pragma unroll
     for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
 
@@ -146,10 +157,10 @@ gram_dmma_kernel(const double* __restrict__ A, const long M, const long N, const
     const double* ws = sW + (c % GST) * GKB;
 #pragma unroll
     for (int k4 = 0; k4 < GKB; k4 += 4) {
-      double af[8], bf[4];
+      double af[GMT], bf[4];
       const int r = k4 + lr;
 #pragma unroll
-      for (int mt = 0; mt < 8; ++mt)
+      for (int mt = 0; mt < GMT; ++mt)
         af[mt] = (LAYOUT == 0) ? a[r * GP0 + wm + mt * 8 + lc] : a[(wm + mt * 8 + lc) * GP1 + r];
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) {
@@ -157,7 +168,7 @@ gram_dmma_kernel(const double* __restrict__ A, const long M, const long N, const
         if (WEIGHT) bf[nt] *= ws[r];
       }
 #pragma unroll
-      for (int mt = 0; mt < 8; ++mt)
+      for (int mt = 0; mt < GMT; ++mt)
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
     }
@@ -167,7 +178,7 @@ gram_dmma_kernel(const double* __restrict__ A, const long M, const long N, const
   // partial tile -> workspace [split][tile][128][128]
   double* Wt = W + ((long)blockIdx.y * gridDim.x + blockIdx.x) * (GT * GT);
 #pragma unroll
-  for (int mt = 0; mt < 8; ++mt)
+  for (int mt = 0; mt < GMT; ++mt)
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) {
       const int row = wm + mt * 8 + lc, col = wn + nt * 8 + 2 * lr;
@@ -238,7 +249,7 @@ int launch_gram(const double* A, long M, long N, int layout, const double* w, lo
   do {                                                                                                       \
     auto k = gram_dmma_kernel<L, V, WT>;                                                                     \
     PODSDF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GramSmem<L>::BYTES)); \
-    k<<<grid, 256, GramSmem<L>::BYTES, st>>>(A, M, N, w, P, W, side, rows_per_split);                        \
+    k<<<grid, GTHR, GramSmem<L>::BYTES, st>>>(A, M, N, w, P, W, side, rows_per_split);                       \
   } while (0)
   if (layout == 0) {
     if (vec) { if (w) LAUNCH(0, true, true); else LAUNCH(0, true, false); }
