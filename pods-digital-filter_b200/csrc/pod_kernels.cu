@@ -15,6 +15,7 @@
 #include "pod_kernels.cuh"
 
 #include <algorithm>
+#include <type_traits>
 
 namespace podsdf {
 
@@ -355,52 +356,68 @@ project_dmma_kernel(const double* __restrict__ A, const long M, const long N, co
     }
   };
 
-  double acc[2][NTL][2];
+  // The number of live 8-mode column tiles is CTA-uniform but not a compile-time constant, and predicating the MMAs on it
+  // costs the tensor pipe a slot for every predicated-off DMMA (nm = 100: 16 issued for 13 executed per row tile -- the
+  // pipe was 85 % busy at 66 % of its useful peak, ncu).  So the whole loop is instantiated per count.
+  auto run = [&](auto tag) {
+    constexpr int NV = decltype(tag)::value;
+    double acc[2][NV][2];
 #pragma unroll
-  for (int a = 0; a < 2; ++a)
+    for (int a = 0; a < 2; ++a)
 #pragma unroll
-    for (int b = 0; b < NTL; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+      for (int b = 0; b < NV; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
 
-  for (int s = 0; s < PST - 1; ++s) {
-    if (s < nchunks) load_stage(s, s);
-    cp_async_commit();
-  }
-  for (int c = 0; c < nchunks; ++c) {
-    cp_async_wait<PST - 2>();
-    __syncthreads();
-    if (c + PST - 1 < nchunks) load_stage(c + PST - 1, (c + PST - 1) % PST);
-    cp_async_commit();
-    const double* a = sA + (c % PST) * ATILE;
-    const double* tt = sT + (c % PST) * TTILE;
-#pragma unroll
-    for (int k4 = 0; k4 < PKB; k4 += 4) {
-      double af[2], bf[NTL];
-      const int t = k4 + lr;
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
-        af[mt] = (LAYOUT == 0) ? a[(wr + mt * 8 + lc) * PPA0 + t] : a[t * PPA1 + wr + mt * 8 + lc];
-#pragma unroll
-      for (int nt = 0; nt < NTL; ++nt)
-        if (nt < ntl) bf[nt] = tt[t * PPT + nt * 8 + lc];
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-        for (int nt = 0; nt < NTL; ++nt)
-          if (nt < ntl) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
+    for (int s = 0; s < PST - 1; ++s) {
+      if (s < nchunks) load_stage(s, s);
+      cp_async_commit();
     }
-  }
-  cp_async_wait<0>();
+    for (int c = 0; c < nchunks; ++c) {
+      cp_async_wait<PST - 2>();
+      __syncthreads();
+      if (c + PST - 1 < nchunks) load_stage(c + PST - 1, (c + PST - 1) % PST);
+      cp_async_commit();
+      const double* a = sA + (c % PST) * ATILE;
+      const double* tt = sT + (c % PST) * TTILE;
 #pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
+      for (int k4 = 0; k4 < PKB; k4 += 4) {
+        double af[2], bf[NV];
+        const int t = k4 + lr;
 #pragma unroll
-    for (int nt = 0; nt < NTL; ++nt) {
-      const long row = row0 + wr + mt * 8 + lc;
-      const int m = m0 + nt * 8 + 2 * lr;
-      if (row < M) {
-        if (m < nm) Phi[row * nm + m] = acc[mt][nt][0] * dinv[m] * scale;
-        if (m + 1 < nm) Phi[row * nm + m + 1] = acc[mt][nt][1] * dinv[m + 1] * scale;
+        for (int mt = 0; mt < 2; ++mt)
+          af[mt] = (LAYOUT == 0) ? a[(wr + mt * 8 + lc) * PPA0 + t] : a[t * PPA1 + wr + mt * 8 + lc];
+#pragma unroll
+        for (int nt = 0; nt < NV; ++nt) bf[nt] = tt[t * PPT + nt * 8 + lc];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < NV; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
       }
     }
+    cp_async_wait<0>();
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < NV; ++nt) {
+        const long row = row0 + wr + mt * 8 + lc;
+        const int m = m0 + nt * 8 + 2 * lr;
+        if (row < M) {
+          if (m < nm) Phi[row * nm + m] = acc[mt][nt][0] * dinv[m] * scale;
+          if (m + 1 < nm) Phi[row * nm + m + 1] = acc[mt][nt][1] * dinv[m + 1] * scale;
+        }
+      }
+  };
+#define PODSDF_PROJ_CASE(n) \
+  case n:                   \
+    if constexpr (n <= NTL) run(std::integral_constant<int, n>{}); \
+    break;
+  switch (ntl) {
+    PODSDF_PROJ_CASE(1) PODSDF_PROJ_CASE(2) PODSDF_PROJ_CASE(3) PODSDF_PROJ_CASE(4)
+    PODSDF_PROJ_CASE(5) PODSDF_PROJ_CASE(6) PODSDF_PROJ_CASE(7) PODSDF_PROJ_CASE(8)
+    PODSDF_PROJ_CASE(9) PODSDF_PROJ_CASE(10) PODSDF_PROJ_CASE(11) PODSDF_PROJ_CASE(12)
+    PODSDF_PROJ_CASE(13) PODSDF_PROJ_CASE(14) PODSDF_PROJ_CASE(15) PODSDF_PROJ_CASE(16)
+    default: break;
+  }
+#undef PODSDF_PROJ_CASE
 }
 
 template <int LAYOUT, int PM>
