@@ -85,9 +85,8 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned
                "l"(src), "r"(bytes), "r"(mbar) : "memory");
 }
 
-// ---- grid barrier for the cooperative kernels (all CTAs co-resident: launched with cudaLaunchCooperativeKernel).
-// Monotone counter: barrier number `phase` (1, 2, ...) is passed when the counter reaches phase * gridDim.x.
-// Spins are bounded: a lost CTA raises the error flag instead of hanging the GPU.
+// ---- acquire / release accesses of the progress counters and the error flag (the cooperative kernels spin on them; all
+// their CTAs are co-resident, and every spin is bounded: a lost CTA raises the error flag instead of hanging the GPU)
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
   unsigned v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
@@ -95,26 +94,6 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
 }
 __device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ bool grid_barrier(unsigned* counter, unsigned* err, unsigned phase) {
-  __shared__ int s_ok;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(counter, 1u);
-    const unsigned target = phase * gridDim.x;
-    int ok = 1;
-    unsigned spins = 0;
-    while (ld_acquire_u32(counter) < target) {
-      if (++spins > (1u << 24)) {
-        if ((spins & 0xFFFFu) == 0 && ld_acquire_u32(err) != 0) { ok = 0; break; }
-        if (spins > (1u << 28)) { atomicExch(err, 1u); ok = 0; break; }
-      }
-    }
-    s_ok = ok;
-  }
-  __syncthreads();
-  return s_ok != 0;
 }
 
 // ---- flagged 16-byte mailbox entries {lo, flag, hi, flag}: value and "it is there" travel in ONE store and ONE load,
@@ -819,7 +798,6 @@ sbr_extract_band_kernel(const double* __restrict__ A, const long N, double* __re
 //   task (i, k) starts when sweep i-1 has finished task k+1: prog[i-1] >= k+2 (progress counters in global memory,
 //   release / acquire).  Reflectors go to V2[i][row] / TAU2[i][k] for the back-transformation.
 // ------------------------------------------------------------------------------------------------
-constexpr int TP = B + 1;   // tile pitch
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -852,278 +830,11 @@ __device__ __forceinline__ void cpa16_cg(void* smem_dst, const void* gsrc, bool 
 // The blocks of a task are worked on in the band layout itself: sB[c][d] = B[j0 + c + d][j0 + c] is a copy of
 // band columns j0 .. j0+L-1 (64 doubles each, fetched with ONE batch of 16-byte L2 copies: a task costs one
 // memory round trip in, one out).  D(r, c) = sB[c][r - c] (r >= c, mirrored otherwise), E(a, c) = sB[c][B - c + a].
-__global__ void __launch_bounds__(32)
-sbr_chase_kernel(double* __restrict__ Bb, const long N, double* __restrict__ V2, double* __restrict__ TAU2,
-                 const long ntask_max, unsigned* __restrict__ bar) {
-  __shared__ __align__(16) double sB[B][LDB];
-  __shared__ double sv[B], sq[B];
-  const int lane = threadIdx.x;
-  unsigned* err = bar + 1;
-  unsigned* prog = bar + 2;
-  const long nsweep = N - 2;
-#ifdef PODSDF_CHASE_PROFILE
-  long long pc[5] = {0, 0, 0, 0, 0}, ptasks = 0;
-#define PCLK(n) { const long long t_ = clock64(); pc[n] += t_ - plast; plast = t_; }
-  long long plast = clock64();
-#else
-#define PCLK(n)
-#endif
-  for (long i = blockIdx.x; i < nsweep; i += gridDim.x) {
-    const int nt = (int)((N - 1 - i + B - 1) / B);
-    double v = 0.0, tau = 0.0;                       // reflector of the current task (lane = row inside J_k)
-    for (int k = 0; k < nt; ++k) {
-      PCLK(4)
-      // ---- dependency: sweep i-1 has finished task k+1
-      if (i > 0) {
-        int ok = 1;
-        if (lane == 0) {
-          const unsigned need = (unsigned)(k + 2);
-          unsigned spins = 0;
-          while (ld_acquire_u32(prog + i - 1) < need) {
-            if (++spins > (1u << 22)) {
-              if ((spins & 0xFFFFu) == 0 && ld_acquire_u32(err) != 0) { ok = 0; break; }
-              if (spins > (1u << 27)) { atomicExch(err, 2u); ok = 0; break; }
-            }
-          }
-        }
-        ok = __shfl_sync(0xffffffffu, ok, 0);
-        if (!ok) return;
-      }
-      PCLK(0)
-      const long j0 = i + 1 + (long)k * B;
-      const int L = (int)min((long)B, N - j0);
-      const int L2 = (int)max(0L, min((long)B, N - j0 - B));
-      // ---- fetch band columns j0 .. j0+L-1 (zero-filled beyond)
-#pragma unroll
-      for (int c = 0; c < B; ++c) cpa16_cg(&sB[c][2 * lane], Bb + (j0 + c) * LDB + 2 * lane, c < L);
-      cpa_commit();
-      if (k == 0) {                                  // reflector of column i (overlaps the copies)
-        const double x = (lane < L) ? __ldcg(Bb + i * LDB + 1 + lane) : 0.0;
-        double beta;
-        warp_house(x, lane, v, tau, beta);
-        if (lane < L) __stcg(Bb + i * LDB + 1 + lane, lane == 0 ? beta : 0.0);
-      }
-      if (lane >= L) v = 0.0;
-      if (lane < L) V2[i * N + j0 + lane] = v;
-      if (lane == 0) TAU2[i * ntask_max + k] = tau;
-      sv[lane] = v;
-      cpa_wait<0>();
-      __syncwarp();
-      PCLK(1)
-      // ---- D <- H D H, H = I - tau v v^T: p = tau D v, q = p - (tau/2)(p^T v) v, D -= v q^T + q v^T
-      {
-        double pp[4] = {0.0, 0.0, 0.0, 0.0};        // four independent chains: one warp has no other latency cover
-#pragma unroll
-        for (int c = 0; c < B; ++c) {
-          const int idx = (c <= lane) ? c * LDB + lane - c : lane * LDB + c - lane;
-          pp[c & 3] = fma((&sB[0][0])[idx], sv[c], pp[c & 3]);
-        }
-        const double pl = tau * ((pp[0] + pp[1]) + (pp[2] + pp[3]));
-        const double kk = 0.5 * tau * warp_sum(pl * v);
-        const double ql = fma(-kk, v, pl);
-        sq[lane] = ql;
-        __syncwarp();
-#pragma unroll
-        for (int c = 0; c < B; ++c)
-          if (c <= lane) sB[c][lane - c] -= fma(v, sq[c], ql * sv[c]);     // lower part: every entry once
-        __syncwarp();
-      }
-      double v2 = 0.0, tau2 = 0.0;
-      if (L2 > 0) {
-        // ---- E <- E H (lane = row a of E)
-        double yy[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-        for (int c = 0; c < B; ++c) yy[c & 3] = fma(sB[c][B - c + lane], sv[c], yy[c & 3]);
-        const double yl = tau * ((yy[0] + yy[1]) + (yy[2] + yy[3]));
-#pragma unroll
-        for (int c = 0; c < B; ++c) sB[c][B - c + lane] = fma(-yl, sv[c], sB[c][B - c + lane]);
-        __syncwarp();
-        double beta2;
-        warp_house(lane < L2 ? sB[0][B + lane] : 0.0, lane, v2, tau2, beta2);
-        if (lane >= L2) v2 = 0.0;
-        sq[lane] = v2;
-        __syncwarp();
-        // ---- E <- H2 E: z_c = tau2 v2^T E[:, c] (lane = column c), then lane = row a again
-        double zz[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-        for (int a2 = 0; a2 < B; ++a2) zz[a2 & 3] = fma(sq[a2], sB[lane][B - lane + a2], zz[a2 & 3]);
-        const double zl = tau2 * ((zz[0] + zz[1]) + (zz[2] + zz[3]));
-        __syncwarp();
-        sq[lane] = zl;
-        __syncwarp();
-#pragma unroll
-        for (int c = 0; c < B; ++c) sB[c][B - c + lane] = fma(-v2, sq[c], sB[c][B - c + lane]);
-        sB[0][B + lane] = (lane == 0) ? beta2 : 0.0;       // exactly (beta, 0, ..., 0)
-        __syncwarp();
-      }
-      PCLK(2)
-      // ---- write back the entries of this task: column c, d in [0, len_c)
-#pragma unroll
-      for (int c = 0; c < B; ++c) {
-        const int len = (c < L) ? ((L2 > 0) ? B - c + L2 : L - c) : 0;
-        const int d0 = 2 * lane;
-        double* dst = Bb + (j0 + c) * LDB + d0;
-        if (d0 + 1 < len) __stcg(reinterpret_cast<double2*>(dst), make_double2(sB[c][d0], sB[c][d0 + 1]));
-        else if (d0 < len) __stcg(dst, sB[c][d0]);
-      }
-      v = v2;
-      tau = tau2;
-      // ---- publish progress.  The warp barrier orders every lane's stores before lane 0's release store
-      // (cumulativity), so one fence -- the one inside st.release.gpu -- is enough: an explicit __threadfence()
-      // here cost another 1.5 us per task (profiles/r02_sbr_profile.md)
-      __syncwarp();
-      if (lane == 0) st_release_u32(prog + i, (k + 1 == nt) ? 0x7fffffffu : (unsigned)(k + 1));
-      __syncwarp();
-      PCLK(3)
-#ifdef PODSDF_CHASE_PROFILE
-      ++ptasks;
-#endif
-    }
-  }
-#ifdef PODSDF_CHASE_PROFILE
-  if (lane == 0 && (blockIdx.x == 0 || blockIdx.x == 7 || blockIdx.x == gridDim.x - 1))
-    printf("chase cta %d: tasks %lld, cycles per task: wait %lld, load %lld, compute %lld, store+fence+publish %lld, loop %lld\n",
-           blockIdx.x, ptasks, pc[0] / ptasks, pc[1] / ptasks, pc[2] / ptasks, pc[3] / ptasks, pc[4] / ptasks);
-#endif
-}
-
 // ------------------------------------------------------------------------------------------------
-// Stage 2, two warps per task.  A lone warp runs the ~2000 instructions of a task at IPC ~0.4, and the task time
-// IS the critical path (profiles/r02_sbr_profile.md: load 0.5 us, compute 2.7 us, store + release 3 us per task).
-// D <- H D H and the E chain (E <- E H, new reflector, E <- H' E) only share the incoming reflector and touch
-// disjoint band entries, so warp 1 takes D and warp 0 (the owner of the reflector chain) takes E; each warp
-// copies in half of the columns and writes back its own entries.
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(64)
-sbr_chase2_kernel(double* __restrict__ Bb, const long N, double* __restrict__ V2, double* __restrict__ TAU2,
-                  const long ntask_max, unsigned* __restrict__ bar) {
-  __shared__ __align__(16) double sB[B][LDB];
-  __shared__ double sv[B], sqE[B], sqD[B];
-  __shared__ double s_tau;
-  __shared__ int s_ok;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  unsigned* err = bar + 1;
-  unsigned* prog = bar + 2;
-  const long nsweep = N - 2;
-  for (long i = blockIdx.x; i < nsweep; i += gridDim.x) {
-    const int nt = (int)((N - 1 - i + B - 1) / B);
-    double v = 0.0, tau = 0.0;                       // warp 0: reflector of the current task (lane = row inside J_k)
-    for (int k = 0; k < nt; ++k) {
-      // ---- dependency: sweep i-1 has finished task k+1
-      if (threadIdx.x == 0) {
-        int ok = 1;
-        if (i > 0) {
-          const unsigned need = (unsigned)(k + 2);
-          unsigned spins = 0;
-          while (ld_acquire_u32(prog + i - 1) < need) {
-            if (++spins > (1u << 22)) {
-              if ((spins & 0xFFFFu) == 0 && ld_acquire_u32(err) != 0) { ok = 0; break; }
-              if (spins > (1u << 27)) { atomicExch(err, 2u); ok = 0; break; }
-            }
-          }
-        }
-        s_ok = ok;
-      }
-      __syncthreads();
-      if (!s_ok) return;
-      const long j0 = i + 1 + (long)k * B;
-      const int L = (int)min((long)B, N - j0);
-      const int L2 = (int)max(0L, min((long)B, N - j0 - B));
-      // ---- fetch band columns j0 .. j0+L-1 (zero-filled beyond), half per warp
-#pragma unroll
-      for (int cc = 0; cc < B / 2; ++cc) {
-        const int c = warp * (B / 2) + cc;
-        cpa16_cg(&sB[c][2 * lane], Bb + (j0 + c) * LDB + 2 * lane, c < L);
-      }
-      cpa_commit();
-      if (warp == 0) {
-        if (k == 0) {                                // reflector of column i (overlaps the copies)
-          const double x = (lane < L) ? __ldcg(Bb + i * LDB + 1 + lane) : 0.0;
-          double beta;
-          warp_house(x, lane, v, tau, beta);
-          if (lane < L) __stcg(Bb + i * LDB + 1 + lane, lane == 0 ? beta : 0.0);
-        }
-        if (lane >= L) v = 0.0;
-        if (lane < L) V2[i * N + j0 + lane] = v;
-        if (lane == 0) {
-          TAU2[i * ntask_max + k] = tau;
-          s_tau = tau;
-        }
-        sv[lane] = v;
-      }
-      cpa_wait<0>();
-      __syncthreads();
-      if (warp == 1) {
-        // ---- D <- H D H, H = I - tau v v^T: p = tau D v, q = p - (tau/2)(p^T v) v, D -= v q^T + q v^T
-        const double tD = s_tau, vD = sv[lane];
-        double pp[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-        for (int c = 0; c < B; ++c) {
-          const int idx = (c <= lane) ? c * LDB + lane - c : lane * LDB + c - lane;
-          pp[c & 3] = fma((&sB[0][0])[idx], sv[c], pp[c & 3]);
-        }
-        const double pl = tD * ((pp[0] + pp[1]) + (pp[2] + pp[3]));
-        const double kk = 0.5 * tD * warp_sum(pl * vD);
-        const double ql = fma(-kk, vD, pl);
-        sqD[lane] = ql;
-        __syncwarp();
-#pragma unroll
-        for (int c = 0; c < B; ++c)
-          if (c <= lane) sB[c][lane - c] -= fma(vD, sqD[c], ql * sv[c]);     // lower part: every entry once
-        __syncwarp();
-#pragma unroll
-        for (int c = 0; c < B; ++c) {                // write back column c, d in [0, L - c)
-          const int len = L - c, d0 = 2 * lane;
-          double* dst = Bb + (j0 + c) * LDB + d0;
-          if (d0 + 1 < len) __stcg(reinterpret_cast<double2*>(dst), make_double2(sB[c][d0], sB[c][d0 + 1]));
-          else if (d0 < len) __stcg(dst, sB[c][d0]);
-        }
-      } else {
-        double v2 = 0.0, tau2 = 0.0;
-        if (L2 > 0) {
-          // ---- E <- E H (lane = row a of E)
-          double yy[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-          for (int c = 0; c < B; ++c) yy[c & 3] = fma(sB[c][B - c + lane], sv[c], yy[c & 3]);
-          const double yl = tau * ((yy[0] + yy[1]) + (yy[2] + yy[3]));
-#pragma unroll
-          for (int c = 0; c < B; ++c) sB[c][B - c + lane] = fma(-yl, sv[c], sB[c][B - c + lane]);
-          __syncwarp();
-          double beta2;
-          warp_house(lane < L2 ? sB[0][B + lane] : 0.0, lane, v2, tau2, beta2);
-          if (lane >= L2) v2 = 0.0;
-          sqE[lane] = v2;
-          __syncwarp();
-          // ---- E <- H2 E: z_c = tau2 v2^T E[:, c] (lane = column c), then lane = row a again
-          double zz[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-          for (int a2 = 0; a2 < B; ++a2) zz[a2 & 3] = fma(sqE[a2], sB[lane][B - lane + a2], zz[a2 & 3]);
-          const double zl = tau2 * ((zz[0] + zz[1]) + (zz[2] + zz[3]));
-          __syncwarp();
-          sqE[lane] = zl;
-          __syncwarp();
-#pragma unroll
-          for (int c = 0; c < B; ++c) sB[c][B - c + lane] = fma(-v2, sqE[c], sB[c][B - c + lane]);
-          sB[0][B + lane] = (lane == 0) ? beta2 : 0.0;       // exactly (beta, 0, ..., 0)
-          __syncwarp();
-#pragma unroll
-          for (int c = 0; c < B; ++c)                // write back column c, d = B - c + a
-            if (c < L && lane < L2) __stcg(Bb + (j0 + c) * LDB + B - c + lane, sB[c][B - c + lane]);
-        }
-        v = v2;
-        tau = tau2;
-      }
-      // ---- publish progress: the CTA barrier orders both warps' stores before thread 0's release store
-      __syncthreads();
-      if (threadIdx.x == 0) st_release_u32(prog + i, (k + 1 == nt) ? 0x7fffffffu : (unsigned)(k + 1));
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Stage 2, four warps per task.  With two warps the task's own dependent arithmetic (~2.4 us) is what the 2 N-long
-// chain is made of (hand-offs through shared memory or DSMEM instead of L2 bought 6 %), so the
-// blocks are split once more by columns: warps 0 / 1 take columns 0-15 / 16-31 of the E-block chain, warps 2 / 3
+// Stage 2, four warps per task (the first versions ran a task on one warp -- IPC ~0.4 on ~2000 instructions, 139 ms --
+// and on two, D block / E chain, 105 ms; both are in the history of this file).  With two warps the task's own dependent
+// arithmetic (~2.4 us) is what the 2 N-long chain is made of (hand-offs through shared memory or DSMEM instead of L2
+// bought 6 %), so the blocks are split once more by columns: warps 0 / 1 take columns 0-15 / 16-31 of the E-block chain, warps 2 / 3
 // those of the D block; partial matrix-vector products meet in shared memory behind 64-thread named barriers.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void pair_barrier(const int id) {
@@ -2205,19 +1916,16 @@ static int sbr_stage2(long N, const SbrWs& w, double* d, double* e, cudaStream_t
     unsigned* bar = w.bar;
     uint4* mail2 = reinterpret_cast<uint4*>(w.mail2);
     void* args[] = {&Bb, &Narg, &V2, &TAU2, &ntm, &bar, &mail2};
-    // PODSDF_CHASE (A/B only): 1 = one warp per task, 2 = two warps, 4 = four warps with every hand-off through the
-    // band, 5 = four warps, the critical column through mailboxes, 7 = three task groups per sweep (67 ms: twelve
+    // PODSDF_CHASE (A/B only): 4 = four warps per task with every hand-off through the band, 5 = four warps, the critical column through mailboxes, 7 = three task groups per sweep (67 ms: twelve
     // latency-bound warps on an SM slow each other down); default: two task groups (47 ms)
     const char* variant = getenv("PODSDF_CHASE");
     const int var = variant ? atoi(variant) : 0;
-    const void* kern = (var == 1) ? (const void*)sbr_chase_kernel
-                     : (var == 2) ? (const void*)sbr_chase2_kernel
-                     : (var == 4) ? (const void*)sbr_chase4_kernel
+    const void* kern = (var == 4) ? (const void*)sbr_chase4_kernel
                      : (var == 5) ? (const void*)sbr_chase5_kernel
                      : (var == 7) ? (const void*)sbr_chase6_kernel<3> : (const void*)sbr_chase6_kernel<2>;
     const int groups = (var == 7) ? 3 : 2;
-    const int threads = (var == 1) ? 32 : ((var == 2) ? 64 : ((var == 4 || var == 5) ? 128 : 128 * groups));
-    const size_t dyn = (var == 1 || var == 2 || var == 4 || var == 5) ? 0 : (size_t)groups * B * LDB * sizeof(double);
+    const int threads = (var == 4 || var == 5) ? 128 : 128 * groups;
+    const size_t dyn = (var == 4 || var == 5) ? 0 : (size_t)groups * B * LDB * sizeof(double);
     if (dyn > 0) PODSDF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
     int per_sm = 1;
     PODSDF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, dyn));
