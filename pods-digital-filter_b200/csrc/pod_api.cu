@@ -203,12 +203,15 @@ int eig_top_inplace(int device, double* C_dev, long N, int nm, double* lambda_de
     PODSDF_TRY(launch_tridiag_prepare(d, e, N, e2, bounds, st));
     SideStream& side = side_stream(device);
     if (!side.ok) return fail(PODSDF_ERR_CUDA, "side stream creation failed");
-    PODSDF_CUDA(cudaEventRecord(side.fork, st));
-    PODSDF_CUDA(cudaStreamWaitEvent(side.s, side.fork, 0));
-    rc = launch_tridiag_bisect(d, e2, bounds, N, first, lambda_dev, side.s);
-    if (!rc) {
-      PODSDF_CUDA(cudaEventRecord(side.join, side.s));
-      side_pending = true;
+    static const int side_mode = getenv("PODSDF_EIG_SIDE") ? atoi(getenv("PODSDF_EIG_SIDE")) : 1;   // A/B: 0 = after the vectors
+    if (side_mode == 1) {
+      PODSDF_CUDA(cudaEventRecord(side.fork, st));
+      PODSDF_CUDA(cudaStreamWaitEvent(side.s, side.fork, 0));
+      rc = launch_tridiag_bisect(d, e2, bounds, N, first, lambda_dev, side.s);
+      if (!rc) {
+        PODSDF_CUDA(cudaEventRecord(side.join, side.s));
+        side_pending = true;
+      }
     }
     auto join_side = [&]() {            // every exit below waits for the side stream: it shares the scratch
       if (side_pending) cudaStreamWaitEvent(st, side.join, 0);
@@ -257,6 +260,7 @@ int eig_top_inplace(int device, double* C_dev, long N, int nm, double* lambda_de
       for (int j = 0; j < nm && fast_ok; ++j)
         if (!(hres[j] < 1.0e-13)) fast_ok = false;
     }
+    if (side_mode != 1 && !rc) rc = launch_tridiag_bisect(d, e2, bounds, N, first, lambda_dev, st);
     join_side();                                             // all of lambda is written
     if (!fast_ok) PODSDF_CUDA(cudaMemcpyAsync(C_dev, Ccopy, sizeof(double) * nn, cudaMemcpyDeviceToDevice, st));
   }
