@@ -1932,8 +1932,13 @@ static int sbr_stage2(long N, const SbrWs& w, double* d, double* e, cudaStream_t
     // mailbox flags of an earlier solve must not look like this one's (flag = sweep + 1 > 0)
     PODSDF_CUDA(cudaMemsetAsync(w.mail2, 0, sizeof(double) * 4 * (size_t)w.ntask_max * LDB, st));
     long G = (long)sms * (per_sm < 4 ? per_sm : 4);             // all chains co-resident (cooperative launch checks it)
+    const long G_max = G;
+    // the sweeps advance in step, so the slowest CTA sets the pace: with the two-group kernel an SM that hosts two CTAs
+    // (sixteen latency-bound warps) holds everybody back (N = 10^4: 52 ms with 164 CTAs on 148 SMs, 48 ms with 148)
+    if (var != 4 && var != 5 && G > sms) G = sms;
     const long useful = (N + 2 * B - 1) / (2 * B) + 8;          // sweeps that can be in flight at once
     if (G > useful) G = useful;
+    if (const char* og = getenv("PODSDF_CHASE_G")) G = std::min<long>(G_max, std::max(1, atoi(og)));   // A/B only
     if (G > nsweep) G = nsweep;
     PODSDF_CUDA(cudaLaunchCooperativeKernel(kern, dim3((unsigned)G), dim3(threads), args, dyn, st));
     count_launch();
