@@ -302,14 +302,17 @@ def run_cfg1(args, pkg, torch, dev, local_rank, cpu_too=True):
     ours(1)                                                      # warm-up (workspaces, cuSOLVER handle if route 0)
     torch.cuda.synchronize(dev)
     reps = 5
-    t0 = time.perf_counter()
+    each = []                                                    # (plan creation / destruction allocate and free device
+    t0 = time.perf_counter()                                     #  memory every time: 16 ms to 60 ms per run were seen)
     for r in range(reps):
+        t1 = time.perf_counter()
         o = ours(2 + r)
-    torch.cuda.synchronize(dev)
+        torch.cuda.synchronize(dev)
+        each.append(time.perf_counter() - t1)
     wall = (time.perf_counter() - t0) / reps
     d2h = o["mean"].nbytes + o["Phi"].nbytes + 8 * ns
     out = {"workload": "cfg1 in full: 64x64x3 planes, 1000 steps, nf=10, ln=5, adapt1d + identity rotation, PODFS 20 modes, et=0.9",
-           "ours": {"wall_s": wall, "planes_per_s": ns / wall, "snapshots_per_s": ns / wall, "reps": reps,
+           "ours": {"wall_s": wall, "wall_each_s": each, "planes_per_s": ns / wall, "snapshots_per_s": ns / wall, "reps": reps,
                     "api": "DfPlan + pipeline.df_to_podfs (what digitalfilters.main() runs when not verbose), results on the host",
                     "h2d_bytes": 5 * J * K * 8, "d2h_bytes": int(d2h), "modes_kept": int(len(o["c_count"])),
                     "fourier_coefficients_kept": int(np.sum(o["c_count"]))}}
