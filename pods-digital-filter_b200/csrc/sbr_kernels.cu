@@ -1844,7 +1844,7 @@ static int sbr_stage1(double* A, long N, const SbrWs& w, cudaStream_t st) {
     count_launch(4);
     mark(k, 1, st);
     // 1e: rank-2b update of the lower tiles.  The first tile column (it contains the next panel) goes first; the
-    // next panel's QR -- a latency-bound chain of grid barriers on a few SMs -- then runs on the high-priority
+    // next panel's QR -- a latency-bound chain of 33 exchanges between a few dozen CTAs -- then runs on the high-priority
     // stream beside the rest of the update.
     const int side = (int)((N + UT - 1) / UT - r0 / UT);
     const bool ahead = k + 1 < w.npanel;
@@ -1982,7 +1982,7 @@ int sbr_stage1_only(double* A, long N, double* ws, double* band, cudaStream_t st
   unsigned herr = 0;
   PODSDF_CUDA(cudaMemcpyAsync(&herr, w.bar + 1, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
   PODSDF_CUDA(cudaStreamSynchronize(st));
-  if (herr != 0) return fail(PODSDF_ERR_CUDA, "band reduction: a grid barrier timed out");
+  if (herr != 0) return fail(PODSDF_ERR_CUDA, "band reduction: a wait between the CTAs of the panel QR timed out");
   return 0;
 }
 
