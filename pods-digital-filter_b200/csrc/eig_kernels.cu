@@ -74,10 +74,11 @@ __device__ __forceinline__ int sturm_count(const double* __restrict__ d, const d
 // instead of ~55, four times the threads) serves all the others -- more lanes per eigenvalue there would saturate
 // the SMs with divisions (measured).  Tolerances are dstebz's defaults: relative 2 ulp, absolute ulp * |T|.
 template <int G>
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(1024)
 tridiag_sect_kernel(const double* __restrict__ d, const double* __restrict__ e2, const double* __restrict__ bounds,
                     const long N, const long k_first, const long k_end, double* __restrict__ lam) {
-  const long gid = (blockIdx.x * 64L + threadIdx.x) / G;          // eigenvalue handled by this group of lanes
+  // eigenvalue handled by this group of lanes (grid-stride: the launch may use a few fat CTAs, see launch_tridiag_bisect)
+  for (long gid = ((long)blockIdx.x * blockDim.x + threadIdx.x) / G;; gid += (long)gridDim.x * blockDim.x / G) {
   const long k = k_first + gid;
   const int lane = threadIdx.x & 31;
   const int gl = lane % G;                                         // position inside the group
@@ -112,6 +113,7 @@ tridiag_sect_kernel(const double* __restrict__ d, const double* __restrict__ e2,
     hi = nhi;
   }
   if (gl == 0) lam[k] = 0.5 * (lo + hi);
+  }
 }
 
 // Inverse iteration for the nm largest eigenvalues.  CTA j owns vector j (eigenvalue lam[N-1-j]): LU of T - lambda I
@@ -365,10 +367,24 @@ int launch_tridiag_prepare(const double* d, const double* e, long N, double* e2,
 }
 
 int launch_tridiag_bisect(const double* d, const double* e2, const double* bounds, long N, long k_end, double* lam,
-                          cudaStream_t st) {
+                          cudaStream_t st, int reserve_sms) {
   if (k_end <= 0) return 0;
   constexpr int G = 4;
-  tridiag_sect_kernel<G><<<(unsigned)ceil_div(k_end * G, 64L), 64, 0, st>>>(d, e2, bounds, N, 0, k_end, lam);
+  // This kernel runs on a side stream beside the inverse iteration and the back-transformation of the leading vectors,
+  // whose CTAs need whole SMs (512 threads x 128 registers).  Its own CTAs live for the whole ~20 ms (a chain of
+  // dependent divisions), so small CTAs spread over every SM keep those kernels waiting for registers (measured: 11 ms
+  // of the 22 ms it should hide).  With `reserve_sms` > 0 it is packed into a few 1024-thread CTAs -- at most one per SM
+  // that the others do not need -- and strides over its eigenvalues.
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long lanes = k_end * G;
+  if (reserve_sms > 0 && sms - reserve_sms >= 16 && lanes > 64L * sms) {
+    const long fat = std::min<long>(sms - reserve_sms, ceil_div(lanes, 1024L));
+    tridiag_sect_kernel<G><<<(unsigned)fat, 1024, 0, st>>>(d, e2, bounds, N, 0, k_end, lam);
+  } else {
+    tridiag_sect_kernel<G><<<(unsigned)ceil_div(lanes, 64L), 64, 0, st>>>(d, e2, bounds, N, 0, k_end, lam);
+  }
   count_launch();
   PODSDF_CUDA(cudaGetLastError());
   return 0;

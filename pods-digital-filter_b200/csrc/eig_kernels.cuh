@@ -9,7 +9,7 @@ namespace podsdf {
 // indices [k_first, N), one warp each (33-section: a fifth of the serial Sturm sweeps of a plain bisection).
 int launch_tridiag_prepare(const double* d, const double* e, long N, double* e2, double* bounds, cudaStream_t st);
 int launch_tridiag_bisect(const double* d, const double* e2, const double* bounds, long N, long k_end, double* lam,
-                          cudaStream_t st);
+                          cudaStream_t st, int reserve_sms = 0);
 int launch_tridiag_multisect(const double* d, const double* e2, const double* bounds, long N, long k_first, double* lam,
                              cudaStream_t st);
 size_t tridiag_invit_workspace_doubles(long N, int nm);

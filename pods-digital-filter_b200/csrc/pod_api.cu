@@ -204,10 +204,11 @@ int eig_top_inplace(int device, double* C_dev, long N, int nm, double* lambda_de
     SideStream& side = side_stream(device);
     if (!side.ok) return fail(PODSDF_ERR_CUDA, "side stream creation failed");
     static const int side_mode = getenv("PODSDF_EIG_SIDE") ? atoi(getenv("PODSDF_EIG_SIDE")) : 1;   // A/B: 0 = after the vectors
+    static const bool fat_side = !(getenv("PODSDF_EIG_SIDE_FAT") && atoi(getenv("PODSDF_EIG_SIDE_FAT")) == 0);   // A/B
     if (side_mode == 1) {
       PODSDF_CUDA(cudaEventRecord(side.fork, st));
       PODSDF_CUDA(cudaStreamWaitEvent(side.s, side.fork, 0));
-      rc = launch_tridiag_bisect(d, e2, bounds, N, first, lambda_dev, side.s);
+      rc = launch_tridiag_bisect(d, e2, bounds, N, first, lambda_dev, side.s, fat_side ? nm : 0);
       if (!rc) {
         PODSDF_CUDA(cudaEventRecord(side.join, side.s));
         side_pending = true;
