@@ -12,6 +12,8 @@
 
 #include "eig_kernels.cuh"
 
+#include <cstdlib>
+
 namespace podsdf {
 
 // bounds[0] = gl, [1] = gu (Gershgorin interval, widened as dstebz does), [2] = pivmin, [3] = |T| (max-norm bound)
@@ -114,6 +116,60 @@ tridiag_sect_kernel(const double* __restrict__ d, const double* __restrict__ e2,
   }
   if (gl == 0) lam[k] = 0.5 * (lo + hi);
   }
+}
+
+// The leading eigenvalues, one CTA of BS_THREADS lanes per eigenvalue: every Sturm sweep shrinks the bracket
+// (BS_THREADS + 1)-fold, so seven sweeps do what eleven did with one warp per eigenvalue.  A sweep is a chain of N
+// dependent divisions that a warp issues at IPC ~0.25 whatever it does (four chains per lane took 2.3x longer per
+// sweep), only nm + 1 eigenvalues are wanted before the inverse iteration can start, and the SMs the side-stream
+// bisection leaves alone are idle: the parallelism goes into more points per sweep.  256 lanes: two CTAs fit an SM, so
+// nm + 1 = 101 CTAs still run in one wave on the 100 SMs that bisection does not use.
+constexpr int BS_THREADS = 256;
+__global__ void __launch_bounds__(BS_THREADS)
+tridiag_sect_block_kernel(const double* __restrict__ d, const double* __restrict__ e2, const double* __restrict__ bounds,
+                          const long N, const long k_first, const long k_end, double* __restrict__ lam) {
+  __shared__ unsigned s_above[BS_THREADS / 32];
+  __shared__ int s_any;
+  const long k = k_first + blockIdx.x;
+  if (k >= k_end) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double lo = bounds[0], hi = bounds[1];
+  const double pivmin = bounds[2], tnorm = bounds[3];
+  for (int it = 0; it < 64; ++it) {
+    const double tol = fmax(2.0 * DBL_EPSILON * fmax(fabs(lo), fabs(hi)), DBL_EPSILON * tnorm) + 2.0 * pivmin;
+    if (hi - lo <= tol) break;                                     // (uniform: lo, hi are the same in every thread)
+    const double w = (hi - lo) / (double)(BS_THREADS + 1);
+    const double x = lo + (double)(tid + 1) * w;
+    const bool inside = (x > lo) && (x < hi);                      // false once the points collapse onto the ends
+    if (tid == 0) s_any = 0;
+    __syncthreads();
+    if (inside) s_any = 1;
+    __syncthreads();
+    if (!s_any) break;
+    const int c = inside ? sturm_count(d, e2, N, x, pivmin) : (x >= hi ? (int)N : 0);
+    const unsigned above = __ballot_sync(0xffffffffu, c > k);
+    if (lane == 0) s_above[warp] = above;
+    __syncthreads();
+    int jfirst = -1;                                               // first point with more than k eigenvalues below it
+#pragma unroll
+    for (int q = 0; q < BS_THREADS / 32; ++q)
+      if (jfirst < 0 && s_above[q] != 0u) jfirst = q * 32 + __ffs(s_above[q]) - 1;
+    double nlo, nhi;
+    if (jfirst < 0) {
+      nlo = lo + (double)BS_THREADS * w;
+      nhi = hi;
+    } else {
+      nhi = lo + (double)(jfirst + 1) * w;
+      nlo = (jfirst > 0) ? lo + (double)jfirst * w : lo;
+    }
+    nlo = fmin(fmax(nlo, lo), hi);
+    nhi = fmax(fmin(nhi, hi), nlo);
+    __syncthreads();                                               // s_above / s_any are rewritten in the next sweep
+    if (nlo == lo && nhi == hi) break;                             // no progress: the bracket is at rounding level
+    lo = nlo;
+    hi = nhi;
+  }
+  if (tid == 0) lam[k] = 0.5 * (lo + hi);
 }
 
 // Inverse iteration for the nm largest eigenvalues.  CTA j owns vector j (eigenvalue lam[N-1-j]): LU of T - lambda I
@@ -393,7 +449,11 @@ int launch_tridiag_bisect(const double* d, const double* e2, const double* bound
 int launch_tridiag_multisect(const double* d, const double* e2, const double* bounds, long N, long k_first, double* lam,
                              cudaStream_t st) {
   if (k_first >= N) return 0;
-  tridiag_sect_kernel<32><<<(unsigned)ceil_div((N - k_first) * 32, 64L), 64, 0, st>>>(d, e2, bounds, N, k_first, N, lam);
+  static const bool warp_version = getenv("PODSDF_EIG_MULTISECT_WARP") != nullptr;      // A/B: one warp per eigenvalue
+  if (warp_version)
+    tridiag_sect_kernel<32><<<(unsigned)ceil_div((N - k_first) * 32, 64L), 64, 0, st>>>(d, e2, bounds, N, k_first, N, lam);
+  else
+    tridiag_sect_block_kernel<<<(unsigned)(N - k_first), BS_THREADS, 0, st>>>(d, e2, bounds, N, k_first, N, lam);
   count_launch();
   PODSDF_CUDA(cudaGetLastError());
   return 0;
