@@ -312,7 +312,7 @@ def run_cfg1(args, pkg, torch, dev, local_rank, cpu_too=True):
     wall = (time.perf_counter() - t0) / reps
     d2h = o["mean"].nbytes + o["Phi"].nbytes + 8 * ns
     out = {"workload": "cfg1 in full: 64x64x3 planes, 1000 steps, nf=10, ln=5, adapt1d + identity rotation, PODFS 20 modes, et=0.9",
-           "ours": {"wall_s": wall, "wall_each_s": each, "planes_per_s": ns / wall, "snapshots_per_s": ns / wall, "reps": reps,
+           "ours": {"wall_s": wall, "wall_each_s": each, "wall_median_s": float(np.median(each)), "planes_per_s": ns / wall, "snapshots_per_s": ns / wall, "reps": reps,
                     "api": "DfPlan + pipeline.df_to_podfs (what digitalfilters.main() runs when not verbose), results on the host",
                     "h2d_bytes": 5 * J * K * 8, "d2h_bytes": int(d2h), "modes_kept": int(len(o["c_count"])),
                     "fourier_coefficients_kept": int(np.sum(o["c_count"]))}}
